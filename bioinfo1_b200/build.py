@@ -1,0 +1,68 @@
+"""In-tree native build (no setuptools, no JIT cache): nvcc for the CUDA library, g++ for the
+C++ drop-in wrappers. Outputs land next to this file so they travel with gpurun snapshots.
+
+    libb200map.so   CUDA kernels + the C ABI of include/b200map.h          (csrc/capi.cu)
+    libteam_b200.so team::Align / team::KMER drop-in wrappers over the ABI (csrc/team_*.cpp)
+"""
+import os
+import shutil
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(HERE, "csrc")
+INCLUDE = os.path.join(ROOT, "include")
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "--use_fast_math", "-Xcompiler", "-fPIC,-O2,-Wall", "-shared", "-Xptxas", "-v",
+              "--expt-relaxed-constexpr"]
+
+
+def _nvcc():
+    for c in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", shutil.which("nvcc")):
+        if c and os.path.exists(c):
+            return c
+    raise RuntimeError("nvcc not found")
+
+
+def _newer(target, sources):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(s) > t for s in sources)
+
+
+def _run(cmd, verbose, log_path=None):
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if log_path:
+        with open(log_path, "w") as f:
+            f.write(" ".join(cmd) + "\n" + r.stdout)
+    if verbose or r.returncode != 0:
+        print(r.stdout)
+    if r.returncode != 0:
+        raise RuntimeError("build failed: " + " ".join(cmd))
+
+
+def lib_path(name="libb200map.so"):
+    return os.path.join(HERE, name)
+
+
+def build_all(verbose=False, force=False):
+    cuda_src = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh"))]
+    hdrs = [os.path.join(INCLUDE, f) for f in sorted(os.listdir(INCLUDE))]
+    out = lib_path()
+    if force or _newer(out, cuda_src + hdrs + [os.path.abspath(__file__)]):
+        _run([_nvcc()] + NVCC_FLAGS + ["-I", INCLUDE, "-o", out, os.path.join(CSRC, "capi.cu")], verbose,
+             os.path.join(HERE, "build_capi.log"))
+    cpp_src = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.startswith("team_") and f.endswith(".cpp")]
+    if cpp_src:
+        out2 = lib_path("libteam_b200.so")
+        if force or _newer(out2, cpp_src + hdrs + [out]):
+            _run(["g++", "-O2", "-std=c++17", "-Wall", "-fPIC", "-shared", "-I", INCLUDE, "-o", out2] + cpp_src +
+                 ["-L", HERE, "-lb200map", "-Wl,-rpath,$ORIGIN"], verbose)
+    return out
+
+
+if __name__ == "__main__":
+    import sys
+    build_all(verbose=True, force="--force" in sys.argv)

@@ -1,0 +1,617 @@
+// capi.cu -- host side of the C ABI declared in include/b200map.h: contexts, shape-only
+// plans (wave schedule + per-pair descriptors), kernel launches, and the host-buffer
+// convenience entry points. No CPU implementation of the hot path lives here: without a
+// usable device every entry point returns B200_E_NOGPU.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <climits>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include <cub/device/device_scan.cuh>
+#include <cub/iterator/transform_input_iterator.cuh>
+
+#include "../../include/b200map.h"
+#include "align_fill_generic.cuh"
+#include "align_walk.cuh"
+#include "common.cuh"
+#include "minimize.cuh"
+
+using namespace b200;
+
+// ------------------------------------------------------------------ errors ----
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+#define CU(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e__ = (call);                                                             \
+        if (e__ != cudaSuccess) {                                                             \
+            const int code__ = (e__ == cudaErrorMemoryAllocation) ? B200_E_NOMEM : B200_E_CUDA; \
+            return fail(code__, std::string(#call) + ": " + cudaGetErrorString(e__));         \
+        }                                                                                     \
+    } while (0)
+#define TRY(expr)                \
+    do {                         \
+        int rc__ = (expr);       \
+        if (rc__ != B200_OK) return rc__; \
+    } while (0)
+
+extern "C" const char* b200_last_error(void) { return g_err.c_str(); }
+extern "C" int b200_version(void) { return 1; }
+extern "C" int b200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+// ------------------------------------------------------------------ context ----
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return B200_OK;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            want = bytes;
+            e = cudaMalloc(&p, want);
+        }
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            p = nullptr;
+            return fail(B200_E_NOMEM, "cudaMalloc of " + std::to_string(bytes) + " bytes failed");
+        }
+        cap = want;
+        return B200_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct HostBuf {  // pinned staging
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return B200_OK;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        if (cudaMallocHost(&p, bytes + bytes / 8 + 256) != cudaSuccess) {
+            cudaGetLastError();
+            p = nullptr;
+            return fail(B200_E_NOMEM, "cudaMallocHost failed");
+        }
+        cap = bytes + bytes / 8 + 256;
+        return B200_OK;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct b200_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    // workspaces shared by every plan run on this context (one run at a time per context)
+    DevBuf dirs, bnd, counter, end_i, end_j, runs, n_runs, cigar_len, scan_tmp, flags, total;
+    // staging for the host-buffer entry points
+    DevBuf d_q, d_t, d_score, d_tb, d_cigar, d_cigar_off, d_seq, d_hash, d_pos, d_flag;
+    HostBuf h_q, h_t, h_off;
+    // options
+    int64_t dir_budget_bytes = 48ll << 30;
+    int64_t force_generic = 0;
+    int64_t chunk_pairs = 0;
+    // counters
+    int64_t kernel_launches = 0, h2d_bytes = 0, d2h_bytes = 0;
+};
+
+static int set_device(const b200_ctx* c) {
+    CU(cudaSetDevice(c->device));
+    return B200_OK;
+}
+
+extern "C" int b200_ctx_create(int device, b200_ctx** out) {
+    if (!out) return fail(B200_E_ARG, "b200_ctx_create: out is null");
+    *out = nullptr;
+    int n = b200_device_count();
+    if (n <= 0) return fail(B200_E_NOGPU, "no CUDA device visible (this library has no CPU fallback)");
+    if (device < 0 || device >= n) return fail(B200_E_ARG, "device index out of range");
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(B200_E_NOGPU, std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) +
+                                      "; kernels are built for sm_100a only");
+    b200_ctx* c = new (std::nothrow) b200_ctx();
+    if (!c) return fail(B200_E_NOMEM, "out of host memory");
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    CU(cudaSetDevice(device));
+    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess)
+        c->dir_budget_bytes = std::max<int64_t>(1ll << 30, (int64_t)(free_b / 3));
+    *out = c;
+    return B200_OK;
+}
+
+extern "C" void b200_ctx_destroy(b200_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+    for (DevBuf* b : {&c->dirs, &c->bnd, &c->counter, &c->end_i, &c->end_j, &c->runs, &c->n_runs,
+                      &c->cigar_len, &c->scan_tmp, &c->flags, &c->total, &c->d_q, &c->d_t, &c->d_score, &c->d_tb,
+                      &c->d_cigar, &c->d_cigar_off, &c->d_seq, &c->d_hash, &c->d_pos, &c->d_flag})
+        b->release();
+    for (HostBuf* b : {&c->h_q, &c->h_t, &c->h_off}) b->release();
+    delete c;
+}
+
+extern "C" int b200_ctx_set_option(b200_ctx* c, const char* key, int64_t value) {
+    if (!c || !key) return fail(B200_E_ARG, "null argument");
+    const std::string k(key);
+    if (k == "dir_budget_bytes") c->dir_budget_bytes = std::max<int64_t>(value, 1 << 20);
+    else if (k == "force_generic") c->force_generic = value;
+    else if (k == "chunk_pairs") c->chunk_pairs = value;
+    else return fail(B200_E_ARG, "unknown option " + k);
+    return B200_OK;
+}
+
+extern "C" int64_t b200_ctx_get_counter(b200_ctx* c, const char* key) {
+    if (!c || !key) return -1;
+    const std::string k(key);
+    if (k == "kernel_launches") return c->kernel_launches;
+    if (k == "h2d_bytes") return c->h2d_bytes;
+    if (k == "d2h_bytes") return c->d2h_bytes;
+    return -1;
+}
+
+// per-thread default contexts for the reference-shaped entry points
+static int default_ctx(int device, b200_ctx** out) {
+    struct Holder {
+        std::vector<b200_ctx*> v;
+        ~Holder() { for (auto* c : v) b200_ctx_destroy(c); }
+    };
+    static thread_local Holder h;
+    if (device < 0) return fail(B200_E_ARG, "negative device index");
+    if ((size_t)device >= h.v.size()) h.v.resize(device + 1, nullptr);
+    if (!h.v[device]) TRY(b200_ctx_create(device, &h.v[device]));
+    *out = h.v[device];
+    return B200_OK;
+}
+
+// ------------------------------------------------------------------ align plan ----
+struct Wave {
+    uint32_t first, count;  // range in the work order
+    uint64_t dir_words;
+};
+
+struct b200_align_plan {
+    b200_ctx* ctx = nullptr;
+    size_t n = 0;
+    int type = 0;
+    Scores sc{};
+    bool want_cigar = false;
+    uint64_t cells = 0, cigar_bound = 0, run_slots = 0;
+    uint32_t max_T = 0;
+    std::vector<Wave> waves;
+    DevBuf d_pairs, d_work;
+};
+
+extern "C" void b200_align_plan_destroy(b200_align_plan* p) {
+    if (!p) return;
+    cudaSetDevice(p->ctx->device);
+    p->d_pairs.release();
+    p->d_work.release();
+    delete p;
+}
+extern "C" uint64_t b200_align_plan_cells(const b200_align_plan* p) { return p ? p->cells : 0; }
+extern "C" uint64_t b200_align_plan_cigar_bound(const b200_align_plan* p) { return p ? p->cigar_bound : 0; }
+
+extern "C" int b200_align_plan_create(b200_ctx* ctx, size_t n, const uint64_t* q_off, const uint64_t* t_off,
+                                      int type, int match, int mismatch, int gap, int want_cigar,
+                                      b200_align_plan** out) {
+    if (!ctx || !out || (n && (!q_off || !t_off))) return fail(B200_E_ARG, "b200_align_plan_create: null argument");
+    *out = nullptr;
+    if (type < 0 || type > 2) return fail(B200_E_TYPE, "Unknown AlignmentType provided.");
+    if (n > 0xfffffff0ull) return fail(B200_E_ARG, "batch too large");
+    TRY(set_device(ctx));
+    b200_align_plan* p = new (std::nothrow) b200_align_plan();
+    if (!p) return fail(B200_E_NOMEM, "out of host memory");
+    p->ctx = ctx; p->n = n; p->type = type; p->sc = Scores{match, mismatch, gap};
+    p->want_cigar = want_cigar != 0;
+
+    std::vector<PairDesc> pairs(n);
+    std::vector<uint64_t> cells(n);
+    bool uniform = true;
+    for (size_t i = 0; i < n; ++i) {
+        const uint64_t ql = q_off[i + 1] - q_off[i], tl = t_off[i + 1] - t_off[i];
+        if (q_off[i + 1] < q_off[i] || t_off[i + 1] < t_off[i] || ql > 0x3fffffffull || tl > 0x3fffffffull) {
+            delete p;
+            return fail(B200_E_ARG, "offsets must be non-decreasing and sequences shorter than 2^30");
+        }
+        PairDesc& d = pairs[i];
+        d.q_off = q_off[i]; d.t_off = t_off[i];
+        d.Q = (uint32_t)ql; d.T = (uint32_t)tl;
+        d.pitch = (d.T + 3u) & ~3u;
+        d.klass = 0;
+        d.dir_off = 0;
+        d.run_off = p->run_slots;
+        p->run_slots += ql + tl + 1;
+        cells[i] = ql * tl;
+        p->cells += cells[i];
+        p->cigar_bound += std::max<uint64_t>(2, 2 * (ql + tl));
+        p->max_T = std::max(p->max_T, d.T);
+        if (i && (d.Q != pairs[0].Q || d.T != pairs[0].T)) uniform = false;
+    }
+    // work order: largest first so the dynamic scheduler's tail is made of small pairs
+    std::vector<uint32_t> order(n);
+    std::iota(order.begin(), order.end(), 0u);
+    if (!uniform)
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return cells[a] > cells[b]; });
+    // waves: consecutive slices of the order whose direction matrices fit the HBM budget
+    const uint64_t budget_words = (uint64_t)ctx->dir_budget_bytes / 4;
+    Wave cur{0, 0, 0};
+    for (uint32_t k = 0; k < n; ++k) {
+        PairDesc& d = pairs[order[k]];
+        const uint64_t words = p->want_cigar ? (uint64_t)div_up(d.Q, kRowsPerWord) * d.pitch : 0;
+        if (cur.count && cur.dir_words + words > budget_words) {
+            p->waves.push_back(cur);
+            cur = Wave{k, 0, 0};
+        }
+        d.dir_off = cur.dir_words;
+        cur.dir_words += words;
+        ++cur.count;
+    }
+    if (cur.count) p->waves.push_back(cur);
+
+    int rc = p->d_pairs.ensure(std::max<size_t>(1, n) * sizeof(PairDesc));
+    if (rc == B200_OK) rc = p->d_work.ensure(std::max<size_t>(1, n) * sizeof(uint32_t));
+    if (rc == B200_OK && n) {
+        cudaError_t e = cudaMemcpyAsync(p->d_pairs.p, pairs.data(), n * sizeof(PairDesc), cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(p->d_work.p, order.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) rc = fail(B200_E_CUDA, std::string("plan upload: ") + cudaGetErrorString(e));
+        ctx->h2d_bytes += n * (sizeof(PairDesc) + sizeof(uint32_t));
+    }
+    if (rc != B200_OK) { b200_align_plan_destroy(p); return rc; }
+    *out = p;
+    return B200_OK;
+}
+
+struct U32ToU64 {
+    __host__ __device__ uint64_t operator()(const uint32_t& v) const { return (uint64_t)v; }
+};
+
+template <int TYPE>
+static void launch_fill_generic(b200_align_plan* p, const Wave& wv, const uint8_t* d_q, const uint8_t* d_t,
+                                uint32_t* d_dirs, int32_t* d_score, int n_blocks, cudaStream_t st) {
+    b200_ctx* c = p->ctx;
+    fill_generic_kernel<TYPE><<<n_blocks, 128, 0, st>>>(
+        d_q, d_t, p->d_pairs.as<PairDesc>(), p->d_work.as<uint32_t>() + wv.first, wv.count,
+        c->counter.as<uint32_t>(), c->flags.as<uint8_t>(), (uint8_t)0, (uint8_t)0, p->sc, d_dirs,
+        c->bnd.as<int32_t>(), p->max_T + 8, d_score, c->end_i.as<uint32_t>(),
+        c->end_j.as<uint32_t>());
+    c->kernel_launches++;
+}
+
+extern "C" int b200_align_plan_run(b200_align_plan* p, const char* d_q_buf, const char* d_t_buf,
+                                   int32_t* d_score, uint32_t* d_target_begin, char* d_cigar,
+                                   uint64_t* d_cigar_off, uint64_t cigar_cap, void* stream) {
+    if (!p) return fail(B200_E_ARG, "null plan");
+    b200_ctx* c = p->ctx;
+    const size_t n = p->n;
+    if (p->want_cigar && (!d_cigar_off || (!d_cigar && cigar_cap))) return fail(B200_E_ARG, "plan wants CIGARs but no buffers given");
+    if (!d_score) return fail(B200_E_ARG, "d_score is null");
+    TRY(set_device(c));
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    if (n == 0) {
+        if (d_cigar_off) CU(cudaMemsetAsync(d_cigar_off, 0, sizeof(uint64_t), st));
+        return B200_OK;
+    }
+    const uint8_t* dq = reinterpret_cast<const uint8_t*>(d_q_buf);
+    const uint8_t* dt = reinterpret_cast<const uint8_t*>(d_t_buf);
+
+    // persistent grid: 4 warps per CTA, enough CTAs to fill every SM
+    const int n_blocks = (int)std::min<uint64_t>((uint64_t)c->sm_count * 8, div_up64(n, 4));
+    const uint64_t n_warps = (uint64_t)n_blocks * 4;
+    uint64_t max_dir_words = 0;
+    for (const Wave& w : p->waves) max_dir_words = std::max(max_dir_words, w.dir_words);
+    TRY(c->counter.ensure(64));
+    TRY(c->flags.ensure(n));
+    TRY(c->bnd.ensure(n_warps * (size_t)(p->max_T + 8) * sizeof(int32_t)));
+    TRY(c->end_i.ensure(n * 4));
+    TRY(c->end_j.ensure(n * 4));
+    if (p->want_cigar) {
+        TRY(c->dirs.ensure(std::max<uint64_t>(max_dir_words, 4) * 4));
+        TRY(c->runs.ensure(p->run_slots * 4));
+        TRY(c->n_runs.ensure(n * 4));
+        TRY(c->cigar_len.ensure(n * 4));
+        TRY(c->total.ensure(8));
+    }
+
+    classify_kernel<<<(unsigned)div_up64(n * 32, 256), 256, 0, st>>>(dq, dt, p->d_pairs.as<PairDesc>(), (uint32_t)n,
+                                                                  c->flags.as<uint8_t>());
+    c->kernel_launches++;
+
+    for (const Wave& wv : p->waves) {
+        CU(cudaMemsetAsync(c->counter.p, 0, 64, st));
+        uint32_t* d_dirs = p->want_cigar ? c->dirs.as<uint32_t>() : nullptr;
+        const int nb = (int)std::min<uint64_t>((uint64_t)n_blocks, div_up64(wv.count, 4));
+        switch (p->type) {
+            case 0: launch_fill_generic<0>(p, wv, dq, dt, d_dirs, d_score, nb, st); break;
+            case 1: launch_fill_generic<1>(p, wv, dq, dt, d_dirs, d_score, nb, st); break;
+            default: launch_fill_generic<2>(p, wv, dq, dt, d_dirs, d_score, nb, st); break;
+        }
+        if (p->want_cigar) {
+            const unsigned wb = (unsigned)div_up64(wv.count, 128);
+            const uint32_t* work = p->d_work.as<uint32_t>() + wv.first;
+            switch (p->type) {
+                case 0: walk_kernel<0><<<wb, 128, 0, st>>>(p->d_pairs.as<PairDesc>(), work, wv.count, d_dirs, c->end_i.as<uint32_t>(), c->end_j.as<uint32_t>(), c->runs.as<uint32_t>(), c->n_runs.as<uint32_t>(), c->cigar_len.as<uint32_t>()); break;
+                case 1: walk_kernel<1><<<wb, 128, 0, st>>>(p->d_pairs.as<PairDesc>(), work, wv.count, d_dirs, c->end_i.as<uint32_t>(), c->end_j.as<uint32_t>(), c->runs.as<uint32_t>(), c->n_runs.as<uint32_t>(), c->cigar_len.as<uint32_t>()); break;
+                default: walk_kernel<2><<<wb, 128, 0, st>>>(p->d_pairs.as<PairDesc>(), work, wv.count, d_dirs, c->end_i.as<uint32_t>(), c->end_j.as<uint32_t>(), c->runs.as<uint32_t>(), c->n_runs.as<uint32_t>(), c->cigar_len.as<uint32_t>()); break;
+            }
+            c->kernel_launches++;
+        }
+    }
+    CU(cudaGetLastError());
+
+    if (d_target_begin) {
+        target_begin_kernel<<<(unsigned)div_up64(n, 256), 256, 0, st>>>((uint32_t)n, p->type, c->end_j.as<uint32_t>(), d_target_begin);
+        c->kernel_launches++;
+    }
+    if (p->want_cigar) {
+        cub::TransformInputIterator<uint64_t, U32ToU64, const uint32_t*> in(c->cigar_len.as<uint32_t>(), U32ToU64());
+        size_t tmp_bytes = 0;
+        CU(cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, in, d_cigar_off + 1, (int)n, st));
+        TRY(c->scan_tmp.ensure(tmp_bytes));
+        CU(cudaMemsetAsync(d_cigar_off, 0, sizeof(uint64_t), st));
+        CU(cub::DeviceScan::InclusiveSum(c->scan_tmp.p, tmp_bytes, in, d_cigar_off + 1, (int)n, st));
+        c->kernel_launches += 2;
+        uint64_t total = 0;
+        CU(cudaMemcpyAsync(&total, d_cigar_off + n, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        if (total > cigar_cap)
+            return fail(B200_E_CAP, "CIGAR buffer too small: need " + std::to_string(total) + " bytes, have " + std::to_string(cigar_cap));
+        emit_kernel<<<(unsigned)div_up64(n, 128), 128, 0, st>>>(p->d_pairs.as<PairDesc>(), (uint32_t)n, c->runs.as<uint32_t>(), c->n_runs.as<uint32_t>(), d_cigar_off, d_cigar);
+        c->kernel_launches++;
+    }
+    CU(cudaGetLastError());
+    return B200_OK;
+}
+
+// ------------------------------------------------------------------ align, host buffers ----
+extern "C" int b200_align_batch_packed(b200_ctx* c, size_t n, const char* q_buf, const uint64_t* q_off,
+                                       const char* t_buf, const uint64_t* t_off, int type, int match,
+                                       int mismatch, int gap, int32_t* score, uint32_t* target_begin,
+                                       char* cigar_buf, uint64_t* cigar_off, uint64_t cigar_cap) {
+    if (!c) return fail(B200_E_ARG, "null context");
+    if (type < 0 || type > 2) return fail(B200_E_TYPE, "Unknown AlignmentType provided.");
+    if (n && (!q_off || !t_off || !score)) return fail(B200_E_ARG, "null argument");
+    const bool want_cigar = cigar_off != nullptr;
+    if (want_cigar && !cigar_buf && cigar_cap) return fail(B200_E_ARG, "cigar_buf is null");
+    if (n == 0) { if (cigar_off) cigar_off[0] = 0; return B200_OK; }
+    TRY(set_device(c));
+    // rebase offsets so that only the referenced byte ranges are copied
+    const uint64_t q0 = q_off[0], q1 = q_off[n], t0 = t_off[0], t1 = t_off[n];
+    if (((q1 > q0) && !q_buf) || ((t1 > t0) && !t_buf)) return fail(B200_E_ARG, "null sequence buffer");
+    std::vector<uint64_t> qo(n + 1), to(n + 1);
+    for (size_t i = 0; i <= n; ++i) { qo[i] = q_off[i] - q0; to[i] = t_off[i] - t0; }
+    b200_align_plan* plan = nullptr;
+    TRY(b200_align_plan_create(c, n, qo.data(), to.data(), type, match, mismatch, gap, want_cigar ? 1 : 0, &plan));
+    struct Guard { b200_align_plan* p; ~Guard() { b200_align_plan_destroy(p); } } guard{plan};
+
+    const uint64_t dev_cigar_cap = want_cigar ? std::min<uint64_t>(plan->cigar_bound, std::max<uint64_t>(cigar_cap, 2)) : 0;
+    TRY(c->d_q.ensure(q1 - q0 + 64));
+    TRY(c->d_t.ensure(t1 - t0 + 64));
+    TRY(c->d_score.ensure(n * 4));
+    TRY(c->d_tb.ensure(n * 4));
+    if (want_cigar) { TRY(c->d_cigar.ensure(dev_cigar_cap + 16)); TRY(c->d_cigar_off.ensure((n + 1) * 8)); }
+    cudaStream_t st = c->stream;
+    if (q1 > q0) CU(cudaMemcpyAsync(c->d_q.p, q_buf + q0, q1 - q0, cudaMemcpyHostToDevice, st));
+    if (t1 > t0) CU(cudaMemcpyAsync(c->d_t.p, t_buf + t0, t1 - t0, cudaMemcpyHostToDevice, st));
+    c->h2d_bytes += (q1 - q0) + (t1 - t0);
+    TRY(b200_align_plan_run(plan, c->d_q.as<char>(), c->d_t.as<char>(), c->d_score.as<int32_t>(),
+                            c->d_tb.as<uint32_t>(), want_cigar ? c->d_cigar.as<char>() : nullptr,
+                            want_cigar ? c->d_cigar_off.as<uint64_t>() : nullptr, dev_cigar_cap, st));
+    CU(cudaMemcpyAsync(score, c->d_score.p, n * 4, cudaMemcpyDeviceToHost, st));
+    c->d2h_bytes += n * 4;
+    if (target_begin) { CU(cudaMemcpyAsync(target_begin, c->d_tb.p, n * 4, cudaMemcpyDeviceToHost, st)); c->d2h_bytes += n * 4; }
+    if (want_cigar) {
+        CU(cudaMemcpyAsync(cigar_off, c->d_cigar_off.p, (n + 1) * 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        const uint64_t total = cigar_off[n];
+        if (total > cigar_cap) return fail(B200_E_CAP, "CIGAR buffer too small: need " + std::to_string(total));
+        if (total) CU(cudaMemcpyAsync(cigar_buf, c->d_cigar.p, total, cudaMemcpyDeviceToHost, st));
+        c->d2h_bytes += (n + 1) * 8 + total;
+    }
+    CU(cudaStreamSynchronize(st));
+    return B200_OK;
+}
+
+extern "C" int b200_align_batch(int device, size_t n, const char* const* query, const uint32_t* query_len,
+                                const char* const* target, const uint32_t* target_len, int type, int match,
+                                int mismatch, int gap, int32_t* score, uint32_t* target_begin,
+                                char* cigar_buf, uint64_t* cigar_off, uint64_t cigar_cap) {
+    if (type < 0 || type > 2) return fail(B200_E_TYPE, "Unknown AlignmentType provided.");
+    if (n && (!query || !query_len || !target || !target_len || !score)) return fail(B200_E_ARG, "null argument");
+    b200_ctx* c = nullptr;
+    TRY(default_ctx(device, &c));
+    if (n == 0) { if (cigar_off) cigar_off[0] = 0; return B200_OK; }
+    TRY(set_device(c));
+    uint64_t qtot = 0, ttot = 0;
+    for (size_t i = 0; i < n; ++i) { qtot += query_len[i]; ttot += target_len[i]; }
+    TRY(c->h_q.ensure(qtot + 1));
+    TRY(c->h_t.ensure(ttot + 1));
+    TRY(c->h_off.ensure(2 * (n + 1) * sizeof(uint64_t)));
+    uint64_t* qo = c->h_off.as<uint64_t>();
+    uint64_t* to = qo + (n + 1);
+    uint64_t qa = 0, ta = 0;
+    for (size_t i = 0; i < n; ++i) {
+        if ((query_len[i] && !query[i]) || (target_len[i] && !target[i])) return fail(B200_E_ARG, "null sequence pointer");
+        qo[i] = qa; to[i] = ta;
+        if (query_len[i]) std::memcpy(c->h_q.as<char>() + qa, query[i], query_len[i]);
+        if (target_len[i]) std::memcpy(c->h_t.as<char>() + ta, target[i], target_len[i]);
+        qa += query_len[i]; ta += target_len[i];
+    }
+    qo[n] = qa; to[n] = ta;
+    return b200_align_batch_packed(c, n, c->h_q.as<char>(), qo, c->h_t.as<char>(), to, type, match, mismatch, gap,
+                                   score, target_begin, cigar_buf, cigar_off, cigar_cap);
+}
+
+// ------------------------------------------------------------------ minimizers ----
+extern "C" uint64_t b200_minimize_count(uint32_t len, uint32_t k, uint32_t w) {
+    if (len < k || w == 0) return 0;
+    const uint64_t n = (uint64_t)len - k + 1;
+    const uint64_t full = n >= w ? n - w + 1 : 0;
+    const uint64_t tail = n < (uint64_t)w - 1 ? n : (uint64_t)w - 1;
+    return (uint64_t)(w - 1) + full + tail;
+}
+
+struct b200_min_plan {
+    b200_ctx* ctx = nullptr;
+    size_t n = 0;
+    uint32_t k = 0, w = 0;
+    uint64_t tuples = 0;
+    size_t n_tiles = 0;
+    size_t smem_bytes = 0;
+    std::vector<uint64_t> out_off;
+    DevBuf d_off, d_out_off, d_fwd, d_tiles;
+};
+
+extern "C" void b200_min_plan_destroy(b200_min_plan* p) {
+    if (!p) return;
+    cudaSetDevice(p->ctx->device);
+    p->d_off.release(); p->d_out_off.release(); p->d_fwd.release(); p->d_tiles.release();
+    delete p;
+}
+extern "C" uint64_t b200_min_plan_tuples(const b200_min_plan* p) { return p ? p->tuples : 0; }
+extern "C" const uint64_t* b200_min_plan_out_off(const b200_min_plan* p) { return p ? p->out_off.data() : nullptr; }
+
+extern "C" int b200_min_plan_create(b200_ctx* ctx, size_t n, const uint64_t* off, uint32_t k, uint32_t w,
+                                    const uint8_t* is_fwd, b200_min_plan** out) {
+    if (!ctx || !out || (n && !off)) return fail(B200_E_ARG, "b200_min_plan_create: null argument");
+    *out = nullptr;
+    TRY(set_device(ctx));
+    b200_min_plan* p = new (std::nothrow) b200_min_plan();
+    if (!p) return fail(B200_E_NOMEM, "out of host memory");
+    p->ctx = ctx; p->n = n; p->k = k; p->w = w;
+    p->out_off.assign(n + 1, 0);
+    std::vector<MinTile> tiles;
+    std::vector<uint8_t> fwd(std::max<size_t>(n, 1), 1);
+    for (size_t i = 0; i < n; ++i) {
+        if (off[i + 1] < off[i] || off[i + 1] - off[i] > 0xfffffff0ull) { delete p; return fail(B200_E_ARG, "bad offsets"); }
+        const uint64_t cnt = b200_minimize_count((uint32_t)(off[i + 1] - off[i]), k, w);
+        p->out_off[i + 1] = p->out_off[i] + cnt;
+        for (uint64_t f = 0; f < cnt; f += kMinTile) tiles.push_back(MinTile{(uint32_t)i, (uint32_t)f});
+        if (is_fwd) fwd[i] = is_fwd[i] ? 1 : 0;
+    }
+    p->tuples = p->out_off[n];
+    p->n_tiles = tiles.size();
+    // shared memory: packed codes + one hash per k-mer the tile can touch
+    const uint64_t nx = (uint64_t)kMinTile + 2ull * w + 1;
+    const uint64_t nwords = (nx + k - 1 + 15) / 16 + 1;
+    p->smem_bytes = (size_t)((nwords + nx) * 4);
+    if (p->smem_bytes > 200 * 1024) { delete p; return fail(B200_E_ARG, "window/k-mer length too large for the shared-memory tile"); }
+    int rc = p->d_off.ensure((n + 1) * 8);
+    if (rc == B200_OK) rc = p->d_out_off.ensure((n + 1) * 8);
+    if (rc == B200_OK) rc = p->d_fwd.ensure(std::max<size_t>(n, 1));
+    if (rc == B200_OK) rc = p->d_tiles.ensure(std::max<size_t>(tiles.size(), 1) * sizeof(MinTile));
+    if (rc == B200_OK) {
+        cudaError_t e = cudaSuccess;
+        if (n) e = cudaMemcpyAsync(p->d_off.p, off, (n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(p->d_out_off.p, p->out_off.data(), (n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess && n) e = cudaMemcpyAsync(p->d_fwd.p, fwd.data(), n, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess && !tiles.empty()) e = cudaMemcpyAsync(p->d_tiles.p, tiles.data(), tiles.size() * sizeof(MinTile), cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) rc = fail(B200_E_CUDA, std::string("min plan upload: ") + cudaGetErrorString(e));
+    }
+    if (rc != B200_OK) { b200_min_plan_destroy(p); return rc; }
+    *out = p;
+    return B200_OK;
+}
+
+extern "C" int b200_min_plan_run(b200_min_plan* p, const char* d_buf, uint32_t* d_hash, uint32_t* d_pos,
+                                 uint8_t* d_flag, void* stream) {
+    if (!p) return fail(B200_E_ARG, "null plan");
+    if (p->n_tiles == 0) return B200_OK;
+    if (!d_buf || !d_hash || !d_pos || !d_flag) return fail(B200_E_ARG, "null device buffer");
+    b200_ctx* c = p->ctx;
+    TRY(set_device(c));
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    if (p->smem_bytes > 48 * 1024)
+        CU(cudaFuncSetAttribute(minimize_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes));
+    minimize_kernel<0><<<(unsigned)p->n_tiles, kMinThreads, p->smem_bytes, st>>>(
+        reinterpret_cast<const uint8_t*>(d_buf), p->d_off.as<uint64_t>(), p->d_out_off.as<uint64_t>(),
+        p->d_fwd.as<uint8_t>(), p->d_tiles.as<MinTile>(), p->k, p->w, d_hash, d_pos, d_flag);
+    c->kernel_launches++;
+    CU(cudaGetLastError());
+    return B200_OK;
+}
+
+extern "C" int b200_minimize_batch_packed(b200_ctx* c, size_t n, const char* buf, const uint64_t* off, uint32_t k,
+                                          uint32_t w, const uint8_t* is_fwd, uint32_t* hash, uint32_t* pos,
+                                          uint8_t* flag, uint64_t* out_off, uint64_t cap) {
+    if (!c) return fail(B200_E_ARG, "null context");
+    if (n && (!off || !out_off)) return fail(B200_E_ARG, "null argument");
+    if (n == 0) { if (out_off) out_off[0] = 0; return B200_OK; }
+    TRY(set_device(c));
+    const uint64_t b0 = off[0], b1 = off[n];
+    std::vector<uint64_t> o(n + 1);
+    for (size_t i = 0; i <= n; ++i) o[i] = off[i] - b0;
+    b200_min_plan* plan = nullptr;
+    TRY(b200_min_plan_create(c, n, o.data(), k, w, is_fwd, &plan));
+    struct Guard { b200_min_plan* p; ~Guard() { b200_min_plan_destroy(p); } } guard{plan};
+    std::memcpy(out_off, plan->out_off.data(), (n + 1) * 8);
+    const uint64_t tot = plan->tuples;
+    if (tot > cap) return fail(B200_E_CAP, "minimizer output needs " + std::to_string(tot) + " tuples");
+    if (tot == 0) return B200_OK;
+    if (!hash || !pos || !flag || !buf) return fail(B200_E_ARG, "null buffer");
+    TRY(c->d_seq.ensure(b1 - b0 + 64));
+    TRY(c->d_hash.ensure(tot * 4));
+    TRY(c->d_pos.ensure(tot * 4));
+    TRY(c->d_flag.ensure(tot));
+    cudaStream_t st = c->stream;
+    CU(cudaMemcpyAsync(c->d_seq.p, buf + b0, b1 - b0, cudaMemcpyHostToDevice, st));
+    c->h2d_bytes += b1 - b0;
+    TRY(b200_min_plan_run(plan, c->d_seq.as<char>(), c->d_hash.as<uint32_t>(), c->d_pos.as<uint32_t>(), c->d_flag.as<uint8_t>(), st));
+    CU(cudaMemcpyAsync(hash, c->d_hash.p, tot * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(pos, c->d_pos.p, tot * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(flag, c->d_flag.p, tot, cudaMemcpyDeviceToHost, st));
+    c->d2h_bytes += tot * 9;
+    CU(cudaStreamSynchronize(st));
+    return B200_OK;
+}
+
+extern "C" int b200_minimize_batch(int device, size_t n, const char* const* seq, const uint32_t* len, uint32_t k,
+                                   uint32_t w, const uint8_t* is_fwd, uint32_t* hash, uint32_t* pos, uint8_t* flag,
+                                   uint64_t* out_off, uint64_t cap) {
+    if (n && (!seq || !len || !out_off)) return fail(B200_E_ARG, "null argument");
+    b200_ctx* c = nullptr;
+    TRY(default_ctx(device, &c));
+    if (n == 0) { if (out_off) out_off[0] = 0; return B200_OK; }
+    uint64_t tot = 0;
+    for (size_t i = 0; i < n; ++i) tot += len[i];
+    TRY(c->h_q.ensure(tot + 1));
+    TRY(c->h_off.ensure((n + 1) * 8));
+    uint64_t* o = c->h_off.as<uint64_t>();
+    uint64_t a = 0;
+    for (size_t i = 0; i < n; ++i) {
+        if (len[i] && !seq[i]) return fail(B200_E_ARG, "null sequence pointer");
+        o[i] = a;
+        if (len[i]) std::memcpy(c->h_q.as<char>() + a, seq[i], len[i]);
+        a += len[i];
+    }
+    o[n] = a;
+    return b200_minimize_batch_packed(c, n, c->h_q.as<char>(), o, k, w, is_fwd, hash, pos, flag, out_off, cap);
+}

@@ -1,0 +1,39 @@
+// common.cuh -- shared device/host definitions for the B200 alignment + minimizer kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b200 {
+
+constexpr int kWarp = 32;
+constexpr unsigned kFull = 0xffffffffu;
+
+// Direction matrix layout (HBM), shared by every fill kernel and the walker:
+//   one 32-bit word holds the 2-bit codes of kRowsPerWord consecutive rows at one column;
+//   word(rowblock rb, column j) = dirs[dir_off + rb * pitch + (j-1)], pitch = roundup4(T).
+//   code: 0 diagonal ('M'), 1 left ('I', consumes target), 2 up ('D', consumes query),
+//         3 stop (local only: cell score == 0, reference team_alignment.cpp:202).
+constexpr int kRowsPerWord = 16;
+
+struct PairDesc {
+    uint64_t q_off;    // byte offset of the query in the query buffer
+    uint64_t t_off;    // byte offset of the target in the target buffer
+    uint64_t dir_off;  // word offset of this pair's direction matrix inside the wave buffer
+    uint64_t run_off;  // element offset of this pair's run slots inside the run scratch
+    uint32_t Q, T;
+    uint32_t pitch;    // words per row block
+    uint32_t klass;    // kernel class chosen at plan time (see capi.cu)
+};
+static_assert(sizeof(PairDesc) == 48, "PairDesc layout");
+
+constexpr uint8_t kFlagDash = 1;     // pair contains a '-' byte (free gap, team_alignment.cpp:25-28)
+constexpr uint8_t kFlagNonACGT = 2;  // pair contains a byte outside "ACGT"
+
+struct Scores {
+    int match, mismatch, gap;
+};
+
+__host__ __device__ inline uint32_t div_up(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
+__host__ __device__ inline uint64_t div_up64(uint64_t a, uint64_t b) { return (a + b - 1) / b; }
+
+}  // namespace b200

@@ -1,0 +1,138 @@
+/* include/b200map.h -- the drop-in boundary: a plain C ABI over the B200 (sm_100a) kernels.
+ *
+ * Everything the reference's hot path does on the CPU is reachable through these entry
+ * points; there is no CPU fallback behind them (a missing GPU is an error code, never a
+ * silent slow path).
+ *
+ * What each entry point replaces in the reference (AnamarijaKic/bioinfo1):
+ *   b200_align_*      n x team::Align(query, query_len, target, target_len, type, match,
+ *                     mismatch, gap, cigar*, target_begin*)
+ *                       decl  team_alignment/team_alignment.hpp:14-23
+ *                       impl  team_alignment/team_alignment.cpp:49-350
+ *                       calls team_mapper.cpp:666-678 and :755-767 (one per mapped read)
+ *   b200_minimize_*   n x team::KMER(is_fwd).Minimize(sequence, len, kmer_len, window_len)
+ *                       decl  team_minimizers/team_minimizers.hpp:20-23
+ *                       impl  team_minimizers/team_minimizers.cpp:122-225
+ *                       calls team_mapper.cpp:417-427 (index), :606 and :713 (per read)
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no STL, no exceptions, no globals cross this line;
+ *   - every function returns B200_OK (0) or a negative B200_E_* code, with a thread-local
+ *     message available from b200_last_error();
+ *   - "packed" = all sequences concatenated in one byte buffer `buf` with an offsets array
+ *     `off` of n+1 entries (sequence i is buf[off[i] .. off[i+1]));
+ *   - CIGAR bytes may contain NUL (the reference's empty-path CIGAR is the 2-byte string
+ *     "1\0", team_alignment.cpp:145-159): lengths always come from `cigar_off`, never strlen;
+ *   - AlignmentType values are the reference enum's (team_alignment.hpp:8-12).
+ */
+#ifndef B200MAP_H
+#define B200MAP_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+    B200_OK = 0,
+    B200_E_TYPE = -1,  /* unknown AlignmentType (reference: std::invalid_argument, team_alignment.cpp:73) */
+    B200_E_NOMEM = -2, /* host or device allocation failed */
+    B200_E_CUDA = -3,  /* CUDA runtime error (message has the detail) */
+    B200_E_CAP = -4,   /* an output buffer is too small; nothing partial is reported as success */
+    B200_E_ARG = -5,   /* null/inconsistent argument */
+    B200_E_NOGPU = -6  /* no usable sm_100 device */
+};
+
+enum { B200_GLOBAL = 0, B200_LOCAL = 1, B200_SEMIGLOBAL = 2 };
+
+typedef struct b200_ctx b200_ctx;               /* one per (host thread, device): streams + workspaces */
+typedef struct b200_align_plan b200_align_plan; /* shape-only schedule of one alignment batch */
+typedef struct b200_min_plan b200_min_plan;     /* shape-only schedule of one minimizer batch */
+
+const char* b200_last_error(void);
+int b200_device_count(void);
+int b200_version(void); /* ABI version, currently 1 */
+
+int b200_ctx_create(int device, b200_ctx** out);
+void b200_ctx_destroy(b200_ctx* ctx);
+/* Tunables (all optional): "dir_budget_bytes" (HBM given to 2-bit direction storage per wave),
+ * "force_generic" (1 = route every pair through the int32 byte-compare kernel),
+ * "chunk_pairs" (host-API pipeline chunk). Returns B200_E_ARG for an unknown key. */
+int b200_ctx_set_option(b200_ctx* ctx, const char* key, int64_t value);
+/* Counters since the context was created: "kernel_launches", "h2d_bytes", "d2h_bytes". */
+int64_t b200_ctx_get_counter(b200_ctx* ctx, const char* key);
+
+/* ------------------------------------------------------------------ alignment ---- */
+
+/* Reference-shaped batch: arrays of n independent Align() argument tuples sharing type and
+ * scores. `target_begin`, `cigar_buf`/`cigar_off` may be NULL (score only, like passing
+ * nullptr to the reference). `cigar_off` has n+1 entries. Uses (and lazily creates) a
+ * per-thread default context for `device`. */
+int b200_align_batch(int device, size_t n,
+                     const char* const* query, const uint32_t* query_len,
+                     const char* const* target, const uint32_t* target_len,
+                     int type, int match, int mismatch, int gap,
+                     int32_t* score, uint32_t* target_begin,
+                     char* cigar_buf, uint64_t* cigar_off, uint64_t cigar_cap);
+
+/* Same, with packed HOST buffers (pinned or pageable). Work is pipelined in chunks so that
+ * the host->device copy of chunk c+1 overlaps the kernels of chunk c. */
+int b200_align_batch_packed(b200_ctx* ctx, size_t n,
+                            const char* q_buf, const uint64_t* q_off,
+                            const char* t_buf, const uint64_t* t_off,
+                            int type, int match, int mismatch, int gap,
+                            int32_t* score, uint32_t* target_begin,
+                            char* cigar_buf, uint64_t* cigar_off, uint64_t cigar_cap);
+
+/* Device-resident path. The plan is built from lengths only (host offsets), owns the
+ * per-pair descriptors and the wave schedule, and can be run any number of times on
+ * sequences already in HBM. All `d_*` pointers are device memory; `stream` is a
+ * cudaStream_t (NULL = the context's own stream). `d_target_begin`, `d_cigar`,
+ * `d_cigar_off` may be NULL when the plan was created with want_cigar = 0.
+ * On return the work is enqueued and, if want_cigar, the total CIGAR byte count has been
+ * checked against cigar_cap (that check synchronises `stream` once). */
+int b200_align_plan_create(b200_ctx* ctx, size_t n, const uint64_t* q_off, const uint64_t* t_off,
+                           int type, int match, int mismatch, int gap, int want_cigar,
+                           b200_align_plan** out);
+void b200_align_plan_destroy(b200_align_plan* plan);
+uint64_t b200_align_plan_cells(const b200_align_plan* plan);       /* sum of Q*T */
+uint64_t b200_align_plan_cigar_bound(const b200_align_plan* plan); /* worst-case CIGAR bytes */
+int b200_align_plan_run(b200_align_plan* plan, const char* d_q_buf, const char* d_t_buf,
+                        int32_t* d_score, uint32_t* d_target_begin,
+                        char* d_cigar, uint64_t* d_cigar_off, uint64_t cigar_cap, void* stream);
+
+/* ------------------------------------------------------------------ minimizers ---- */
+
+/* Number of tuples Minimize() returns for a sequence of length len
+ * (team_minimizers.cpp:140-222): 0 if len < k or w == 0, else
+ * (w-1) + max(0, n-w+1) + min(w-1, n) with n = len-k+1. */
+uint64_t b200_minimize_count(uint32_t len, uint32_t k, uint32_t w);
+
+/* Reference-shaped batch: n x KMER(is_fwd[i]).Minimize(seq[i], len[i], k, w). Outputs are
+ * structure-of-arrays, tuple i of sequence s at index out_off[s] + i. `out_off` (n+1
+ * entries) is written by the call; `cap` is the capacity of hash/pos/flag in tuples.
+ * Bytes past a sequence's end count as code 0 (what the reference reads from a NUL-padded
+ * buffer when len < k+w-2, team_minimizers.cpp:146-152). */
+int b200_minimize_batch(int device, size_t n, const char* const* seq, const uint32_t* len,
+                        uint32_t k, uint32_t w, const uint8_t* is_fwd,
+                        uint32_t* hash, uint32_t* pos, uint8_t* flag, uint64_t* out_off, uint64_t cap);
+
+int b200_minimize_batch_packed(b200_ctx* ctx, size_t n, const char* buf, const uint64_t* off,
+                               uint32_t k, uint32_t w, const uint8_t* is_fwd,
+                               uint32_t* hash, uint32_t* pos, uint8_t* flag, uint64_t* out_off,
+                               uint64_t cap);
+
+int b200_min_plan_create(b200_ctx* ctx, size_t n, const uint64_t* off, uint32_t k, uint32_t w,
+                         const uint8_t* is_fwd, b200_min_plan** out);
+void b200_min_plan_destroy(b200_min_plan* plan);
+uint64_t b200_min_plan_tuples(const b200_min_plan* plan);       /* total tuples = out_off[n] */
+const uint64_t* b200_min_plan_out_off(const b200_min_plan* plan); /* host array, n+1 entries */
+int b200_min_plan_run(b200_min_plan* plan, const char* d_buf, uint32_t* d_hash, uint32_t* d_pos,
+                      uint8_t* d_flag, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200MAP_H */

@@ -1,0 +1,71 @@
+// oracle/ref_shim.cpp -- TEST INFRASTRUCTURE ONLY (never linked into the product).
+//
+// A C-ABI veneer over the *unmodified* reference translation units
+//   /root/reference/team_alignment/team_alignment.cpp   (team::Align,          :49-350)
+//   /root/reference/team_minimizers/team_minimizers.cpp (team::KMER::Minimize, :122-225)
+// so that Python (ctypes) and bench.py can drive the reference's own CPU code.
+// The reference sources are compiled where they lie (see oracle/Makefile); only
+// the resulting shared object lands in oracle/_ref/ (git-ignored).
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <tuple>
+#include <vector>
+#include <exception>
+
+#include "team_alignment.hpp"
+#include "team_minimizers.hpp"
+
+extern "C" {
+
+// Returns 0 on success, -1 if the reference threw. *cigar_len receives the
+// full byte length (CIGARs may contain a NUL: the "1\0" empty-path case).
+int ref_align(const char* q, uint32_t ql, const char* t, uint32_t tl, int type,
+              int match, int mismatch, int gap, int want_cigar,
+              int32_t* score, uint32_t* target_begin,
+              char* cigar_buf, uint64_t cigar_cap, uint64_t* cigar_len) {
+    try {
+        std::string cg;
+        unsigned int tb = 0xdeadbeefu;
+        int s = team::Align(q, ql, t, tl, static_cast<team::AlignmentType>(type), match, mismatch,
+                            gap, want_cigar ? &cg : nullptr, &tb);
+        *score = s;
+        *target_begin = tb;
+        if (cigar_len) *cigar_len = cg.size();
+        if (want_cigar && cigar_buf) {
+            if (cg.size() > cigar_cap) return -2;
+            std::memcpy(cigar_buf, cg.data(), cg.size());
+        }
+        return 0;
+    } catch (const std::exception&) {
+        return -1;
+    }
+}
+
+// Two-call protocol: call with cap = 0 to learn the tuple count, then again with
+// buffers. `seq` must stay readable for the few bytes past `len` that the
+// reference touches when len < k + w - 2: callers pass a
+// zero-padded buffer.
+int64_t ref_minimize(const char* seq, uint32_t len, uint32_t k, uint32_t w, int is_fwd,
+                     uint32_t* hash, uint32_t* pos, uint8_t* flag, uint64_t cap) {
+    team::KMER km(is_fwd != 0);
+    auto v = km.Minimize(seq, len, k, w);
+    if (cap >= v.size()) {
+        for (size_t i = 0; i < v.size(); ++i) {
+            hash[i] = std::get<0>(v[i]);
+            pos[i] = std::get<1>(v[i]);
+            flag[i] = std::get<2>(v[i]) ? 1 : 0;
+        }
+    }
+    return static_cast<int64_t>(v.size());
+}
+
+// Side state after the last ref_minimize (process-global in the reference,
+// team_minimizers.cpp:19-22): number of distinct tuples and of distinct hashes.
+void ref_minimize_side_state(uint64_t* n_unique_tuples, uint64_t* n_distinct_hashes) {
+    team::KMER km(true);
+    *n_unique_tuples = km.GetUniqueMinimizers().size();
+    *n_distinct_hashes = km.GetMinimizerFrequencies().size();
+}
+
+}  // extern "C"

@@ -1,0 +1,67 @@
+"""ctypes bindings for the two CPU checkers (test infrastructure only).
+
+* ``oracle``  -- oracle/liboracle.so, our C restatement (always present after build()).
+* ``ref``     -- oracle/_ref/libref.so, the unmodified reference translation units behind
+                 oracle/ref_shim.cpp (present when built in the authoring container; it
+                 travels to the GPU box as a prebuilt file).
+
+Both expose the same call shapes so tests can be parametrised over them.
+"""
+import ctypes as C
+import os
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GLOBAL, LOCAL, SEMI = 0, 1, 2
+TYPE_NAMES = {GLOBAL: "global", LOCAL: "local", SEMI: "semiGlobal"}
+
+
+class _Checker:
+    def __init__(self, path, prefix):
+        self.path = path
+        self.lib = C.CDLL(path)
+        self._align = getattr(self.lib, prefix + "_align")
+        self._align.restype = C.c_int
+        self._align.argtypes = [C.c_char_p, C.c_uint32, C.c_char_p, C.c_uint32, C.c_int, C.c_int, C.c_int,
+                                C.c_int, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_uint32), C.c_char_p,
+                                C.c_uint64, C.POINTER(C.c_uint64)]
+        self._minimize = getattr(self.lib, prefix + "_minimize")
+        self._minimize.restype = C.c_int64
+        self._minimize.argtypes = [C.c_char_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_uint64]
+
+    def align(self, q: bytes, t: bytes, typ: int, match=1, mismatch=-1, gap=-1, want_cigar=True):
+        """-> (score, target_begin, cigar_bytes | None)"""
+        score = C.c_int32(0)
+        tb = C.c_uint32(0)
+        cap = 8 * (len(q) + len(t)) + 16
+        buf = C.create_string_buffer(cap)
+        clen = C.c_uint64(0)
+        rc = self._align(q, len(q), t, len(t), typ, match, mismatch, gap, 1 if want_cigar else 0,
+                         C.byref(score), C.byref(tb), buf, cap, C.byref(clen))
+        if rc != 0:
+            raise ValueError(f"align rc={rc}")
+        return score.value, tb.value, (buf.raw[:clen.value] if want_cigar else None)
+
+    def minimize(self, seq: bytes, k: int, w: int, is_fwd=True):
+        """-> list of (hash, pos, flag)"""
+        import numpy as np
+        padded = seq + b"\0" * (k + w + 8)
+        n = self._minimize(padded, len(seq), k, w, 1 if is_fwd else 0, None, None, None, 0)
+        if n < 0:
+            raise ValueError(f"minimize rc={n}")
+        h = np.empty(max(n, 1), dtype=np.uint32)
+        p = np.empty(max(n, 1), dtype=np.uint32)
+        f = np.empty(max(n, 1), dtype=np.uint8)
+        n2 = self._minimize(padded, len(seq), k, w, 1 if is_fwd else 0, h.ctypes.data, p.ctypes.data,
+                            f.ctypes.data, n)
+        assert n2 == n
+        return h[:n], p[:n], f[:n]
+
+
+def load_oracle():
+    return _Checker(os.path.join(ROOT, "oracle", "liboracle.so"), "oracle")
+
+
+def load_ref():
+    p = os.path.join(ROOT, "oracle", "_ref", "libref.so")
+    return _Checker(p, "ref") if os.path.exists(p) else None

@@ -1,0 +1,65 @@
+"""No-GPU checks of the boundary: the C-ABI library loads, exports every symbol that
+include/b200map.h declares, and refuses to compute without a device (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from bioinfo1_b200 import build, capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "b200map.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(b200_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = ctypes.CDLL(build.lib_path())
+    syms = _declared_symbols()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/b200map.h but not exported"
+
+
+def test_version_and_count_formula():
+    L = capi.lib()
+    assert L.b200_version() == 1
+    # (w-1) + max(0, n-w+1) + min(w-1, n), n = len-k+1  (team_minimizers.cpp:140-222)
+    assert L.b200_minimize_count(4_600_000, 15, 5) == 4_599_990
+    assert L.b200_minimize_count(15, 3, 3) == 15
+    assert L.b200_minimize_count(3, 3, 3) == 3
+    assert L.b200_minimize_count(2, 3, 3) == 0
+    assert L.b200_minimize_count(9, 3, 0) == 0
+    assert L.b200_minimize_count(9, 3, 1) == 7
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(capi.B200Error) as e:
+        capi.Context(0)
+    assert e.value.code == capi.E_NOGPU
+    with pytest.raises(capi.B200Error) as e:
+        capi.align_batch_pointers(0, [b"ACGT"], [b"ACGT"], capi.GLOBAL)
+    assert e.value.code == capi.E_NOGPU
+
+
+def test_unknown_alignment_type_is_rejected_before_any_device_work():
+    with pytest.raises(capi.B200Error) as e:
+        capi.align_batch_pointers(0, [b"ACGT"], [b"ACGT"], 7)
+    assert e.value.code == capi.E_TYPE
+
+
+def test_product_does_not_reference_the_oracle():
+    bad = []
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "bioinfo1_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp")) and f != "smoke.py":
+                if re.search(r"oracle[/_.]|liboracle|libref", open(os.path.join(dirpath, f), errors="replace").read()):
+                    bad.append(f)
+    assert not bad, bad

@@ -1,0 +1,146 @@
+"""GPU parity tests (bit-exact): every result that crosses the C ABI is compared with the CPU
+oracle (oracle/liboracle.so) and with the committed golden vectors from the reference."""
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+from cpu_checkers import ROOT, load_oracle, load_ref
+import seqgen
+
+pytestmark = pytest.mark.gpu
+ORACLE = load_oracle()
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from bioinfo1_b200 import capi
+    c = capi.Context(0)
+    yield c
+    c.close()
+
+
+def _check_batch(ctx, qs, ts, typ, m=1, x=-1, g=-1, checker=ORACLE):
+    got = ctx.align(qs, ts, typ, m, x, g, True)
+    got_s = ctx.align(qs, ts, typ, m, x, g, False)
+    for k, (q, t) in enumerate(zip(qs, ts)):
+        exp = checker.align(q, t, typ, m, x, g, True)
+        assert got[k] == exp, (k, typ, m, x, g, len(q), len(t), q[:40], t[:40], got[k][:2], exp[:2])
+        assert got_s[k][:2] == exp[:2]
+
+
+def test_golden_vectors_through_the_abi(ctx):
+    with open(os.path.join(ROOT, "tests", "golden", "align_golden.json")) as f:
+        cases = json.load(f)["cases"]
+    groups = {}
+    for c in cases:
+        groups.setdefault((c["type"], c["match"], c["mismatch"], c["gap"]), []).append(c)
+    n = 0
+    for (typ, m, x, g), cs in groups.items():
+        qs = [bytes.fromhex(c["q"]) for c in cs]
+        ts = [bytes.fromhex(c["t"]) for c in cs]
+        got = ctx.align(qs, ts, typ, m, x, g, True)
+        for c, r in zip(cs, got):
+            assert r == (c["score"], c["target_begin"], bytes.fromhex(c["cigar"])), (c["tag"], typ, m, x, g, c["q"], c["t"])
+            n += 1
+    assert n == len(cases)
+
+
+@pytest.mark.parametrize("typ", [0, 1, 2])
+def test_random_batches_vs_oracle(ctx, typ):
+    rng = random.Random(100 + typ)
+    for ab, (m, x, g) in ((b"ACGT", (1, -1, -1)), (b"ACGTN-", (2, -3, -2)), (b"AC", (1, -1, 1)), (b"ACGTacgt-", (0, -2, -1)),
+                          (b"ACGT", (3, 2, -4)), (b"ACGT", (-1, 1, 0))):
+        qs = [bytes(rng.choice(ab) for _ in range(rng.randint(0, 90))) for _ in range(300)]
+        ts = [bytes(rng.choice(ab) for _ in range(rng.randint(0, 90))) for _ in range(300)]
+        _check_batch(ctx, qs, ts, typ, m, x, g)
+
+
+@pytest.mark.parametrize("typ", [0, 1, 2])
+def test_related_pairs_across_tile_edges(ctx, typ):
+    rng = np.random.default_rng(7 + typ)
+    qs, ts = [], []
+    for n in (1, 15, 16, 17, 31, 32, 33, 150, 511, 512, 513, 1023, 1024, 1025, 1700):
+        t = seqgen.random_dna(rng, n)
+        q = seqgen.mutate(rng, t, sub=0.03, ins=0.05, dele=0.05)
+        qs.append(q.tobytes()); ts.append(t.tobytes())
+        qs.append(t.tobytes()); ts.append(q.tobytes())
+    _check_batch(ctx, qs, ts, typ)
+    _check_batch(ctx, qs, ts, typ, 2, -3, -2)
+
+
+@pytest.mark.parametrize("typ", [0, 1, 2])
+def test_long_pair_multi_stripe(ctx, typ):
+    qs, ts = seqgen.ont_like_pairs(11 + typ, 3, mean_len=2500, min_len=1800, max_len=3200)
+    qs = [q.tobytes() for q in qs] + [b"A" * 700, b"ACGT" * 300]
+    ts = [t.tobytes() for t in ts] + [b"ACGT" * 400, b"A" * 900]
+    _check_batch(ctx, qs, ts, typ)
+
+
+def test_short_pair_batch_config2_shape(ctx):
+    """BASELINE config 2 at reduced count: 150 x 150 global, score + CIGAR."""
+    qb, qo, tb, to = seqgen.short_pairs(3, 4096)
+    score, tbeg, cig, coff = ctx.align_packed(qb, qo, tb, to, 0)
+    for k in range(0, 4096, 7):
+        q = qb[int(qo[k]):int(qo[k + 1])].tobytes()
+        t = tb[int(to[k]):int(to[k + 1])].tobytes()
+        exp = ORACLE.align(q, t, 0)
+        assert (int(score[k]), int(tbeg[k]), cig[int(coff[k]):int(coff[k + 1])].tobytes()) == exp
+    # size-independent property on the full batch: CIGAR op counts rebuild both lengths
+    for k in range(4096):
+        c = cig[int(coff[k]):int(coff[k + 1])].tobytes().decode()
+        num, tot = "", {"M": 0, "I": 0, "D": 0}
+        for ch in c:
+            if ch.isdigit():
+                num += ch
+            else:
+                tot[ch] += int(num); num = ""
+        assert tot["M"] + tot["D"] == 150 and tot["M"] + tot["I"] == 150
+
+
+def test_multiple_waves_give_identical_results(ctx):
+    rng = np.random.default_rng(5)
+    qs, ts = [], []
+    for _ in range(200):
+        t = seqgen.random_dna(rng, int(rng.integers(50, 400)))
+        q = seqgen.mutate(rng, t, sub=0.05, ins=0.03, dele=0.03)
+        qs.append(q.tobytes()); ts.append(t.tobytes())
+    one = ctx.align(qs, ts, 2)
+    ctx.set_option("dir_budget_bytes", 1 << 20)
+    try:
+        many = ctx.align(qs, ts, 2)
+    finally:
+        ctx.set_option("dir_budget_bytes", 8 << 30)
+    assert one == many
+
+
+def test_pointer_array_entry_point_and_errors(ctx):
+    from bioinfo1_b200 import capi
+    qs = [b"GTACC", b"", b"ACG", b"TGACGTACATGGACA"]
+    ts = [b"GATACGTTA", b"", b"", b"CGTACATGGA"]
+    got = capi.align_batch_pointers(0, qs, ts, capi.SEMIGLOBAL)
+    assert got == [ORACLE.align(q, t, 2) for q, t in zip(qs, ts)]
+    assert got[0] == (2, 0, b"5I1M1I2M2D") and got[1] == (0, 0, b"1\0")
+    # too-small CIGAR buffer is an error, not a truncated success
+    qb, qo = capi.pack(qs)
+    tb, to = capi.pack(ts)
+    with pytest.raises(capi.B200Error) as e:
+        ctx.align_packed(qb, qo, tb, to, 0, cigar_cap=3)
+    assert e.value.code == capi.E_CAP
+    with pytest.raises(capi.B200Error) as e:
+        ctx.align_packed(qb, qo, tb, to, 5)
+    assert e.value.code == capi.E_TYPE
+    assert ctx.align([], [], 0) == []
+
+
+def test_live_reference_spot_check(ctx):
+    ref = load_ref()
+    if ref is None:
+        pytest.skip("oracle/_ref/libref.so not present")
+    rng = random.Random(9)
+    qs = [bytes(rng.choice(b"ACGT-N") for _ in range(rng.randint(0, 200))) for _ in range(100)]
+    ts = [bytes(rng.choice(b"ACGT-N") for _ in range(rng.randint(0, 200))) for _ in range(100)]
+    for typ in (0, 1, 2):
+        _check_batch(ctx, qs, ts, typ, 2, -1, -2, checker=ref)
