@@ -112,9 +112,42 @@ struct b200_ctx {
     int64_t dir_budget_bytes = 48ll << 30;
     int64_t force_generic = 0;
     int64_t chunk_pairs = 0;
+    int64_t profile = 0;   // 1 = bracket kernels with CUDA events (adds a sync per run)
     // counters
     int64_t kernel_launches = 0, h2d_bytes = 0, d2h_bytes = 0;
+    // per-kind device time, filled only when profile == 1: 0 fill, 1 walk, 2 emit, 3 other
+    double kind_us[4] = {0, 0, 0, 0};
+    int64_t kind_launches[4] = {0, 0, 0, 0};
+    struct Span { int kind; cudaEvent_t a, b; };
+    std::vector<Span> spans;
+    std::vector<cudaEvent_t> event_pool;
 };
+
+// Event brackets around a kernel launch on stream `st` (no-ops unless ctx->profile).
+static void prof_begin(b200_ctx* c, cudaStream_t st, int kind) {
+    if (!c->profile) return;
+    b200_ctx::Span sp{kind, nullptr, nullptr};
+    for (cudaEvent_t* e : {&sp.a, &sp.b}) {
+        if (!c->event_pool.empty()) { *e = c->event_pool.back(); c->event_pool.pop_back(); }
+        else cudaEventCreate(e);
+    }
+    cudaEventRecord(sp.a, st);
+    c->spans.push_back(sp);
+}
+static void prof_end(b200_ctx* c, cudaStream_t st) {
+    if (!c->profile) return;
+    cudaEventRecord(c->spans.back().b, st);
+}
+static void prof_collect(b200_ctx* c, cudaStream_t st) {
+    if (!c->profile) return;
+    cudaStreamSynchronize(st);
+    for (auto& sp : c->spans) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess) { c->kind_us[sp.kind] += ms * 1e3; c->kind_launches[sp.kind]++; }
+        c->event_pool.push_back(sp.a); c->event_pool.push_back(sp.b);
+    }
+    c->spans.clear();
+}
 
 static int set_device(const b200_ctx* c) {
     CU(cudaSetDevice(c->device));
@@ -149,6 +182,8 @@ extern "C" void b200_ctx_destroy(b200_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+    for (auto& sp : c->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
+    for (auto e : c->event_pool) cudaEventDestroy(e);
     for (DevBuf* b : {&c->dirs, &c->bnd, &c->counter, &c->end_i, &c->end_j, &c->runs, &c->n_runs,
                       &c->cigar_len, &c->scan_tmp, &c->flags, &c->total, &c->d_q, &c->d_t, &c->d_score, &c->d_tb,
                       &c->d_cigar, &c->d_cigar_off, &c->d_seq, &c->d_hash, &c->d_pos, &c->d_flag})
@@ -163,6 +198,11 @@ extern "C" int b200_ctx_set_option(b200_ctx* c, const char* key, int64_t value) 
     if (k == "dir_budget_bytes") c->dir_budget_bytes = std::max<int64_t>(value, 1 << 20);
     else if (k == "force_generic") c->force_generic = value;
     else if (k == "chunk_pairs") c->chunk_pairs = value;
+    else if (k == "profile") c->profile = value;
+    else if (k == "reset_counters") {
+        c->kernel_launches = c->h2d_bytes = c->d2h_bytes = 0;
+        for (int i = 0; i < 4; ++i) { c->kind_us[i] = 0; c->kind_launches[i] = 0; }
+    }
     else return fail(B200_E_ARG, "unknown option " + k);
     return B200_OK;
 }
@@ -173,6 +213,11 @@ extern "C" int64_t b200_ctx_get_counter(b200_ctx* c, const char* key) {
     if (k == "kernel_launches") return c->kernel_launches;
     if (k == "h2d_bytes") return c->h2d_bytes;
     if (k == "d2h_bytes") return c->d2h_bytes;
+    static const char* kinds[4] = {"fill", "walk", "emit", "other"};
+    for (int i = 0; i < 4; ++i) {
+        if (k == std::string(kinds[i]) + "_ns") return (int64_t)(c->kind_us[i] * 1e3);
+        if (k == std::string(kinds[i]) + "_launches") return c->kind_launches[i];
+    }
     return -1;
 }
 
@@ -297,11 +342,13 @@ template <int TYPE>
 static void launch_fill_generic(b200_align_plan* p, const Wave& wv, const uint8_t* d_q, const uint8_t* d_t,
                                 uint32_t* d_dirs, int32_t* d_score, int n_blocks, cudaStream_t st) {
     b200_ctx* c = p->ctx;
+    prof_begin(c, st, 0);
     fill_generic_kernel<TYPE><<<n_blocks, 128, 0, st>>>(
         d_q, d_t, p->d_pairs.as<PairDesc>(), p->d_work.as<uint32_t>() + wv.first, wv.count,
         c->counter.as<uint32_t>(), c->flags.as<uint8_t>(), (uint8_t)0, (uint8_t)0, p->sc, d_dirs,
         c->bnd.as<int32_t>(), p->max_T + 8, d_score, c->end_i.as<uint32_t>(),
         c->end_j.as<uint32_t>());
+    prof_end(c, st);
     c->kernel_launches++;
 }
 
@@ -340,8 +387,10 @@ extern "C" int b200_align_plan_run(b200_align_plan* p, const char* d_q_buf, cons
         TRY(c->total.ensure(8));
     }
 
+    prof_begin(c, st, 3);
     classify_kernel<<<(unsigned)div_up64(n * 32, 256), 256, 0, st>>>(dq, dt, p->d_pairs.as<PairDesc>(), (uint32_t)n,
                                                                   c->flags.as<uint8_t>());
+    prof_end(c, st);
     c->kernel_launches++;
 
     for (const Wave& wv : p->waves) {
@@ -356,11 +405,13 @@ extern "C" int b200_align_plan_run(b200_align_plan* p, const char* d_q_buf, cons
         if (p->want_cigar) {
             const unsigned wb = (unsigned)div_up64(wv.count, 128);
             const uint32_t* work = p->d_work.as<uint32_t>() + wv.first;
+            prof_begin(c, st, 1);
             switch (p->type) {
                 case 0: walk_kernel<0><<<wb, 128, 0, st>>>(p->d_pairs.as<PairDesc>(), work, wv.count, d_dirs, c->end_i.as<uint32_t>(), c->end_j.as<uint32_t>(), c->runs.as<uint32_t>(), c->n_runs.as<uint32_t>(), c->cigar_len.as<uint32_t>()); break;
                 case 1: walk_kernel<1><<<wb, 128, 0, st>>>(p->d_pairs.as<PairDesc>(), work, wv.count, d_dirs, c->end_i.as<uint32_t>(), c->end_j.as<uint32_t>(), c->runs.as<uint32_t>(), c->n_runs.as<uint32_t>(), c->cigar_len.as<uint32_t>()); break;
                 default: walk_kernel<2><<<wb, 128, 0, st>>>(p->d_pairs.as<PairDesc>(), work, wv.count, d_dirs, c->end_i.as<uint32_t>(), c->end_j.as<uint32_t>(), c->runs.as<uint32_t>(), c->n_runs.as<uint32_t>(), c->cigar_len.as<uint32_t>()); break;
             }
+            prof_end(c, st);
             c->kernel_launches++;
         }
     }
@@ -376,17 +427,22 @@ extern "C" int b200_align_plan_run(b200_align_plan* p, const char* d_q_buf, cons
         CU(cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, in, d_cigar_off + 1, (int)n, st));
         TRY(c->scan_tmp.ensure(tmp_bytes));
         CU(cudaMemsetAsync(d_cigar_off, 0, sizeof(uint64_t), st));
+        prof_begin(c, st, 3);
         CU(cub::DeviceScan::InclusiveSum(c->scan_tmp.p, tmp_bytes, in, d_cigar_off + 1, (int)n, st));
+        prof_end(c, st);
         c->kernel_launches += 2;
         uint64_t total = 0;
         CU(cudaMemcpyAsync(&total, d_cigar_off + n, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
         if (total > cigar_cap)
             return fail(B200_E_CAP, "CIGAR buffer too small: need " + std::to_string(total) + " bytes, have " + std::to_string(cigar_cap));
+        prof_begin(c, st, 2);
         emit_kernel<<<(unsigned)div_up64(n, 128), 128, 0, st>>>(p->d_pairs.as<PairDesc>(), (uint32_t)n, c->runs.as<uint32_t>(), c->n_runs.as<uint32_t>(), d_cigar_off, d_cigar);
+        prof_end(c, st);
         c->kernel_launches++;
     }
     CU(cudaGetLastError());
+    prof_collect(c, st);
     return B200_OK;
 }
 

@@ -23,6 +23,10 @@ int oracle_align(const char* q, uint32_t ql, const char* t, uint32_t tl, int typ
                  int32_t* score, uint32_t* target_begin,
                  char* cigar_buf, uint64_t cigar_cap, uint64_t* cigar_len);
 
+int64_t oracle_align_batch(uint64_t n, const char* qbuf, const uint64_t* qoff, const char* tbuf,
+                           const uint64_t* toff, int type, int match, int mismatch, int gap, int want_cigar,
+                           int32_t* score, uint32_t* target_begin, uint64_t* cigar_bytes);
+
 /* Returns the tuple count; fills the arrays only when cap >= count.
  * Bytes at index >= len are treated as code 0 (what the reference reads from a
  * NUL-padded buffer, team_minimizers.cpp:146-152). */

@@ -159,3 +159,28 @@ done:
     free(prev); free(cur); free(lastcol); free(tr);
     return rc;
 }
+
+/* Packed batch, single thread (bench.py's CPU arm runs one call per host thread). */
+int64_t oracle_align_batch(uint64_t n, const char* qbuf, const uint64_t* qoff, const char* tbuf,
+                           const uint64_t* toff, int type, int match, int mismatch, int gap, int want_cigar,
+                           int32_t* score, uint32_t* target_begin, uint64_t* cigar_bytes) {
+    uint64_t bytes = 0, cap = 0;
+    char* buf = NULL;
+    for (uint64_t i = 0; i < n; ++i) {
+        const uint64_t ql = qoff[i + 1] - qoff[i], tl = toff[i + 1] - toff[i];
+        if (want_cigar && 2 * (ql + tl) + 16 > cap) {
+            cap = 2 * (ql + tl) + 16;
+            free(buf);
+            buf = (char*)malloc(cap);
+            if (!buf) return -3;
+        }
+        uint64_t len = 0;
+        int rc = oracle_align(qbuf + qoff[i], (uint32_t)ql, tbuf + toff[i], (uint32_t)tl, type, match, mismatch,
+                              gap, want_cigar, &score[i], &target_begin[i], buf, cap, &len);
+        if (rc) { free(buf); return rc; }
+        bytes += len;
+    }
+    free(buf);
+    if (cigar_bytes) *cigar_bytes = bytes;
+    return (int64_t)n;
+}

@@ -42,6 +42,29 @@ int ref_align(const char* q, uint32_t ql, const char* t, uint32_t tl, int type,
     }
 }
 
+// Packed batch (single thread; bench.py runs one call per host thread on disjoint slices).
+// Returns the number of pairs aligned, or -1 if the reference threw.
+int64_t ref_align_batch(uint64_t n, const char* qbuf, const uint64_t* qoff, const char* tbuf,
+                        const uint64_t* toff, int type, int match, int mismatch, int gap, int want_cigar,
+                        int32_t* score, uint32_t* target_begin, uint64_t* cigar_bytes) {
+    uint64_t bytes = 0;
+    try {
+        std::string cg;
+        for (uint64_t i = 0; i < n; ++i) {
+            unsigned int tb = 0;
+            score[i] = team::Align(qbuf + qoff[i], (unsigned)(qoff[i + 1] - qoff[i]), tbuf + toff[i],
+                                   (unsigned)(toff[i + 1] - toff[i]), static_cast<team::AlignmentType>(type),
+                                   match, mismatch, gap, want_cigar ? &cg : nullptr, &tb);
+            target_begin[i] = tb;
+            bytes += cg.size();
+        }
+    } catch (const std::exception&) {
+        return -1;
+    }
+    if (cigar_bytes) *cigar_bytes = bytes;
+    return (int64_t)n;
+}
+
 // Two-call protocol: call with cap = 0 to learn the tuple count, then again with
 // buffers. `seq` must stay readable for the few bytes past `len` that the
 // reference touches when len < k + w - 2: callers pass a

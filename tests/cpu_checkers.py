@@ -29,6 +29,26 @@ class _Checker:
         self._minimize.argtypes = [C.c_char_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_uint64]
 
+        self._align_batch = getattr(self.lib, prefix + "_align_batch")
+        self._align_batch.restype = C.c_int64
+        self._align_batch.argtypes = [C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                      C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
+        self.kind = "reference" if prefix == "ref" else "port"
+
+    def align_batch(self, qbuf, qoff, tbuf, toff, typ, match=1, mismatch=-1, gap=-1, want_cigar=True):
+        """Packed numpy buffers -> (score[], target_begin[], total cigar bytes); releases the GIL."""
+        import numpy as np
+        n = len(qoff) - 1
+        score = np.empty(max(n, 1), dtype=np.int32)
+        tb = np.empty(max(n, 1), dtype=np.uint32)
+        nbytes = C.c_uint64(0)
+        rc = self._align_batch(n, qbuf.ctypes.data, qoff.ctypes.data, tbuf.ctypes.data, toff.ctypes.data, typ, match,
+                               mismatch, gap, 1 if want_cigar else 0, score.ctypes.data, tb.ctypes.data,
+                               C.byref(nbytes))
+        if rc != n:
+            raise ValueError(f"align_batch rc={rc}")
+        return score[:n], tb[:n], nbytes.value
+
     def align(self, q: bytes, t: bytes, typ: int, match=1, mismatch=-1, gap=-1, want_cigar=True):
         """-> (score, target_begin, cigar_bytes | None)"""
         score = C.c_int32(0)

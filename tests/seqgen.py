@@ -54,15 +54,24 @@ def short_pairs(seed, n, length=150, sub=0.05, indel=0.01):
     # indels: shift the tail of a read by one base at ~indel rate (cheap but real indels)
     q2 = qbuf.reshape(n, length).copy()
     n_ev = rng.poisson(indel * length, size=n)
-    for row in np.nonzero(n_ev)[0]:
-        for _ in range(int(n_ev[row])):
-            p = int(rng.integers(0, length - 1))
-            if rng.random() < 0.5:   # deletion in the query
-                q2[row, p:-1] = q2[row, p + 1:]
-                q2[row, -1] = ACGT[rng.integers(0, 4)]
-            else:                    # insertion in the query
-                q2[row, p + 1:] = q2[row, p:-1]
-                q2[row, p] = ACGT[rng.integers(0, 4)]
+    cols = np.arange(length, dtype=np.int32)[None, :]
+    for rnd in range(int(n_ev.max()) if n else 0):
+        rows = np.nonzero(n_ev > rnd)[0]
+        for c0 in range(0, len(rows), 1 << 17):       # bounded temporaries
+            rr = rows[c0:c0 + (1 << 17)]
+            p = rng.integers(0, length - 1, size=len(rr)).astype(np.int32)[:, None]
+            is_del = rng.random(len(rr)) < 0.5
+            fill = ACGT[rng.integers(0, 4, size=len(rr))]
+            sub = q2[rr]
+            # deletion at p: everything right of p moves left, a fresh base enters at the end
+            idx_del = np.minimum(cols + (cols >= p), length - 1)
+            d = np.take_along_axis(sub, idx_del, axis=1)
+            d[:, -1] = fill
+            # insertion at p: everything from p moves right, a fresh base lands at p
+            idx_ins = cols - (cols > p)
+            i_ = np.take_along_axis(sub, idx_ins, axis=1)
+            i_[np.arange(len(rr)), p[:, 0]] = fill
+            q2[rr] = np.where(is_del[:, None], d, i_)
     off = (np.arange(n + 1, dtype=np.uint64) * np.uint64(length))
     return np.append(q2.reshape(-1), np.uint8(0)), off, np.append(tbuf, np.uint8(0)), off.copy()
 
