@@ -1,0 +1,237 @@
+// align_fill_short.cuh -- K1: the short-pair DP fill (BASELINE config 2: 1M x 150x150).
+//
+// One THREAD owns two whole pairs, one in each 16-bit half of its registers, so a warp works on
+// 64 pairs with no shuffles, no idle lanes and no wavefront fill/drain. Rows are processed in
+// blocks of 32 (registers), columns are swept left to right; the bottom row of a block is parked
+// in an L1/L2-resident scratch row and picked up by the next block.
+//
+// Arithmetic (bit-exact restatement of team_alignment.cpp:104-114, ties diagonal > left > up):
+// every candidate is carried as 4*score + tag with tag 2 = diagonal, 1 = left, 0 = up, so a plain
+// signed max implements both the maximum and the reference's tie order, and the low two bits of
+// the winner ARE the direction (stored as code = 2 - tag... see kTagToCode). Per pair of cells:
+//     S   = PRMT(tabA, tabB, sel[r])              substitution term from a per-column byte table
+//     m1  = VIADDMNMX.S16x2(diag, S, left)        max(diag + S, left)
+//     Z   = VIADDMNMX.S16x2(up, 4*gap, m1)        max(up + 4*gap, m1)
+//     Zc  = Z & 0xFFFCFFFC                        strip the tag: 4*H
+//     Lv  = VIADD.16x2(Zc, 4*gap + 1)             what the right/diagonal neighbours consume
+//     acc = acc*4 + (Z - Zc)                      2-bit direction, 8 rows per 16-bit half
+// = 4 alu-pipe + 2 fma-pipe + 1 PRMT issue slots for TWO cells.
+//
+// Eligibility (decided on the host, capi.cu): both sequences pure ACGT, |s - gap| <= 31 for
+// s in {match, mismatch}, and 4 * ((Q+T+2) * max|score| + 2) <= 32767 so nothing leaves int16.
+#pragma once
+#include "common.cuh"
+
+namespace b200 {
+
+constexpr int kShortRows = 32;       // rows per register block
+constexpr int kShortThreads = 64;    // 2 warps per CTA, every warp independent
+
+// Sequences packed 2 bits per base, 16 bases per word, base k of a word at bits [2k, 2k+1].
+// Codes: A=0 C=1 G=2 T=3. Pair p's query words start at (q_off >> 4) + p (see pack_kernel).
+__device__ __forceinline__ uint32_t acgt_code(uint32_t c) { return (c >> 1) & 3u; }  // A=0 C=1 T=2 G=3 on ASCII
+// (ASCII: A=0x41 -> 0, C=0x43 -> 1, G=0x47 -> 3, T=0x54 -> 2; any bijection works for equality.)
+
+// One warp per pair: classify (flags) and write the 2-bit packed copies.
+__global__ void __launch_bounds__(256)
+pack_kernel(const uint8_t* __restrict__ qbuf, const uint8_t* __restrict__ tbuf,
+            const PairDesc* __restrict__ pairs, uint32_t n, uint8_t* __restrict__ flags,
+            uint32_t* __restrict__ qpk, uint32_t* __restrict__ tpk, uint32_t* __restrict__ n_flagged) {
+    const uint32_t p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (p >= n) return;
+    const PairDesc pd = pairs[p];
+    bool dash = false, other = false;
+    for (int which = 0; which < 2; ++which) {
+        const uint8_t* s = which ? tbuf + pd.t_off : qbuf + pd.q_off;
+        const uint32_t len = which ? pd.T : pd.Q;
+        uint32_t* dst = (which ? tpk + (pd.t_off >> 4) : qpk + (pd.q_off >> 4)) + p;
+        const uint32_t nw = (len + 15) / 16;
+        for (uint32_t w = lane; w < nw; w += kWarp) {
+            uint32_t word = 0;
+#pragma unroll
+            for (int b = 0; b < 16; ++b) {
+                const uint32_t at = w * 16 + b;
+                const uint32_t c = at < len ? (uint32_t)s[at] : (uint32_t)'A';
+                dash |= (c == '-');
+                other |= !(c == 'A' || c == 'C' || c == 'G' || c == 'T');
+                word |= acgt_code(c) << (2 * b);
+            }
+            dst[w] = word;
+        }
+    }
+    const unsigned d = __ballot_sync(kFull, dash), o = __ballot_sync(kFull, other);
+    if (lane == 0) {
+        const uint8_t f = (d ? kFlagDash : 0) | (o ? kFlagNonACGT : 0);
+        flags[p] = f;
+        if (f && n_flagged) atomicAdd(n_flagged, 1u);
+    }
+}
+
+struct ShortGroup {   // one per 64-pair group (one warp's worth of work)
+    uint64_t dir_off;  // word offset of the group's direction block inside the wave buffer
+    uint32_t cols;     // Tg: columns per row block = max T over the group
+    uint32_t pad;
+};
+
+struct ShortConsts {
+    uint32_t tab_match;   // byte table seeds, see make_short_consts()
+    uint32_t tab_mis;
+    uint32_t g4;          // 4*gap in both halves
+    uint32_t kl;          // 4*gap + 1 in both halves
+    int gap, init;
+};
+
+__host__ __device__ inline uint32_t dup16(int v) { return ((uint32_t)(uint16_t)(int16_t)v) * 0x10001u; }
+
+__host__ inline ShortConsts make_short_consts(const Scores& sc, int type) {
+    ShortConsts k;
+    // S' = 4*(s - gap) + 1: the diagonal candidate is built from the neighbour's Lv = 4H + 4gap + 1,
+    // and must come out as 4*(H + s) + 2.
+    const int sm = 4 * (sc.match - sc.gap) + 1, sx = 4 * (sc.mismatch - sc.gap) + 1;
+    k.tab_match = (uint32_t)(uint8_t)(int8_t)sm;
+    k.tab_mis = ((uint32_t)(uint8_t)(int8_t)sx) * 0x01010101u;
+    k.g4 = dup16(4 * sc.gap);
+    k.kl = dup16(4 * sc.gap + 1);
+    k.gap = sc.gap;
+    k.init = (type == 0) ? sc.gap : 0;
+    return k;
+}
+
+// PTX prmt in its default mode: selector nibble bit 3 replicates the sign of the chosen byte,
+// which is how an int8 table entry becomes a sign-extended int16 half in one instruction.
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+    return r;
+}
+
+__device__ __forceinline__ int half_lo(uint32_t v) { return (int)(int16_t)(v & 0xffffu); }
+__device__ __forceinline__ int half_hi(uint32_t v) { return (int)(int16_t)(v >> 16); }
+
+// Direction word layout written by this kernel (read back by walk_kernel, klass kClassShort):
+//   uint4 at dirs[dir_off + ((block * Tg + (j-1)) * 32 + lane) * 4 .. +3]; word k covers rows
+//   8k..8k+7 of the block, low half = pair A, high half = pair B, row 8k in the top 2 bits of the
+//   half. Stored value is the TAG (2 diagonal, 1 left, 0 up), i.e. code = kTagToCode(tag).
+template <int TYPE>
+__global__ void __launch_bounds__(kShortThreads)
+fill_short_kernel(const uint32_t* __restrict__ qpk, const uint32_t* __restrict__ tpk,
+                  const PairDesc* __restrict__ pairs, const uint32_t* __restrict__ work, uint32_t n_work,
+                  const ShortGroup* __restrict__ groups, uint32_t* __restrict__ group_counter,
+                  const uint8_t* __restrict__ flags, ShortConsts K,
+                  uint32_t* __restrict__ dirs, uint32_t* bnd, uint32_t bnd_cols,
+                  int32_t* __restrict__ score, uint32_t* __restrict__ end_i, uint32_t* __restrict__ end_j) {
+    constexpr int R = kShortRows;
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    uint32_t* my_bnd = bnd + (size_t)warp_global * bnd_cols * kWarp + lane;   // [col][lane]
+    const uint32_t n_groups = (n_work + 63) / 64;
+    const uint32_t MASK = 0xfffcfffcu;
+
+    for (;;) {
+        uint32_t g = 0;
+        if (lane == 0) g = atomicAdd(group_counter, 1u);
+        g = __shfl_sync(kFull, g, 0);
+        if (g >= n_groups) break;
+
+        // my two pairs
+        const uint32_t wa = g * 64 + 2 * lane, wb = wa + 1;
+        uint32_t pA = 0xffffffffu, pB = 0xffffffffu;
+        uint32_t QA = 0, TA = 0, QB = 0, TB = 0;
+        const uint32_t *qwA = qpk, *twA = tpk, *qwB = qpk, *twB = tpk;
+        const uint64_t dir_off = groups[g].dir_off;
+        const uint32_t Tg = groups[g].cols;
+        if (wa < n_work) {
+            pA = work[wa];
+            const PairDesc d = pairs[pA];
+            if (flags[pA] == 0) { QA = d.Q; TA = d.T; qwA = qpk + (d.q_off >> 4) + pA; twA = tpk + (d.t_off >> 4) + pA; }
+            else pA = 0xffffffffu;   // not pure ACGT: the generic kernel owns it
+        }
+        if (wb < n_work) {
+            pB = work[wb];
+            const PairDesc d = pairs[pB];
+            if (flags[pB] == 0) { QB = d.Q; TB = d.T; qwB = qpk + (d.q_off >> 4) + pB; twB = tpk + (d.t_off >> 4) + pB; }
+            else pB = 0xffffffffu;
+        }
+        const bool liveA = QA && TA, liveB = QB && TB;   // has inner cells
+        const uint32_t Qm = max(liveA ? QA : 0u, liveB ? QB : 0u), Tm = max(liveA ? TA : 0u, liveB ? TB : 0u);
+        const uint32_t n_blocks = (Qm + R - 1) / R;
+        int resA = 0, resB = 0;
+
+        for (uint32_t b = 0; b < n_blocks; ++b) {
+            const uint32_t i0 = b * R;   // rows i0+1 .. i0+R
+            // per-row PRMT selectors: byte0 = tabA[qA], byte1 = its sign, byte2 = tabB[qB], byte3 = sign
+            uint32_t sel[R], Lv[R];
+            {
+                const uint32_t qa0 = qwA[(i0 >> 4)], qa1 = qwA[(i0 >> 4) + 1];
+                const uint32_t qb0 = qwB[(i0 >> 4)], qb1 = qwB[(i0 >> 4) + 1];
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const uint32_t ca = ((r < 16 ? qa0 : qa1) >> (2 * (r & 15))) & 3u;
+                    const uint32_t cb = ((r < 16 ? qb0 : qb1) >> (2 * (r & 15))) & 3u;
+                    sel[r] = ca | ((8u + ca) << 4) | ((4u + cb) << 8) | ((12u + cb) << 12);
+                    const int col0 = (int)((i0 + 1 + r) * (uint32_t)K.init);   // H(i,0)
+                    Lv[r] = __vadd2(dup16(4 * col0), K.kl);
+                }
+            }
+            // top boundary of this block: H(i0, j). Block 0: the border row j*init.
+            uint32_t top_prev = dup16(4 * (int)(i0 * (uint32_t)K.init));   // Zc of (i0, 0)
+            uint32_t tA = 0, tB = 0;
+            uint32_t* dcol = dirs ? dirs + dir_off + ((uint64_t)b * Tg * 32 + lane) * 4 : nullptr;
+
+            for (uint32_t j = 1; j <= Tm; ++j) {
+                if (((j - 1) & 15u) == 0) { tA = twA[(j - 1) >> 4]; tB = twB[(j - 1) >> 4]; }
+                const uint32_t cA = tA & 3u, cB = tB & 3u;
+                tA >>= 2; tB >>= 2;
+                // per-column byte tables: entry c = S'(c, target) = match at c == target code
+                const uint32_t tabA = K.tab_mis ^ ((K.tab_match ^ (K.tab_mis & 0xffu)) << (8 * cA));
+                const uint32_t tabB = K.tab_mis ^ ((K.tab_match ^ (K.tab_mis & 0xffu)) << (8 * cB));
+                uint32_t top = (b == 0) ? dup16(4 * (int)(j * (uint32_t)K.init)) : my_bnd[(size_t)j * kWarp];
+                uint32_t up = top;                       // Zc of the row above
+                uint32_t dg = __vadd2(top_prev, K.kl);   // Lv form of (i0, j-1)
+                top_prev = top;
+                uint32_t acc[4];
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const uint32_t S = prmt(tabA, tabB, sel[r]);
+                    const uint32_t m1 = __viaddmax_s16x2(dg, S, Lv[r]);
+                    uint32_t Z = __viaddmax_s16x2(up, K.g4, m1);
+                    if (TYPE == 1) Z = __vmaxs2(Z, 0x00030003u);   // local: clamp at 0, tag 3 = stop
+                    const uint32_t Zc = Z & MASK;
+                    dg = Lv[r];
+                    Lv[r] = __vadd2(Zc, K.kl);
+                    up = Zc;
+                    if ((r & 7) == 0) acc[r >> 3] = Z - Zc;
+                    else acc[r >> 3] = acc[r >> 3] * 4u + (Z - Zc);
+                }
+                if (b + 1 < n_blocks) my_bnd[(size_t)j * kWarp] = up;
+                if (dcol) *reinterpret_cast<uint4*>(dcol + (uint64_t)(j - 1) * 128) = make_uint4(acc[0], acc[1], acc[2], acc[3]);
+                // end-cell capture (global): the cell (Q, T) of either pair
+                if (TYPE == 0) {
+                    const bool hitA = liveA && j == TA && (QA - 1) / R == b;
+                    const bool hitB = liveB && j == TB && (QB - 1) / R == b;
+                    if (hitA || hitB) {
+                        const uint32_t rA = (QA - 1) % R, rB = (QB - 1) % R;
+                        uint32_t vA = Lv[0], vB = Lv[0];
+#pragma unroll
+                        for (int r = 1; r < R; ++r) { if ((uint32_t)r == rA) vA = Lv[r]; if ((uint32_t)r == rB) vB = Lv[r]; }
+                        if (hitA) resA = (half_lo(vA) - (4 * K.gap + 1)) >> 2;
+                        if (hitB) resB = (half_hi(vB) - (4 * K.gap + 1)) >> 2;
+                    }
+                }
+            }
+        }
+        if (TYPE == 0) {
+            if (pA != 0xffffffffu) {
+                score[pA] = liveA ? resA : (int)((QA + TA) * (uint32_t)K.init);
+                end_i[pA] = QA; end_j[pA] = TA;
+            }
+            if (pB != 0xffffffffu) {
+                score[pB] = liveB ? resB : (int)((QB + TB) * (uint32_t)K.init);
+                end_i[pB] = QB; end_j[pB] = TB;
+            }
+        }
+    }
+}
+
+}  // namespace b200

@@ -49,8 +49,11 @@ walk_kernel(const PairDesc* __restrict__ pairs, const uint32_t* __restrict__ wor
         else if (j == T && i < Q) push(2, Q - i);
     }
     const uint32_t* base = dirs + pd.dir_off;
-    // cache of the last direction word: an 'up' move stays in the same word 15 times out of 16
-    uint32_t cw = 0, cw_rb = 0xffffffffu, cw_j = 0xffffffffu;
+    const bool is_short = (pd.klass & 0xffu) == kClassShort;
+    const uint32_t s_lane = (pd.klass >> 8) & 31u, s_shift = ((pd.klass >> 16) & 1u) * 16u;
+    // cache of the last direction word: an 'up' move usually stays inside the same word
+    uint32_t cw = 0;
+    uint64_t cw_at = ~0ull;
     for (;;) {
         if (TYPE == 1) {
             if (i == 0 || j == 0) break;  // border score is 0
@@ -58,12 +61,20 @@ walk_kernel(const PairDesc* __restrict__ pairs, const uint32_t* __restrict__ wor
             if (i == 0) { if (j) push(1, j); break; }   // row 0: parents point left
             if (j == 0) { push(2, i); break; }          // column 0: parents point up
         }
-        const uint32_t rb = (i - 1) / kRowsPerWord, r = (i - 1) % kRowsPerWord;
-        if (rb != cw_rb || j != cw_j) {
-            cw = __ldg(base + (uint64_t)rb * pd.pitch + (j - 1));
-            cw_rb = rb; cw_j = j;
+        uint64_t at;
+        uint32_t sh;
+        if (is_short) {   // see align_fill_short.cuh
+            const uint32_t b = (i - 1) >> 5, rr = (i - 1) & 31u;
+            at = (((uint64_t)b * pd.pitch + (j - 1)) * 32 + s_lane) * 4 + (rr >> 3);
+            sh = s_shift + 2 * (7 - (rr & 7u));
+        } else {
+            const uint32_t rb = (i - 1) / kRowsPerWord, r = (i - 1) % kRowsPerWord;
+            at = (uint64_t)rb * pd.pitch + (j - 1);
+            sh = 2 * r;
         }
-        const uint32_t code = (cw >> (2 * r)) & 3u;
+        if (at != cw_at) { cw = __ldg(base + at); cw_at = at; }
+        uint32_t code = (cw >> sh) & 3u;
+        if (is_short) code = (code == 3u) ? 3u : 2u - code;   // stored as tag: 2 diag, 1 left, 0 up
         if (TYPE == 1 && code == 3) break;
         push(code, 1);
         if (code == 0) { --i; --j; }

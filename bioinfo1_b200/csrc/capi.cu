@@ -19,6 +19,7 @@
 
 #include "../../include/b200map.h"
 #include "align_fill_generic.cuh"
+#include "align_fill_short.cuh"
 #include "align_walk.cuh"
 #include "common.cuh"
 #include "minimize.cuh"
@@ -104,7 +105,7 @@ struct b200_ctx {
     int sm_count = 148;
     cudaStream_t stream = nullptr;
     // workspaces shared by every plan run on this context (one run at a time per context)
-    DevBuf dirs, bnd, counter, end_i, end_j, runs, n_runs, cigar_len, scan_tmp, flags, total;
+    DevBuf dirs, bnd, bnd_short, qpk, tpk, counter, end_i, end_j, runs, n_runs, cigar_len, scan_tmp, flags, total;
     // staging for the host-buffer entry points
     DevBuf d_q, d_t, d_score, d_tb, d_cigar, d_cigar_off, d_seq, d_hash, d_pos, d_flag;
     HostBuf h_q, h_t, h_off;
@@ -184,7 +185,7 @@ extern "C" void b200_ctx_destroy(b200_ctx* c) {
     if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
     for (auto& sp : c->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     for (auto e : c->event_pool) cudaEventDestroy(e);
-    for (DevBuf* b : {&c->dirs, &c->bnd, &c->counter, &c->end_i, &c->end_j, &c->runs, &c->n_runs,
+    for (DevBuf* b : {&c->dirs, &c->bnd, &c->bnd_short, &c->qpk, &c->tpk, &c->counter, &c->end_i, &c->end_j, &c->runs, &c->n_runs,
                       &c->cigar_len, &c->scan_tmp, &c->flags, &c->total, &c->d_q, &c->d_t, &c->d_score, &c->d_tb,
                       &c->d_cigar, &c->d_cigar_off, &c->d_seq, &c->d_hash, &c->d_pos, &c->d_flag})
         b->release();
@@ -236,8 +237,12 @@ static int default_ctx(int device, b200_ctx** out) {
 }
 
 // ------------------------------------------------------------------ align plan ----
+// A wave is a slice of the work order whose direction matrices fit the HBM budget together and
+// that is served by one fill kernel class.
 struct Wave {
-    uint32_t first, count;  // range in the work order
+    uint32_t klass;
+    uint32_t first, count;   // range in the work order
+    uint32_t first_group;    // short class: index of the first ShortGroup
     uint64_t dir_words;
 };
 
@@ -247,10 +252,14 @@ struct b200_align_plan {
     int type = 0;
     Scores sc{};
     bool want_cigar = false;
-    uint64_t cells = 0, cigar_bound = 0, run_slots = 0;
-    uint32_t max_T = 0;
+    uint64_t cells = 0, cigar_bound = 0, run_slots = 0, q_bytes = 0, t_bytes = 0;
+    uint32_t max_T = 0, max_Q = 0, max_T_short = 0;
+    size_t n_short = 0;
     std::vector<Wave> waves;
-    DevBuf d_pairs, d_work;
+    std::vector<PairDesc> h_pairs;     // kept for the non-ACGT fallback (content is only known at run time)
+    std::vector<uint32_t> h_order;
+    bool patched = false;              // d_pairs currently holds run-specific fallback descriptors
+    DevBuf d_pairs, d_work, d_groups, d_fix_work;
 };
 
 extern "C" void b200_align_plan_destroy(b200_align_plan* p) {
@@ -258,10 +267,29 @@ extern "C" void b200_align_plan_destroy(b200_align_plan* p) {
     cudaSetDevice(p->ctx->device);
     p->d_pairs.release();
     p->d_work.release();
+    p->d_groups.release();
+    p->d_fix_work.release();
     delete p;
 }
 extern "C" uint64_t b200_align_plan_cells(const b200_align_plan* p) { return p ? p->cells : 0; }
 extern "C" uint64_t b200_align_plan_cigar_bound(const b200_align_plan* p) { return p ? p->cigar_bound : 0; }
+
+static inline uint64_t generic_dir_words(uint32_t Q, uint32_t T) {
+    return (uint64_t)div_up(Q, kRowsPerWord) * ((T + 3u) & ~3u);
+}
+
+// Can the int16 tagged kernel (align_fill_short.cuh) represent every value of this pair?
+static bool short_scores_ok(const Scores& sc, int type) {
+    if (type != 0) return false;   // K1 finalises global alignments only (semi/local go through the warp kernels)
+    auto fits8 = [](int v) { return v >= -128 && v <= 127; };
+    const long sm = 4l * ((long)sc.match - sc.gap) + 1, sx = 4l * ((long)sc.mismatch - sc.gap) + 1;
+    return fits8((int)sm) && fits8((int)sx) && std::abs((long)sc.gap) < 4000 && std::abs((long)sc.match) < 4000 &&
+           std::abs((long)sc.mismatch) < 4000;
+}
+static bool short_pair_ok(const Scores& sc, uint32_t Q, uint32_t T) {
+    const long mx = std::max({std::abs((long)sc.match), std::abs((long)sc.mismatch), std::abs((long)sc.gap), 1l});
+    return Q <= 4096 && T <= 4096 && 4l * (((long)Q + T + 2) * mx + 2) <= 32767;
+}
 
 extern "C" int b200_align_plan_create(b200_ctx* ctx, size_t n, const uint64_t* q_off, const uint64_t* t_off,
                                       int type, int match, int mismatch, int gap, int want_cigar,
@@ -275,10 +303,13 @@ extern "C" int b200_align_plan_create(b200_ctx* ctx, size_t n, const uint64_t* q
     if (!p) return fail(B200_E_NOMEM, "out of host memory");
     p->ctx = ctx; p->n = n; p->type = type; p->sc = Scores{match, mismatch, gap};
     p->want_cigar = want_cigar != 0;
+    p->q_bytes = n ? q_off[n] : 0;
+    p->t_bytes = n ? t_off[n] : 0;
 
-    std::vector<PairDesc> pairs(n);
-    std::vector<uint64_t> cells(n);
-    bool uniform = true;
+    std::vector<PairDesc>& pairs = p->h_pairs;
+    pairs.resize(n);
+    const bool short_scores = !ctx->force_generic && short_scores_ok(p->sc, type);
+    std::vector<uint32_t> short_list, generic_list;
     for (size_t i = 0; i < n; ++i) {
         const uint64_t ql = q_off[i + 1] - q_off[i], tl = t_off[i + 1] - t_off[i];
         if (q_off[i + 1] < q_off[i] || t_off[i + 1] < t_off[i] || ql > 0x3fffffffull || tl > 0x3fffffffull) {
@@ -289,42 +320,91 @@ extern "C" int b200_align_plan_create(b200_ctx* ctx, size_t n, const uint64_t* q
         d.q_off = q_off[i]; d.t_off = t_off[i];
         d.Q = (uint32_t)ql; d.T = (uint32_t)tl;
         d.pitch = (d.T + 3u) & ~3u;
-        d.klass = 0;
+        d.klass = kClassGeneric;
         d.dir_off = 0;
         d.run_off = p->run_slots;
         p->run_slots += ql + tl + 1;
-        cells[i] = ql * tl;
-        p->cells += cells[i];
+        p->cells += ql * tl;
         p->cigar_bound += std::max<uint64_t>(2, 2 * (ql + tl));
         p->max_T = std::max(p->max_T, d.T);
-        if (i && (d.Q != pairs[0].Q || d.T != pairs[0].T)) uniform = false;
+        p->max_Q = std::max(p->max_Q, d.Q);
+        if (short_scores && short_pair_ok(p->sc, d.Q, d.T)) short_list.push_back((uint32_t)i);
+        else generic_list.push_back((uint32_t)i);
     }
-    // work order: largest first so the dynamic scheduler's tail is made of small pairs
-    std::vector<uint32_t> order(n);
-    std::iota(order.begin(), order.end(), 0u);
-    if (!uniform)
-        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return cells[a] > cells[b]; });
-    // waves: consecutive slices of the order whose direction matrices fit the HBM budget
+    // thread-per-pair only pays off when there are enough pairs to occupy the machine
+    if (short_list.size() < 8192) {
+        generic_list.insert(generic_list.end(), short_list.begin(), short_list.end());
+        short_list.clear();
+    }
+    auto cells_of = [&](uint32_t a) { return (uint64_t)pairs[a].Q * pairs[a].T; };
+    auto is_sorted_desc = [&](const std::vector<uint32_t>& v, auto key) {
+        for (size_t k = 1; k < v.size(); ++k) if (key(v[k - 1]) < key(v[k])) return false;
+        return true;
+    };
+    // short class: neighbours in a 64-pair group should have the same block count and column count
+    auto short_key = [&](uint32_t a) { return ((uint64_t)div_up(pairs[a].Q, kShortRows) << 40) | ((uint64_t)pairs[a].T << 20) | pairs[a].Q; };
+    if (!is_sorted_desc(short_list, short_key))
+        std::stable_sort(short_list.begin(), short_list.end(), [&](uint32_t a, uint32_t b) { return short_key(a) > short_key(b); });
+    // warp-per-pair classes: largest first so the dynamic scheduler's tail is made of small pairs
+    if (!is_sorted_desc(generic_list, cells_of))
+        std::stable_sort(generic_list.begin(), generic_list.end(), [&](uint32_t a, uint32_t b) { return cells_of(a) > cells_of(b); });
+
+    std::vector<uint32_t>& order = p->h_order;
+    order.reserve(n);
+    std::vector<ShortGroup> groups;
     const uint64_t budget_words = (uint64_t)ctx->dir_budget_bytes / 4;
-    Wave cur{0, 0, 0};
-    for (uint32_t k = 0; k < n; ++k) {
-        PairDesc& d = pairs[order[k]];
-        const uint64_t words = p->want_cigar ? (uint64_t)div_up(d.Q, kRowsPerWord) * d.pitch : 0;
-        if (cur.count && cur.dir_words + words > budget_words) {
-            p->waves.push_back(cur);
-            cur = Wave{k, 0, 0};
+    p->n_short = short_list.size();
+    {   // short waves, in whole groups
+        Wave cur{kClassShort, 0, 0, 0, 0};
+        for (size_t g0 = 0; g0 < short_list.size(); g0 += 64) {
+            const size_t g1 = std::min(short_list.size(), g0 + 64);
+            uint32_t Qg = 0, Tg = 0;
+            for (size_t k = g0; k < g1; ++k) { Qg = std::max(Qg, pairs[short_list[k]].Q); Tg = std::max(Tg, pairs[short_list[k]].T); }
+            p->max_T_short = std::max(p->max_T_short, Tg);
+            const uint64_t words = p->want_cigar ? (uint64_t)div_up(Qg, kShortRows) * Tg * 128 : 0;
+            if (cur.count && cur.dir_words + words > budget_words) {
+                p->waves.push_back(cur);
+                cur = Wave{kClassShort, (uint32_t)order.size(), 0, (uint32_t)groups.size(), 0};
+            }
+            groups.push_back(ShortGroup{cur.dir_words, Tg, 0});
+            for (size_t k = g0; k < g1; ++k) {
+                PairDesc& d = pairs[short_list[k]];
+                const uint32_t slot = (uint32_t)(k - g0);
+                d.klass = kClassShort | ((slot >> 1) << 8) | ((slot & 1u) << 16);
+                d.dir_off = cur.dir_words;
+                d.pitch = Tg;
+                order.push_back(short_list[k]);
+            }
+            cur.dir_words += words;
+            cur.count += (uint32_t)(g1 - g0);
         }
-        d.dir_off = cur.dir_words;
-        cur.dir_words += words;
-        ++cur.count;
+        if (cur.count) p->waves.push_back(cur);
     }
-    if (cur.count) p->waves.push_back(cur);
+    {   // generic waves
+        Wave cur{kClassGeneric, (uint32_t)order.size(), 0, 0, 0};
+        for (uint32_t idx : generic_list) {
+            PairDesc& d = pairs[idx];
+            const uint64_t words = p->want_cigar ? generic_dir_words(d.Q, d.T) : 0;
+            if (cur.count && cur.dir_words + words > budget_words) {
+                p->waves.push_back(cur);
+                cur = Wave{kClassGeneric, (uint32_t)order.size(), 0, 0, 0};
+            }
+            d.dir_off = cur.dir_words;
+            cur.dir_words += words;
+            ++cur.count;
+            order.push_back(idx);
+        }
+        if (cur.count) p->waves.push_back(cur);
+    }
 
     int rc = p->d_pairs.ensure(std::max<size_t>(1, n) * sizeof(PairDesc));
     if (rc == B200_OK) rc = p->d_work.ensure(std::max<size_t>(1, n) * sizeof(uint32_t));
+    if (rc == B200_OK) rc = p->d_groups.ensure(std::max<size_t>(1, groups.size()) * sizeof(ShortGroup));
     if (rc == B200_OK && n) {
         cudaError_t e = cudaMemcpyAsync(p->d_pairs.p, pairs.data(), n * sizeof(PairDesc), cudaMemcpyHostToDevice, ctx->stream);
         if (e == cudaSuccess) e = cudaMemcpyAsync(p->d_work.p, order.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess && !groups.empty())
+            e = cudaMemcpyAsync(p->d_groups.p, groups.data(), groups.size() * sizeof(ShortGroup), cudaMemcpyHostToDevice, ctx->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) rc = fail(B200_E_CUDA, std::string("plan upload: ") + cudaGetErrorString(e));
         ctx->h2d_bytes += n * (sizeof(PairDesc) + sizeof(uint32_t));
@@ -338,18 +418,63 @@ struct U32ToU64 {
     __host__ __device__ uint64_t operator()(const uint32_t& v) const { return (uint64_t)v; }
 };
 
-template <int TYPE>
-static void launch_fill_generic(b200_align_plan* p, const Wave& wv, const uint8_t* d_q, const uint8_t* d_t,
-                                uint32_t* d_dirs, int32_t* d_score, int n_blocks, cudaStream_t st) {
+struct RunBufs {   // per-run device pointers shared by the launch helpers
+    const uint8_t *dq, *dt;
+    uint32_t* dirs;
+    int32_t* score;
+    cudaStream_t st;
+};
+
+static int launch_fill_generic(b200_align_plan* p, const uint32_t* d_work, uint32_t count, const RunBufs& rb) {
     b200_ctx* c = p->ctx;
-    prof_begin(c, st, 0);
-    fill_generic_kernel<TYPE><<<n_blocks, 128, 0, st>>>(
-        d_q, d_t, p->d_pairs.as<PairDesc>(), p->d_work.as<uint32_t>() + wv.first, wv.count,
-        c->counter.as<uint32_t>(), c->flags.as<uint8_t>(), (uint8_t)0, (uint8_t)0, p->sc, d_dirs,
-        c->bnd.as<int32_t>(), p->max_T + 8, d_score, c->end_i.as<uint32_t>(),
-        c->end_j.as<uint32_t>());
-    prof_end(c, st);
+    if (!count) return B200_OK;
+    const int n_blocks = (int)std::min<uint64_t>((uint64_t)c->sm_count * 8, div_up64(count, 4));
+    TRY(c->bnd.ensure((size_t)n_blocks * 4 * (size_t)(p->max_T + 8) * sizeof(int32_t)));
+    CU(cudaMemsetAsync(c->counter.p, 0, 64, rb.st));
+    prof_begin(c, rb.st, 0);
+#define GEN(TY) fill_generic_kernel<TY><<<n_blocks, 128, 0, rb.st>>>(rb.dq, rb.dt, p->d_pairs.as<PairDesc>(), d_work, count, \
+        c->counter.as<uint32_t>(), c->flags.as<uint8_t>(), (uint8_t)0, (uint8_t)0, p->sc, rb.dirs, c->bnd.as<int32_t>(),     \
+        p->max_T + 8, rb.score, c->end_i.as<uint32_t>(), c->end_j.as<uint32_t>())
+    switch (p->type) { case 0: GEN(0); break; case 1: GEN(1); break; default: GEN(2); break; }
+#undef GEN
+    prof_end(c, rb.st);
     c->kernel_launches++;
+    return B200_OK;
+}
+
+static int launch_fill_short(b200_align_plan* p, const Wave& wv, const RunBufs& rb) {
+    b200_ctx* c = p->ctx;
+    const uint32_t n_groups = (wv.count + 63) / 64;
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fill_short_kernel<0>, kShortThreads, 0));
+    per_sm = std::max(per_sm, 1);
+    const int n_blocks = (int)std::min<uint64_t>((uint64_t)c->sm_count * per_sm, div_up64(n_groups, kShortThreads / 32));
+    const uint32_t bnd_cols = p->max_T_short + 2;
+    TRY(c->bnd_short.ensure((size_t)n_blocks * (kShortThreads / 32) * bnd_cols * 32 * sizeof(uint32_t)));
+    CU(cudaMemsetAsync(c->counter.p, 0, 64, rb.st));
+    const ShortConsts K = make_short_consts(p->sc, p->type);
+    prof_begin(c, rb.st, 0);
+    fill_short_kernel<0><<<n_blocks, kShortThreads, 0, rb.st>>>(
+        c->qpk.as<uint32_t>(), c->tpk.as<uint32_t>(), p->d_pairs.as<PairDesc>(), p->d_work.as<uint32_t>() + wv.first,
+        wv.count, p->d_groups.as<ShortGroup>() + wv.first_group, c->counter.as<uint32_t>(), c->flags.as<uint8_t>(), K,
+        rb.dirs, c->bnd_short.as<uint32_t>(), bnd_cols, rb.score, c->end_i.as<uint32_t>(), c->end_j.as<uint32_t>());
+    prof_end(c, rb.st);
+    c->kernel_launches++;
+    return B200_OK;
+}
+
+static int launch_walk(b200_align_plan* p, const uint32_t* d_work, uint32_t count, const RunBufs& rb) {
+    b200_ctx* c = p->ctx;
+    if (!count) return B200_OK;
+    const unsigned wb = (unsigned)div_up64(count, 128);
+    prof_begin(c, rb.st, 1);
+#define WALK(TY) walk_kernel<TY><<<wb, 128, 0, rb.st>>>(p->d_pairs.as<PairDesc>(), d_work, count, rb.dirs, c->end_i.as<uint32_t>(), \
+        c->end_j.as<uint32_t>(), c->runs.as<uint32_t>(), c->n_runs.as<uint32_t>(), c->cigar_len.as<uint32_t>())
+    switch (p->type) { case 0: WALK(0); break; case 1: WALK(1); break; default: WALK(2); break; }
+#undef WALK
+    prof_end(c, rb.st);
+    c->kernel_launches++;
+    return B200_OK;
 }
 
 extern "C" int b200_align_plan_run(b200_align_plan* p, const char* d_q_buf, const char* d_t_buf,
@@ -366,54 +491,99 @@ extern "C" int b200_align_plan_run(b200_align_plan* p, const char* d_q_buf, cons
         if (d_cigar_off) CU(cudaMemsetAsync(d_cigar_off, 0, sizeof(uint64_t), st));
         return B200_OK;
     }
-    const uint8_t* dq = reinterpret_cast<const uint8_t*>(d_q_buf);
-    const uint8_t* dt = reinterpret_cast<const uint8_t*>(d_t_buf);
+    RunBufs rb{reinterpret_cast<const uint8_t*>(d_q_buf), reinterpret_cast<const uint8_t*>(d_t_buf), nullptr, d_score, st};
 
-    // persistent grid: 4 warps per CTA, enough CTAs to fill every SM
-    const int n_blocks = (int)std::min<uint64_t>((uint64_t)c->sm_count * 8, div_up64(n, 4));
-    const uint64_t n_warps = (uint64_t)n_blocks * 4;
     uint64_t max_dir_words = 0;
     for (const Wave& w : p->waves) max_dir_words = std::max(max_dir_words, w.dir_words);
-    TRY(c->counter.ensure(64));
+    TRY(c->counter.ensure(128));
     TRY(c->flags.ensure(n));
-    TRY(c->bnd.ensure(n_warps * (size_t)(p->max_T + 8) * sizeof(int32_t)));
     TRY(c->end_i.ensure(n * 4));
     TRY(c->end_j.ensure(n * 4));
     if (p->want_cigar) {
-        TRY(c->dirs.ensure(std::max<uint64_t>(max_dir_words, 4) * 4));
         TRY(c->runs.ensure(p->run_slots * 4));
         TRY(c->n_runs.ensure(n * 4));
         TRY(c->cigar_len.ensure(n * 4));
-        TRY(c->total.ensure(8));
     }
+    uint32_t* d_nflag = c->counter.as<uint32_t>() + 16;
 
+    // classify every pair (and build the 2-bit copies the short kernel reads)
     prof_begin(c, st, 3);
-    classify_kernel<<<(unsigned)div_up64(n * 32, 256), 256, 0, st>>>(dq, dt, p->d_pairs.as<PairDesc>(), (uint32_t)n,
-                                                                  c->flags.as<uint8_t>());
+    if (p->n_short) {
+        TRY(c->qpk.ensure((p->q_bytes / 16 + n + p->max_Q / 16 + 72) * 4));
+        TRY(c->tpk.ensure((p->t_bytes / 16 + n + p->max_T / 16 + 72) * 4));
+        CU(cudaMemsetAsync(d_nflag, 0, 4, st));
+        pack_kernel<<<(unsigned)div_up64(n * 32, 256), 256, 0, st>>>(rb.dq, rb.dt, p->d_pairs.as<PairDesc>(), (uint32_t)n,
+            c->flags.as<uint8_t>(), c->qpk.as<uint32_t>(), c->tpk.as<uint32_t>(), d_nflag);
+    } else {
+        classify_kernel<<<(unsigned)div_up64(n * 32, 256), 256, 0, st>>>(rb.dq, rb.dt, p->d_pairs.as<PairDesc>(), (uint32_t)n,
+                                                                      c->flags.as<uint8_t>());
+    }
     prof_end(c, st);
     c->kernel_launches++;
 
-    for (const Wave& wv : p->waves) {
-        CU(cudaMemsetAsync(c->counter.p, 0, 64, st));
-        uint32_t* d_dirs = p->want_cigar ? c->dirs.as<uint32_t>() : nullptr;
-        const int nb = (int)std::min<uint64_t>((uint64_t)n_blocks, div_up64(wv.count, 4));
-        switch (p->type) {
-            case 0: launch_fill_generic<0>(p, wv, dq, dt, d_dirs, d_score, nb, st); break;
-            case 1: launch_fill_generic<1>(p, wv, dq, dt, d_dirs, d_score, nb, st); break;
-            default: launch_fill_generic<2>(p, wv, dq, dt, d_dirs, d_score, nb, st); break;
-        }
-        if (p->want_cigar) {
-            const unsigned wb = (unsigned)div_up64(wv.count, 128);
-            const uint32_t* work = p->d_work.as<uint32_t>() + wv.first;
-            prof_begin(c, st, 1);
-            switch (p->type) {
-                case 0: walk_kernel<0><<<wb, 128, 0, st>>>(p->d_pairs.as<PairDesc>(), work, wv.count, d_dirs, c->end_i.as<uint32_t>(), c->end_j.as<uint32_t>(), c->runs.as<uint32_t>(), c->n_runs.as<uint32_t>(), c->cigar_len.as<uint32_t>()); break;
-                case 1: walk_kernel<1><<<wb, 128, 0, st>>>(p->d_pairs.as<PairDesc>(), work, wv.count, d_dirs, c->end_i.as<uint32_t>(), c->end_j.as<uint32_t>(), c->runs.as<uint32_t>(), c->n_runs.as<uint32_t>(), c->cigar_len.as<uint32_t>()); break;
-                default: walk_kernel<2><<<wb, 128, 0, st>>>(p->d_pairs.as<PairDesc>(), work, wv.count, d_dirs, c->end_i.as<uint32_t>(), c->end_j.as<uint32_t>(), c->runs.as<uint32_t>(), c->n_runs.as<uint32_t>(), c->cigar_len.as<uint32_t>()); break;
+    // Pairs planned for the short kernel that turn out not to be pure ACGT fall back to the generic
+    // kernel; their direction matrices go behind the wave's own region. Content-dependent, hence
+    // decided here (one 4-byte read-back) and not in the plan.
+    std::vector<std::vector<uint32_t>> fix(p->waves.size());
+    std::vector<uint64_t> wave_words(p->waves.size());
+    for (size_t k = 0; k < p->waves.size(); ++k) wave_words[k] = p->waves[k].dir_words;
+    bool any_fix = false;
+    if (p->n_short) {
+        uint32_t n_flagged = 0;
+        CU(cudaMemcpyAsync(&n_flagged, d_nflag, 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        if (n_flagged) {
+            std::vector<uint8_t> h_flags(n);
+            CU(cudaMemcpyAsync(h_flags.data(), c->flags.p, n, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            std::vector<PairDesc> patched;
+            for (size_t k = 0; k < p->waves.size(); ++k) {
+                const Wave& wv = p->waves[k];
+                if (wv.klass != kClassShort) continue;
+                for (uint32_t w = wv.first; w < wv.first + wv.count; ++w) {
+                    const uint32_t idx = p->h_order[w];
+                    if (!h_flags[idx]) continue;
+                    if (patched.empty()) patched = p->h_pairs;
+                    PairDesc& d = patched[idx];
+                    d.klass = kClassGeneric;
+                    d.pitch = (d.T + 3u) & ~3u;
+                    d.dir_off = (wave_words[k] + 3) & ~3ull;
+                    wave_words[k] = d.dir_off + (p->want_cigar ? generic_dir_words(d.Q, d.T) : 0);
+                    fix[k].push_back(idx);
+                    any_fix = true;
+                }
             }
-            prof_end(c, st);
-            c->kernel_launches++;
+            if (any_fix) {
+                CU(cudaMemcpyAsync(p->d_pairs.p, patched.data(), n * sizeof(PairDesc), cudaMemcpyHostToDevice, st));
+                CU(cudaStreamSynchronize(st));   // `patched` is pageable and about to go out of scope
+                p->patched = true;
+            }
         }
+        if (!any_fix && p->patched) {
+            CU(cudaMemcpyAsync(p->d_pairs.p, p->h_pairs.data(), n * sizeof(PairDesc), cudaMemcpyHostToDevice, st));
+            CU(cudaStreamSynchronize(st));
+            p->patched = false;
+        }
+    }
+    for (uint64_t w : wave_words) max_dir_words = std::max(max_dir_words, w);
+    if (p->want_cigar) TRY(c->dirs.ensure(std::max<uint64_t>(max_dir_words, 4) * 4 + 64));
+    rb.dirs = p->want_cigar ? c->dirs.as<uint32_t>() : nullptr;
+
+    for (size_t k = 0; k < p->waves.size(); ++k) {
+        const Wave& wv = p->waves[k];
+        const uint32_t* work = p->d_work.as<uint32_t>() + wv.first;
+        if (wv.klass == kClassShort) {
+            TRY(launch_fill_short(p, wv, rb));
+            if (!fix[k].empty()) {
+                TRY(p->d_fix_work.ensure(fix[k].size() * 4));
+                CU(cudaMemcpyAsync(p->d_fix_work.p, fix[k].data(), fix[k].size() * 4, cudaMemcpyHostToDevice, st));
+                CU(cudaStreamSynchronize(st));
+                TRY(launch_fill_generic(p, p->d_fix_work.as<uint32_t>(), (uint32_t)fix[k].size(), rb));
+            }
+        } else {
+            TRY(launch_fill_generic(p, work, wv.count, rb));
+        }
+        if (p->want_cigar) TRY(launch_walk(p, work, wv.count, rb));
     }
     CU(cudaGetLastError());
 

@@ -22,9 +22,12 @@ struct PairDesc {
     uint64_t run_off;  // element offset of this pair's run slots inside the run scratch
     uint32_t Q, T;
     uint32_t pitch;    // words per row block
-    uint32_t klass;    // kernel class chosen at plan time (see capi.cu)
+    uint32_t klass;    // bits 0-7 kernel class (kClass*), short class: bits 8-12 lane, bit 16 half
 };
 static_assert(sizeof(PairDesc) == 48, "PairDesc layout");
+
+constexpr uint32_t kClassGeneric = 0;  // align_fill_generic.cuh layout: word(rb, j) = dirs[dir_off + rb*pitch + j-1]
+constexpr uint32_t kClassShort = 1;    // align_fill_short.cuh layout, pitch = column count of the 64-pair group
 
 constexpr uint8_t kFlagDash = 1;     // pair contains a '-' byte (free gap, team_alignment.cpp:25-28)
 constexpr uint8_t kFlagNonACGT = 2;  // pair contains a byte outside "ACGT"

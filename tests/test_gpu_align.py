@@ -144,3 +144,55 @@ def test_live_reference_spot_check(ctx):
     ts = [bytes(rng.choice(b"ACGT-N") for _ in range(rng.randint(0, 200))) for _ in range(100)]
     for typ in (0, 1, 2):
         _check_batch(ctx, qs, ts, typ, 2, -1, -2, checker=ref)
+
+
+# ---- K1: the thread-per-pair int16 kernel (needs >= 8192 eligible pairs to be selected) -------
+
+def _check_packed_vs_oracle(ctx, qb, qo, tb, to, typ, m, x, g, stride):
+    score, tbeg, cig, coff = ctx.align_packed(qb, qo, tb, to, typ, m, x, g)
+    s_only, tb_only, _, _ = ctx.align_packed(qb, qo, tb, to, typ, m, x, g, want_cigar=False)
+    assert np.array_equal(score, s_only) and np.array_equal(tbeg, tb_only)
+    n = len(qo) - 1
+    sc_ref, tb_ref, _ = ORACLE.align_batch(qb, qo, tb, to, typ, m, x, g)
+    assert np.array_equal(score, sc_ref), np.nonzero(score != sc_ref)[0][:10]
+    assert np.array_equal(tbeg, tb_ref)
+    for k in range(0, n, stride):
+        q = qb[int(qo[k]):int(qo[k + 1])].tobytes()
+        t = tb[int(to[k]):int(to[k + 1])].tobytes()
+        exp = ORACLE.align(q, t, typ, m, x, g)
+        got = (int(score[k]), int(tbeg[k]), cig[int(coff[k]):int(coff[k + 1])].tobytes())
+        assert got == exp, (k, len(q), len(t), got, exp)
+
+
+def test_short_kernel_uniform_150(ctx):
+    qb, qo, tb, to = seqgen.short_pairs(21, 16384)
+    _check_packed_vs_oracle(ctx, qb, qo, tb, to, 0, 1, -1, -1, 5)
+    _check_packed_vs_oracle(ctx, qb, qo, tb, to, 0, 2, -3, -2, 37)
+    _check_packed_vs_oracle(ctx, qb, qo, tb, to, 0, 1, -1, 1, 37)     # positive gap
+
+
+def test_short_kernel_ragged_lengths_and_fallback(ctx):
+    rng = np.random.default_rng(77)
+    n = 12000
+    qs, ts = [], []
+    for k in range(n):
+        T = int(rng.integers(0, 260))
+        t = seqgen.random_dna(rng, T)
+        if k % 3 == 0:
+            q = seqgen.random_dna(rng, int(rng.integers(0, 260)))
+        else:
+            q = seqgen.mutate(rng, t, sub=0.05, ins=0.04, dele=0.04)
+        if k % 97 == 0 and len(q) > 3:      # not pure ACGT: must fall back to the generic kernel
+            q = q.copy(); q[len(q) // 2] = ord("N")
+        if k % 389 == 0 and T > 3:
+            t = t.copy(); t[1] = ord("-")
+        qs.append(q); ts.append(t)
+    qb, qo = seqgen.pack_arrays(qs)
+    tb, to = seqgen.pack_arrays(ts)
+    _check_packed_vs_oracle(ctx, qb, qo, tb, to, 0, 1, -1, -1, 11)
+    # same plan shape, now all-ACGT content: the fallback patch must be undone
+    qs2 = [np.where(np.isin(q, seqgen.ACGT), q, ord("A")).astype(np.uint8) for q in qs]
+    ts2 = [np.where(np.isin(t, seqgen.ACGT), t, ord("C")).astype(np.uint8) for t in ts]
+    qb2, qo2 = seqgen.pack_arrays(qs2)
+    tb2, to2 = seqgen.pack_arrays(ts2)
+    _check_packed_vs_oracle(ctx, qb2, qo2, tb2, to2, 0, 3, -2, -4, 11)
