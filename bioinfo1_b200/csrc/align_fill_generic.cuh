@@ -206,13 +206,15 @@ fill_generic_kernel(const uint8_t* __restrict__ qbuf, const uint8_t* __restrict_
     }
 }
 
-// One warp per pair: flags[p] bit0 = contains '-', bit1 = contains a byte outside "ACGT".
+// One warp per listed pair: flags[p] bit0 = contains '-', bit1 = contains a byte outside "ACGT".
 __global__ void __launch_bounds__(256)
 classify_kernel(const uint8_t* __restrict__ qbuf, const uint8_t* __restrict__ tbuf,
-                const PairDesc* __restrict__ pairs, uint32_t n, uint8_t* __restrict__ flags) {
-    const uint32_t p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+                const PairDesc* __restrict__ pairs, const uint32_t* __restrict__ work, uint32_t n_work,
+                uint8_t* __restrict__ flags) {
+    const uint32_t wi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (p >= n) return;
+    if (wi >= n_work) return;
+    const uint32_t p = work[wi];
     const PairDesc pd = pairs[p];
     bool dash = false, other = false;
     for (int which = 0; which < 2; ++which) {

@@ -11,14 +11,13 @@
 // the winner ARE the direction (stored as code = 2 - tag... see kTagToCode). Per pair of cells:
 //     S   = PRMT(tabA, tabB, sel[r])              substitution term from a per-column byte table
 //     m1  = VIADDMNMX.S16x2(diag, S, left)        max(diag + S, left)
-//     Z   = VIADDMNMX.S16x2(up, 4*gap, m1)        max(up + 4*gap, m1)
-//     Zc  = Z & 0xFFFCFFFC                        strip the tag: 4*H
-//     Lv  = VIADD.16x2(Zc, 4*gap + 1)             what the right/diagonal neighbours consume
-//     acc = acc*4 + (Z - Zc)                      2-bit direction, 8 rows per 16-bit half
-// = 4 alu-pipe + 2 fma-pipe + 1 PRMT issue slots for TWO cells.
+//     Z   = VIADDMNMX.S16x2(up, 4*gap - 1, m1)    max(up + 4*gap - 1, m1)
+//     Y   = LOP3 (Z & 0xFFFCFFFC) | 0x00010001    strip the tag, re-arm the 'left' tag
+//     accZ = accZ*4 + Z ; accY = accY*4 + Y       IMAD chains; accZ - accY + 0x5555.. = 8 tags / half
+// = 3 alu-pipe + 2 fma-pipe + 1 PRMT issue slots for TWO cells (see the moving-frame note below).
 //
 // Eligibility (decided on the host, capi.cu): both sequences pure ACGT, |s - gap| <= 31 for
-// s in {match, mismatch}, and 4 * ((Q+T+2) * max|score| + 2) <= 32767 so nothing leaves int16.
+// s in {match, mismatch}, and 4 * ((Q+T+2) * max|score| + |gap| * T + 4) <= 32767 so nothing leaves int16.
 #pragma once
 #include "common.cuh"
 
@@ -32,39 +31,39 @@ constexpr int kShortThreads = 64;    // 2 warps per CTA, every warp independent
 __device__ __forceinline__ uint32_t acgt_code(uint32_t c) { return (c >> 1) & 3u; }  // A=0 C=1 T=2 G=3 on ASCII
 // (ASCII: A=0x41 -> 0, C=0x43 -> 1, G=0x47 -> 3, T=0x54 -> 2; any bijection works for equality.)
 
-// One warp per pair: classify (flags) and write the 2-bit packed copies.
+// One thread per packed word: classifies its 16 bases (flags, only touched when something other
+// than ACGT shows up, so flags[] must be zeroed first) and writes the 2-bit copy. blockIdx.y picks
+// query (0) or target (1); `wpp` = words per sequence of the longest short pair.
 __global__ void __launch_bounds__(256)
 pack_kernel(const uint8_t* __restrict__ qbuf, const uint8_t* __restrict__ tbuf,
-            const PairDesc* __restrict__ pairs, uint32_t n, uint8_t* __restrict__ flags,
-            uint32_t* __restrict__ qpk, uint32_t* __restrict__ tpk, uint32_t* __restrict__ n_flagged) {
-    const uint32_t p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (p >= n) return;
+            const PairDesc* __restrict__ pairs, const uint32_t* __restrict__ work, uint32_t n_work,
+            uint32_t wpp, uint8_t* __restrict__ flags, uint32_t* __restrict__ qpk,
+            uint32_t* __restrict__ tpk, uint32_t* __restrict__ n_flagged) {
+    const uint64_t id = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t wi = (uint32_t)(id / wpp), w = (uint32_t)(id % wpp);
+    if (wi >= n_work) return;
+    const uint32_t p = work[wi];
     const PairDesc pd = pairs[p];
+    const bool which = blockIdx.y != 0;
+    const uint32_t len = which ? pd.T : pd.Q;
+    if (w * 16 >= len) return;
+    const uint8_t* s = (which ? tbuf + pd.t_off : qbuf + pd.q_off) + w * 16;
+    const uint32_t nb = min(16u, len - w * 16);
+    uint32_t word = 0;
     bool dash = false, other = false;
-    for (int which = 0; which < 2; ++which) {
-        const uint8_t* s = which ? tbuf + pd.t_off : qbuf + pd.q_off;
-        const uint32_t len = which ? pd.T : pd.Q;
-        uint32_t* dst = (which ? tpk + (pd.t_off >> 4) : qpk + (pd.q_off >> 4)) + p;
-        const uint32_t nw = (len + 15) / 16;
-        for (uint32_t w = lane; w < nw; w += kWarp) {
-            uint32_t word = 0;
 #pragma unroll
-            for (int b = 0; b < 16; ++b) {
-                const uint32_t at = w * 16 + b;
-                const uint32_t c = at < len ? (uint32_t)s[at] : (uint32_t)'A';
-                dash |= (c == '-');
-                other |= !(c == 'A' || c == 'C' || c == 'G' || c == 'T');
-                word |= acgt_code(c) << (2 * b);
-            }
-            dst[w] = word;
-        }
+    for (uint32_t b = 0; b < 16; ++b) {
+        const uint32_t c = b < nb ? (uint32_t)s[b] : (uint32_t)'A';
+        dash |= (c == '-');
+        other |= !(c == 'A' || c == 'C' || c == 'G' || c == 'T');
+        word |= acgt_code(c) << (2 * b);
     }
-    const unsigned d = __ballot_sync(kFull, dash), o = __ballot_sync(kFull, other);
-    if (lane == 0) {
-        const uint8_t f = (d ? kFlagDash : 0) | (o ? kFlagNonACGT : 0);
-        flags[p] = f;
-        if (f && n_flagged) atomicAdd(n_flagged, 1u);
+    ((which ? tpk + (pd.t_off >> 4) : qpk + (pd.q_off >> 4)) + p)[w] = word;
+    if (dash || other) {
+        const uint32_t f = (dash ? kFlagDash : 0u) | (other ? kFlagNonACGT : 0u);
+        uint32_t* word32 = reinterpret_cast<uint32_t*>(flags + (p & ~3u));
+        const uint32_t old = atomicOr(word32, f << (8 * (p & 3u)));
+        if (((old >> (8 * (p & 3u))) & 0xffu) == 0) atomicAdd(n_flagged, 1u);
     }
 }
 
@@ -75,10 +74,12 @@ struct ShortGroup {   // one per 64-pair group (one warp's worth of work)
 };
 
 struct ShortConsts {
-    uint32_t tab_match;   // byte table seeds, see make_short_consts()
-    uint32_t tab_mis;
-    uint32_t g4;          // 4*gap in both halves
-    uint32_t kl;          // 4*gap + 1 in both halves
+    uint32_t tab_diff;    // (S'match ^ S'mismatch) in byte 0
+    uint32_t tab_mis;     // S'mismatch in all four bytes
+    uint32_t cu;          // 4*gap - 1 in both halves: what the 'up' candidate adds
+    // Passed as parameters (constant bank) rather than literals on purpose: LOP3 can take only one
+    // immediate, and a literal multiplier of 4 would be strength-reduced onto the (saturated) alu pipe.
+    uint32_t mask, one, four;
     int gap, init;
 };
 
@@ -86,13 +87,11 @@ __host__ __device__ inline uint32_t dup16(int v) { return ((uint32_t)(uint16_t)(
 
 __host__ inline ShortConsts make_short_consts(const Scores& sc, int type) {
     ShortConsts k;
-    // S' = 4*(s - gap) + 1: the diagonal candidate is built from the neighbour's Lv = 4H + 4gap + 1,
-    // and must come out as 4*(H + s) + 2.
     const int sm = 4 * (sc.match - sc.gap) + 1, sx = 4 * (sc.mismatch - sc.gap) + 1;
-    k.tab_match = (uint32_t)(uint8_t)(int8_t)sm;
+    k.tab_diff = ((uint32_t)(uint8_t)(int8_t)sm) ^ ((uint32_t)(uint8_t)(int8_t)sx);
     k.tab_mis = ((uint32_t)(uint8_t)(int8_t)sx) * 0x01010101u;
-    k.g4 = dup16(4 * sc.gap);
-    k.kl = dup16(4 * sc.gap + 1);
+    k.cu = dup16(4 * sc.gap - 1);
+    k.mask = 0xfffcfffcu; k.one = 0x00010001u; k.four = 4u;
     k.gap = sc.gap;
     k.init = (type == 0) ? sc.gap : 0;
     return k;
@@ -106,15 +105,28 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
     return r;
 }
 
+__device__ __forceinline__ uint32_t lop3_and_or(uint32_t a, uint32_t b, uint32_t c) {   // (a & b) | c
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+
 __device__ __forceinline__ int half_lo(uint32_t v) { return (int)(int16_t)(v & 0xffffu); }
 __device__ __forceinline__ int half_hi(uint32_t v) { return (int)(int16_t)(v >> 16); }
 
 // Direction word layout written by this kernel (read back by walk_kernel, klass kClassShort):
 //   uint4 at dirs[dir_off + ((block * Tg + (j-1)) * 32 + lane) * 4 .. +3]; word k covers rows
 //   8k..8k+7 of the block, low half = pair A, high half = pair B, row 8k in the top 2 bits of the
-//   half. Stored value is the TAG (2 diagonal, 1 left, 0 up), i.e. code = kTagToCode(tag).
+//   half. Stored value is the TAG (2 diagonal, 1 left, 0 up; 3 = local stop).
+//
+// Moving frame: the register value of cell (i,j) is Y = 4*H(i,j) - 4*gap*j + 1. In that frame a
+// step to the right costs nothing, so the three candidates are
+//     diagonal  Y(i-1,j-1) + 4*(s-gap) + 1   -> 4H' + 2
+//     left      Y(i,  j-1)                    -> 4H' + 1
+//     up        Y(i-1,j)   + 4*gap - 1        -> 4H' + 0
+// (H' = H - gap*j) and one signed max gives maximum, tie order and direction tag at once.
 template <int TYPE>
-__global__ void __launch_bounds__(kShortThreads)
+__global__ void __launch_bounds__(kShortThreads, 8)
 fill_short_kernel(const uint32_t* __restrict__ qpk, const uint32_t* __restrict__ tpk,
                   const PairDesc* __restrict__ pairs, const uint32_t* __restrict__ work, uint32_t n_work,
                   const ShortGroup* __restrict__ groups, uint32_t* __restrict__ group_counter,
@@ -126,7 +138,8 @@ fill_short_kernel(const uint32_t* __restrict__ qpk, const uint32_t* __restrict__
     const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     uint32_t* my_bnd = bnd + (size_t)warp_global * bnd_cols * kWarp + lane;   // [col][lane]
     const uint32_t n_groups = (n_work + 63) / 64;
-    const uint32_t MASK = 0xfffcfffcu;
+    const uint32_t MASK = K.mask, ONE = K.one, FOUR = K.four;
+    const int frame = 4 * (K.init - K.gap);   // top border row in the moving frame: Y(0,j) = frame*j + 1
 
     for (;;) {
         uint32_t g = 0;
@@ -161,7 +174,7 @@ fill_short_kernel(const uint32_t* __restrict__ qpk, const uint32_t* __restrict__
         for (uint32_t b = 0; b < n_blocks; ++b) {
             const uint32_t i0 = b * R;   // rows i0+1 .. i0+R
             // per-row PRMT selectors: byte0 = tabA[qA], byte1 = its sign, byte2 = tabB[qB], byte3 = sign
-            uint32_t sel[R], Lv[R];
+            uint32_t sel[R], Y[R];
             {
                 const uint32_t qa0 = qwA[(i0 >> 4)], qa1 = qwA[(i0 >> 4) + 1];
                 const uint32_t qb0 = qwB[(i0 >> 4)], qb1 = qwB[(i0 >> 4) + 1];
@@ -170,53 +183,57 @@ fill_short_kernel(const uint32_t* __restrict__ qpk, const uint32_t* __restrict__
                     const uint32_t ca = ((r < 16 ? qa0 : qa1) >> (2 * (r & 15))) & 3u;
                     const uint32_t cb = ((r < 16 ? qb0 : qb1) >> (2 * (r & 15))) & 3u;
                     sel[r] = ca | ((8u + ca) << 4) | ((4u + cb) << 8) | ((12u + cb) << 12);
-                    const int col0 = (int)((i0 + 1 + r) * (uint32_t)K.init);   // H(i,0)
-                    Lv[r] = __vadd2(dup16(4 * col0), K.kl);
+                    Y[r] = dup16(4 * (int)((i0 + 1 + r) * (uint32_t)K.init) + 1);   // column 0, frame 0
                 }
             }
-            // top boundary of this block: H(i0, j). Block 0: the border row j*init.
-            uint32_t top_prev = dup16(4 * (int)(i0 * (uint32_t)K.init));   // Zc of (i0, 0)
-            uint32_t tA = 0, tB = 0;
+            uint32_t top_prev = dup16(4 * (int)(i0 * (uint32_t)K.init) + 1);       // Y(i0, 0)
+            // software prefetch: the boundary row and the packed target words are fetched one step early
+            uint32_t top_next = (b == 0) ? dup16(frame * 1 + 1) : my_bnd[(size_t)1 * kWarp];
+            uint32_t tA_next = twA[0], tB_next = twB[0], tA = 0, tB = 0;
             uint32_t* dcol = dirs ? dirs + dir_off + ((uint64_t)b * Tg * 32 + lane) * 4 : nullptr;
 
             for (uint32_t j = 1; j <= Tm; ++j) {
-                if (((j - 1) & 15u) == 0) { tA = twA[(j - 1) >> 4]; tB = twB[(j - 1) >> 4]; }
+                if (((j - 1) & 15u) == 0) {
+                    tA = tA_next; tB = tB_next;
+                    tA_next = twA[((j - 1) >> 4) + 1]; tB_next = twB[((j - 1) >> 4) + 1];
+                }
                 const uint32_t cA = tA & 3u, cB = tB & 3u;
                 tA >>= 2; tB >>= 2;
-                // per-column byte tables: entry c = S'(c, target) = match at c == target code
-                const uint32_t tabA = K.tab_mis ^ ((K.tab_match ^ (K.tab_mis & 0xffu)) << (8 * cA));
-                const uint32_t tabB = K.tab_mis ^ ((K.tab_match ^ (K.tab_mis & 0xffu)) << (8 * cB));
-                uint32_t top = (b == 0) ? dup16(4 * (int)(j * (uint32_t)K.init)) : my_bnd[(size_t)j * kWarp];
-                uint32_t up = top;                       // Zc of the row above
-                uint32_t dg = __vadd2(top_prev, K.kl);   // Lv form of (i0, j-1)
+                // per-column byte tables: entry c = S'(c, target) (match where c == target code)
+                const uint32_t tabA = K.tab_mis ^ (K.tab_diff << (8 * cA));
+                const uint32_t tabB = K.tab_mis ^ (K.tab_diff << (8 * cB));
+                const uint32_t top = top_next;
+                if (j < Tm) top_next = (b == 0) ? dup16(frame * (int)(j + 1) + 1) : my_bnd[(size_t)(j + 1) * kWarp];
+                uint32_t up = top;        // Y of the row above, this column's frame
+                uint32_t dg = top_prev;   // Y(i0, j-1), previous column's frame
                 top_prev = top;
-                uint32_t acc[4];
+                uint32_t accZ = 0, accY = 0, w[4];
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
                     const uint32_t S = prmt(tabA, tabB, sel[r]);
-                    const uint32_t m1 = __viaddmax_s16x2(dg, S, Lv[r]);
-                    uint32_t Z = __viaddmax_s16x2(up, K.g4, m1);
-                    if (TYPE == 1) Z = __vmaxs2(Z, 0x00030003u);   // local: clamp at 0, tag 3 = stop
-                    const uint32_t Zc = Z & MASK;
-                    dg = Lv[r];
-                    Lv[r] = __vadd2(Zc, K.kl);
-                    up = Zc;
-                    if ((r & 7) == 0) acc[r >> 3] = Z - Zc;
-                    else acc[r >> 3] = acc[r >> 3] * 4u + (Z - Zc);
+                    const uint32_t m1 = __viaddmax_s16x2(dg, S, Y[r]);
+                    uint32_t Z = __viaddmax_s16x2(up, K.cu, m1);
+                    dg = Y[r];
+                    Y[r] = lop3_and_or(Z, MASK, ONE);
+                    up = Y[r];
+                    // direction tags: two multiply-add chains on the fma pipe; (Z - Y) = tag - 1 per half
+                    accZ = accZ * FOUR + Z;
+                    accY = accY * FOUR + Y[r];
+                    if ((r & 7) == 7) { w[r >> 3] = accZ - accY + 0x55555555u; accZ = 0; accY = 0; }
                 }
                 if (b + 1 < n_blocks) my_bnd[(size_t)j * kWarp] = up;
-                if (dcol) *reinterpret_cast<uint4*>(dcol + (uint64_t)(j - 1) * 128) = make_uint4(acc[0], acc[1], acc[2], acc[3]);
+                if (dcol) *reinterpret_cast<uint4*>(dcol + (uint64_t)(j - 1) * 128) = make_uint4(w[0], w[1], w[2], w[3]);
                 // end-cell capture (global): the cell (Q, T) of either pair
                 if (TYPE == 0) {
                     const bool hitA = liveA && j == TA && (QA - 1) / R == b;
                     const bool hitB = liveB && j == TB && (QB - 1) / R == b;
                     if (hitA || hitB) {
                         const uint32_t rA = (QA - 1) % R, rB = (QB - 1) % R;
-                        uint32_t vA = Lv[0], vB = Lv[0];
+                        uint32_t vA = Y[0], vB = Y[0];
 #pragma unroll
-                        for (int r = 1; r < R; ++r) { if ((uint32_t)r == rA) vA = Lv[r]; if ((uint32_t)r == rB) vB = Lv[r]; }
-                        if (hitA) resA = (half_lo(vA) - (4 * K.gap + 1)) >> 2;
-                        if (hitB) resB = (half_hi(vB) - (4 * K.gap + 1)) >> 2;
+                        for (int r = 1; r < R; ++r) { if ((uint32_t)r == rA) vA = Y[r]; if ((uint32_t)r == rB) vB = Y[r]; }
+                        if (hitA) resA = (half_lo(vA) - 1 + 4 * K.gap * (int)j) >> 2;
+                        if (hitB) resB = (half_hi(vB) - 1 + 4 * K.gap * (int)j) >> 2;
                     }
                 }
             }

@@ -253,7 +253,7 @@ struct b200_align_plan {
     Scores sc{};
     bool want_cigar = false;
     uint64_t cells = 0, cigar_bound = 0, run_slots = 0, q_bytes = 0, t_bytes = 0;
-    uint32_t max_T = 0, max_Q = 0, max_T_short = 0;
+    uint32_t max_T = 0, max_Q = 0, max_T_short = 0, max_Q_short = 0;
     size_t n_short = 0;
     std::vector<Wave> waves;
     std::vector<PairDesc> h_pairs;     // kept for the non-ACGT fallback (content is only known at run time)
@@ -288,7 +288,7 @@ static bool short_scores_ok(const Scores& sc, int type) {
 }
 static bool short_pair_ok(const Scores& sc, uint32_t Q, uint32_t T) {
     const long mx = std::max({std::abs((long)sc.match), std::abs((long)sc.mismatch), std::abs((long)sc.gap), 1l});
-    return Q <= 4096 && T <= 4096 && 4l * (((long)Q + T + 2) * mx + 2) <= 32767;
+    return Q <= 4096 && T <= 4096 && 4l * (((long)Q + T + 2) * mx + std::abs((long)sc.gap) * T + 4) <= 32767;
 }
 
 extern "C" int b200_align_plan_create(b200_ctx* ctx, size_t n, const uint64_t* q_off, const uint64_t* t_off,
@@ -361,6 +361,7 @@ extern "C" int b200_align_plan_create(b200_ctx* ctx, size_t n, const uint64_t* q
             uint32_t Qg = 0, Tg = 0;
             for (size_t k = g0; k < g1; ++k) { Qg = std::max(Qg, pairs[short_list[k]].Q); Tg = std::max(Tg, pairs[short_list[k]].T); }
             p->max_T_short = std::max(p->max_T_short, Tg);
+            p->max_Q_short = std::max(p->max_Q_short, Qg);
             const uint64_t words = p->want_cigar ? (uint64_t)div_up(Qg, kShortRows) * Tg * 128 : 0;
             if (cur.count && cur.dir_words + words > budget_words) {
                 p->waves.push_back(cur);
@@ -496,7 +497,7 @@ extern "C" int b200_align_plan_run(b200_align_plan* p, const char* d_q_buf, cons
     uint64_t max_dir_words = 0;
     for (const Wave& w : p->waves) max_dir_words = std::max(max_dir_words, w.dir_words);
     TRY(c->counter.ensure(128));
-    TRY(c->flags.ensure(n));
+    TRY(c->flags.ensure(n + 8));
     TRY(c->end_i.ensure(n * 4));
     TRY(c->end_j.ensure(n * 4));
     if (p->want_cigar) {
@@ -506,20 +507,26 @@ extern "C" int b200_align_plan_run(b200_align_plan* p, const char* d_q_buf, cons
     }
     uint32_t* d_nflag = c->counter.as<uint32_t>() + 16;
 
-    // classify every pair (and build the 2-bit copies the short kernel reads)
+    // classify every pair; short-class pairs also get the 2-bit copies their kernel reads
     prof_begin(c, st, 3);
     if (p->n_short) {
         TRY(c->qpk.ensure((p->q_bytes / 16 + n + p->max_Q / 16 + 72) * 4));
         TRY(c->tpk.ensure((p->t_bytes / 16 + n + p->max_T / 16 + 72) * 4));
         CU(cudaMemsetAsync(d_nflag, 0, 4, st));
-        pack_kernel<<<(unsigned)div_up64(n * 32, 256), 256, 0, st>>>(rb.dq, rb.dt, p->d_pairs.as<PairDesc>(), (uint32_t)n,
-            c->flags.as<uint8_t>(), c->qpk.as<uint32_t>(), c->tpk.as<uint32_t>(), d_nflag);
-    } else {
-        classify_kernel<<<(unsigned)div_up64(n * 32, 256), 256, 0, st>>>(rb.dq, rb.dt, p->d_pairs.as<PairDesc>(), (uint32_t)n,
-                                                                      c->flags.as<uint8_t>());
+        CU(cudaMemsetAsync(c->flags.p, 0, n + 4, st));
+        const uint32_t wpp = std::max(1u, div_up(std::max(p->max_Q_short, p->max_T_short), 16));
+        dim3 grid((unsigned)div_up64((uint64_t)p->n_short * wpp, 256), 2);
+        pack_kernel<<<grid, 256, 0, st>>>(rb.dq, rb.dt, p->d_pairs.as<PairDesc>(), p->d_work.as<uint32_t>(),
+            (uint32_t)p->n_short, wpp, c->flags.as<uint8_t>(), c->qpk.as<uint32_t>(), c->tpk.as<uint32_t>(), d_nflag);
+        c->kernel_launches++;
+    }
+    if (n > p->n_short) {   // the warp-per-pair classes only need the flags
+        classify_kernel<<<(unsigned)div_up64((n - p->n_short) * 32, 256), 256, 0, st>>>(
+            rb.dq, rb.dt, p->d_pairs.as<PairDesc>(), p->d_work.as<uint32_t>() + p->n_short, (uint32_t)(n - p->n_short),
+            c->flags.as<uint8_t>());
+        c->kernel_launches++;
     }
     prof_end(c, st);
-    c->kernel_launches++;
 
     // Pairs planned for the short kernel that turn out not to be pure ACGT fall back to the generic
     // kernel; their direction matrices go behind the wave's own region. Content-dependent, hence
