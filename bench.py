@@ -152,6 +152,7 @@ def main():
     ap.add_argument("--type", type=int, default=0)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--device-only", action="store_true", help="skip the e2e and CPU arms (kernel tuning runs)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -270,6 +271,10 @@ def main():
                                       "emit": emit_ns / prof_steps / 1e6, "other": other_ns / prof_steps / 1e6},
                 "hbm": {"dir_bytes_written_per_step": cells / 4, "hbm_peak_gbs": peaks["hbm_gbs"],
                         "dir_store_gbs": cells / 4 / fill_s / 1e9, "hbm_source": peaks["source"]}}
+
+    if args.device_only:
+        print(json.dumps({"value": value, "ms_per_step": ms_max / args.steps, "roofline": roofline, "clocks": clocks}))
+        return 0
 
     # ---- end-to-end arm: host buffers through the public host C-ABI ---------------------
     hq = torch.from_numpy(qb).pin_memory()

@@ -126,7 +126,7 @@ __device__ __forceinline__ int half_hi(uint32_t v) { return (int)(int16_t)(v >> 
 //     up        Y(i-1,j)   + 4*gap - 1        -> 4H' + 0
 // (H' = H - gap*j) and one signed max gives maximum, tie order and direction tag at once.
 template <int TYPE>
-__global__ void __launch_bounds__(kShortThreads, 8)
+__global__ void __launch_bounds__(kShortThreads, 7)
 fill_short_kernel(const uint32_t* __restrict__ qpk, const uint32_t* __restrict__ tpk,
                   const PairDesc* __restrict__ pairs, const uint32_t* __restrict__ work, uint32_t n_work,
                   const ShortGroup* __restrict__ groups, uint32_t* __restrict__ group_counter,
@@ -188,10 +188,17 @@ fill_short_kernel(const uint32_t* __restrict__ qpk, const uint32_t* __restrict__
             }
             uint32_t top_prev = dup16(4 * (int)(i0 * (uint32_t)K.init) + 1);       // Y(i0, 0)
             // software prefetch: the boundary row and the packed target words are fetched one step early
+            // (two columns early: the compiler sinks the load to the end of the body, so a distance of one
+            // column would leave only a few instructions between issue and use)
             uint32_t top_next = (b == 0) ? dup16(frame * 1 + 1) : my_bnd[(size_t)1 * kWarp];
+            uint32_t top_next2 = (b == 0) ? dup16(frame * 2 + 1) : my_bnd[(size_t)2 * kWarp];
             uint32_t tA_next = twA[0], tB_next = twB[0], tA = 0, tB = 0;
             uint32_t* dcol = dirs ? dirs + dir_off + ((uint64_t)b * Tg * 32 + lane) * 4 : nullptr;
 
+            // hoisted end-cell test: the column at which this block holds cell (Q,T) of either pair
+            const uint32_t jhitA = (TYPE == 0 && liveA && (QA - 1) / R == b) ? TA : 0u;
+            const uint32_t jhitB = (TYPE == 0 && liveB && (QB - 1) / R == b) ? TB : 0u;
+#pragma unroll 2
             for (uint32_t j = 1; j <= Tm; ++j) {
                 if (((j - 1) & 15u) == 0) {
                     tA = tA_next; tB = tB_next;
@@ -203,7 +210,8 @@ fill_short_kernel(const uint32_t* __restrict__ qpk, const uint32_t* __restrict__
                 const uint32_t tabA = K.tab_mis ^ (K.tab_diff << (8 * cA));
                 const uint32_t tabB = K.tab_mis ^ (K.tab_diff << (8 * cB));
                 const uint32_t top = top_next;
-                if (j < Tm) top_next = (b == 0) ? dup16(frame * (int)(j + 1) + 1) : my_bnd[(size_t)(j + 1) * kWarp];
+                top_next = top_next2;
+                if (j + 2 <= Tm) top_next2 = (b == 0) ? dup16(frame * (int)(j + 2) + 1) : my_bnd[(size_t)(j + 2) * kWarp];
                 uint32_t up = top;        // Y of the row above, this column's frame
                 uint32_t dg = top_prev;   // Y(i0, j-1), previous column's frame
                 top_prev = top;
@@ -222,11 +230,11 @@ fill_short_kernel(const uint32_t* __restrict__ qpk, const uint32_t* __restrict__
                     if ((r & 7) == 7) { w[r >> 3] = accZ - accY + 0x55555555u; accZ = 0; accY = 0; }
                 }
                 if (b + 1 < n_blocks) my_bnd[(size_t)j * kWarp] = up;
-                if (dcol) *reinterpret_cast<uint4*>(dcol + (uint64_t)(j - 1) * 128) = make_uint4(w[0], w[1], w[2], w[3]);
+                // streaming store: the direction matrix is written once and must not evict the boundary rows from L2
+                if (dcol) __stcs(reinterpret_cast<uint4*>(dcol + (uint64_t)(j - 1) * 128), make_uint4(w[0], w[1], w[2], w[3]));
                 // end-cell capture (global): the cell (Q, T) of either pair
                 if (TYPE == 0) {
-                    const bool hitA = liveA && j == TA && (QA - 1) / R == b;
-                    const bool hitB = liveB && j == TB && (QB - 1) / R == b;
+                    const bool hitA = j == jhitA, hitB = j == jhitB;
                     if (hitA || hitB) {
                         const uint32_t rA = (QA - 1) % R, rB = (QB - 1) % R;
                         uint32_t vA = Y[0], vB = Y[0];

@@ -450,7 +450,7 @@ static int launch_fill_short(b200_align_plan* p, const Wave& wv, const RunBufs& 
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fill_short_kernel<0>, kShortThreads, 0));
     per_sm = std::max(per_sm, 1);
     const int n_blocks = (int)std::min<uint64_t>((uint64_t)c->sm_count * per_sm, div_up64(n_groups, kShortThreads / 32));
-    const uint32_t bnd_cols = p->max_T_short + 2;
+    const uint32_t bnd_cols = p->max_T_short + 4;
     TRY(c->bnd_short.ensure((size_t)n_blocks * (kShortThreads / 32) * bnd_cols * 32 * sizeof(uint32_t)));
     CU(cudaMemsetAsync(c->counter.p, 0, 64, rb.st));
     const ShortConsts K = make_short_consts(p->sc, p->type);
