@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <climits>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -113,6 +114,7 @@ struct b200_ctx {
     int64_t dir_budget_bytes = 48ll << 30;
     int64_t force_generic = 0;
     int64_t chunk_pairs = 0;
+    b200_align_plan* host_plan = nullptr;   // recycled by the host-buffer entry points
     int64_t profile = 0;   // 1 = bracket kernels with CUDA events (adds a sync per run)
     // counters
     int64_t kernel_launches = 0, h2d_bytes = 0, d2h_bytes = 0;
@@ -179,9 +181,11 @@ extern "C" int b200_ctx_create(int device, b200_ctx** out) {
     return B200_OK;
 }
 
+extern "C" void b200_align_plan_destroy(b200_align_plan* p);
 extern "C" void b200_ctx_destroy(b200_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
+    if (c->host_plan) { b200_align_plan_destroy(c->host_plan); c->host_plan = nullptr; }
     if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
     for (auto& sp : c->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     for (auto e : c->event_pool) cudaEventDestroy(e);
@@ -259,8 +263,54 @@ struct b200_align_plan {
     std::vector<PairDesc> h_pairs;     // kept for the non-ACGT fallback (content is only known at run time)
     std::vector<uint32_t> h_order;
     bool patched = false;              // d_pairs currently holds run-specific fallback descriptors
+    bool uniform = false;              // every pair has the same (Q,T): descriptors were built on the device
+    uint32_t uQ = 0, uT = 0;
+    uint64_t u_qbase = 0, u_tbase = 0;
     DevBuf d_pairs, d_work, d_groups, d_fix_work;
+
+    void reset() {
+        n = 0; cells = cigar_bound = run_slots = q_bytes = t_bytes = 0;
+        max_T = max_Q = max_T_short = max_Q_short = 0; n_short = 0;
+        waves.clear(); h_pairs.clear(); h_order.clear(); patched = false; uniform = false;
+    }
 };
+
+// Uniform batches (every pair the same Q x T, e.g. fixed-length short reads): the descriptors are an
+// affine function of the pair index, so they are generated on the device instead of being built on
+// the host and copied (48 B per pair).
+__global__ void build_uniform_plan_kernel(uint32_t n, uint32_t Q, uint32_t T, uint64_t q_base, uint64_t t_base,
+                                          uint64_t words_per_group, PairDesc* __restrict__ pairs,
+                                          uint32_t* __restrict__ work, ShortGroup* __restrict__ groups) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    PairDesc d;
+    d.q_off = q_base + (uint64_t)i * Q;
+    d.t_off = t_base + (uint64_t)i * T;
+    d.dir_off = (uint64_t)(i >> 6) * words_per_group;
+    d.run_off = (uint64_t)i * ((uint64_t)Q + T + 1);
+    d.Q = Q; d.T = T; d.pitch = T;
+    const uint32_t slot = i & 63u;
+    d.klass = kClassShort | ((slot >> 1) << 8) | ((slot & 1u) << 16);
+    pairs[i] = d;
+    work[i] = i;
+    if (slot == 0) groups[i >> 6] = ShortGroup{d.dir_off, T, 0};
+}
+
+static void materialize_uniform_host(b200_align_plan* p) {   // only needed by the non-ACGT fallback
+    if (!p->uniform || !p->h_pairs.empty()) return;
+    const uint64_t wpg = p->want_cigar ? (uint64_t)div_up(p->uQ, kShortRows) * p->uT * 128 : 0;
+    p->h_pairs.resize(p->n);
+    p->h_order.resize(p->n);
+    for (size_t i = 0; i < p->n; ++i) {
+        PairDesc& d = p->h_pairs[i];
+        d.q_off = p->u_qbase + i * p->uQ; d.t_off = p->u_tbase + i * p->uT;
+        d.dir_off = (i >> 6) * wpg; d.run_off = i * ((uint64_t)p->uQ + p->uT + 1);
+        d.Q = p->uQ; d.T = p->uT; d.pitch = p->uT;
+        const uint32_t slot = (uint32_t)(i & 63u);
+        d.klass = kClassShort | ((slot >> 1) << 8) | ((slot & 1u) << 16);
+        p->h_order[i] = (uint32_t)i;
+    }
+}
 
 extern "C" void b200_align_plan_destroy(b200_align_plan* p) {
     if (!p) return;
@@ -291,33 +341,63 @@ static bool short_pair_ok(const Scores& sc, uint32_t Q, uint32_t T) {
     return Q <= 4096 && T <= 4096 && 4l * (((long)Q + T + 2) * mx + std::abs((long)sc.gap) * T + 4) <= 32767;
 }
 
-extern "C" int b200_align_plan_create(b200_ctx* ctx, size_t n, const uint64_t* q_off, const uint64_t* t_off,
-                                      int type, int match, int mismatch, int gap, int want_cigar,
-                                      b200_align_plan** out) {
-    if (!ctx || !out || (n && (!q_off || !t_off))) return fail(B200_E_ARG, "b200_align_plan_create: null argument");
-    *out = nullptr;
+// Fills `p` (fresh or recycled) for a batch. `rebase`: offsets are taken relative to q_off[0] /
+// t_off[0] (the host entry points copy only the referenced byte range to the device).
+static int plan_build(b200_align_plan* p, b200_ctx* ctx, size_t n, const uint64_t* q_off, const uint64_t* t_off,
+                      bool rebase, bool sync, int type, int match, int mismatch, int gap, int want_cigar) {
     if (type < 0 || type > 2) return fail(B200_E_TYPE, "Unknown AlignmentType provided.");
     if (n > 0xfffffff0ull) return fail(B200_E_ARG, "batch too large");
     TRY(set_device(ctx));
-    b200_align_plan* p = new (std::nothrow) b200_align_plan();
-    if (!p) return fail(B200_E_NOMEM, "out of host memory");
+    p->reset();
     p->ctx = ctx; p->n = n; p->type = type; p->sc = Scores{match, mismatch, gap};
     p->want_cigar = want_cigar != 0;
-    p->q_bytes = n ? q_off[n] : 0;
-    p->t_bytes = n ? t_off[n] : 0;
+    const uint64_t qb = (rebase && n) ? q_off[0] : 0, tb = (rebase && n) ? t_off[0] : 0;
+    p->q_bytes = n ? q_off[n] - qb : 0;
+    p->t_bytes = n ? t_off[n] - tb : 0;
+    const bool short_scores = !ctx->force_generic && short_scores_ok(p->sc, type);
+    const uint64_t budget_words = (uint64_t)ctx->dir_budget_bytes / 4;
+
+    // ---- uniform fast path -------------------------------------------------------------------
+    if (n >= 8192 && short_scores) {
+        const uint64_t Q0 = q_off[1] - q_off[0], T0 = t_off[1] - t_off[0];
+        bool uni = q_off[1] >= q_off[0] && t_off[1] >= t_off[0] && Q0 <= 4096 && T0 <= 4096 &&
+                   short_pair_ok(p->sc, (uint32_t)Q0, (uint32_t)T0);
+        for (size_t i = 1; uni && i < n; ++i)
+            uni = (q_off[i + 1] - q_off[i] == Q0) & (t_off[i + 1] - t_off[i] == T0);
+        const uint64_t n_groups = div_up64(n, 64);
+        const uint64_t wpg = p->want_cigar ? (uint64_t)div_up((uint32_t)Q0, kShortRows) * T0 * 128 : 0;
+        if (uni && n_groups * wpg <= budget_words) {
+            p->uniform = true; p->uQ = (uint32_t)Q0; p->uT = (uint32_t)T0;
+            p->u_qbase = q_off[0] - qb; p->u_tbase = t_off[0] - tb;
+            p->run_slots = n * (Q0 + T0 + 1);
+            p->cells = n * Q0 * T0;
+            p->cigar_bound = n * std::max<uint64_t>(2, 2 * (Q0 + T0));
+            p->max_T = p->max_T_short = (uint32_t)T0;
+            p->max_Q = p->max_Q_short = (uint32_t)Q0;
+            p->n_short = n;
+            p->waves.push_back(Wave{kClassShort, 0, (uint32_t)n, 0, n_groups * wpg});
+            TRY(p->d_pairs.ensure(n * sizeof(PairDesc)));
+            TRY(p->d_work.ensure(n * sizeof(uint32_t)));
+            TRY(p->d_groups.ensure(n_groups * sizeof(ShortGroup)));
+            build_uniform_plan_kernel<<<(unsigned)div_up64(n, 256), 256, 0, ctx->stream>>>(
+                (uint32_t)n, p->uQ, p->uT, p->u_qbase, p->u_tbase, wpg, p->d_pairs.as<PairDesc>(),
+                p->d_work.as<uint32_t>(), p->d_groups.as<ShortGroup>());
+            ctx->kernel_launches++;
+            CU(cudaGetLastError());
+            if (sync) CU(cudaStreamSynchronize(ctx->stream));   // the run may use a different stream
+            return B200_OK;
+        }
+    }
 
     std::vector<PairDesc>& pairs = p->h_pairs;
     pairs.resize(n);
-    const bool short_scores = !ctx->force_generic && short_scores_ok(p->sc, type);
     std::vector<uint32_t> short_list, generic_list;
     for (size_t i = 0; i < n; ++i) {
         const uint64_t ql = q_off[i + 1] - q_off[i], tl = t_off[i + 1] - t_off[i];
-        if (q_off[i + 1] < q_off[i] || t_off[i + 1] < t_off[i] || ql > 0x3fffffffull || tl > 0x3fffffffull) {
-            delete p;
+        if (q_off[i + 1] < q_off[i] || t_off[i + 1] < t_off[i] || ql > 0x3fffffffull || tl > 0x3fffffffull)
             return fail(B200_E_ARG, "offsets must be non-decreasing and sequences shorter than 2^30");
-        }
         PairDesc& d = pairs[i];
-        d.q_off = q_off[i]; d.t_off = t_off[i];
+        d.q_off = q_off[i] - qb; d.t_off = t_off[i] - tb;
         d.Q = (uint32_t)ql; d.T = (uint32_t)tl;
         d.pitch = (d.T + 3u) & ~3u;
         d.klass = kClassGeneric;
@@ -352,7 +432,6 @@ extern "C" int b200_align_plan_create(b200_ctx* ctx, size_t n, const uint64_t* q
     std::vector<uint32_t>& order = p->h_order;
     order.reserve(n);
     std::vector<ShortGroup> groups;
-    const uint64_t budget_words = (uint64_t)ctx->dir_budget_bytes / 4;
     p->n_short = short_list.size();
     {   // short waves, in whole groups
         Wave cur{kClassShort, 0, 0, 0, 0};
@@ -410,6 +489,18 @@ extern "C" int b200_align_plan_create(b200_ctx* ctx, size_t n, const uint64_t* q
         if (e != cudaSuccess) rc = fail(B200_E_CUDA, std::string("plan upload: ") + cudaGetErrorString(e));
         ctx->h2d_bytes += n * (sizeof(PairDesc) + sizeof(uint32_t));
     }
+    return rc;
+}
+
+extern "C" int b200_align_plan_create(b200_ctx* ctx, size_t n, const uint64_t* q_off, const uint64_t* t_off,
+                                      int type, int match, int mismatch, int gap, int want_cigar,
+                                      b200_align_plan** out) {
+    if (!ctx || !out || (n && (!q_off || !t_off))) return fail(B200_E_ARG, "b200_align_plan_create: null argument");
+    *out = nullptr;
+    b200_align_plan* p = new (std::nothrow) b200_align_plan();
+    if (!p) return fail(B200_E_NOMEM, "out of host memory");
+    p->ctx = ctx;
+    const int rc = plan_build(p, ctx, n, q_off, t_off, false, true, type, match, mismatch, gap, want_cigar);
     if (rc != B200_OK) { b200_align_plan_destroy(p); return rc; }
     *out = p;
     return B200_OK;
@@ -540,6 +631,7 @@ extern "C" int b200_align_plan_run(b200_align_plan* p, const char* d_q_buf, cons
         CU(cudaMemcpyAsync(&n_flagged, d_nflag, 4, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
         if (n_flagged) {
+            materialize_uniform_host(p);
             std::vector<uint8_t> h_flags(n);
             CU(cudaMemcpyAsync(h_flags.data(), c->flags.p, n, cudaMemcpyDeviceToHost, st));
             CU(cudaStreamSynchronize(st));
@@ -567,6 +659,7 @@ extern "C" int b200_align_plan_run(b200_align_plan* p, const char* d_q_buf, cons
             }
         }
         if (!any_fix && p->patched) {
+            materialize_uniform_host(p);
             CU(cudaMemcpyAsync(p->d_pairs.p, p->h_pairs.data(), n * sizeof(PairDesc), cudaMemcpyHostToDevice, st));
             CU(cudaStreamSynchronize(st));
             p->patched = false;
@@ -624,6 +717,21 @@ extern "C" int b200_align_plan_run(b200_align_plan* p, const char* d_q_buf, cons
 }
 
 // ------------------------------------------------------------------ align, host buffers ----
+#include <chrono>
+struct PhaseTrace {   // B200_TRACE=1 prints host-side phase timings of the host-buffer entry points
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    std::string line;
+    PhaseTrace() : on(std::getenv("B200_TRACE") != nullptr), t0(std::chrono::steady_clock::now()) {}
+    void mark(const char* what) {
+        if (!on) return;
+        auto t1 = std::chrono::steady_clock::now();
+        line += std::string(what) + "=" + std::to_string(std::chrono::duration<double, std::milli>(t1 - t0).count()) + "ms ";
+        t0 = t1;
+    }
+    ~PhaseTrace() { if (on) std::fprintf(stderr, "[b200 trace] %s\n", line.c_str()); }
+};
+
 extern "C" int b200_align_batch_packed(b200_ctx* c, size_t n, const char* q_buf, const uint64_t* q_off,
                                        const char* t_buf, const uint64_t* t_off, int type, int match,
                                        int mismatch, int gap, int32_t* score, uint32_t* target_begin,
@@ -638,25 +746,33 @@ extern "C" int b200_align_batch_packed(b200_ctx* c, size_t n, const char* q_buf,
     // rebase offsets so that only the referenced byte ranges are copied
     const uint64_t q0 = q_off[0], q1 = q_off[n], t0 = t_off[0], t1 = t_off[n];
     if (((q1 > q0) && !q_buf) || ((t1 > t0) && !t_buf)) return fail(B200_E_ARG, "null sequence buffer");
-    std::vector<uint64_t> qo(n + 1), to(n + 1);
-    for (size_t i = 0; i <= n; ++i) { qo[i] = q_off[i] - q0; to[i] = t_off[i] - t0; }
-    b200_align_plan* plan = nullptr;
-    TRY(b200_align_plan_create(c, n, qo.data(), to.data(), type, match, mismatch, gap, want_cigar ? 1 : 0, &plan));
-    struct Guard { b200_align_plan* p; ~Guard() { b200_align_plan_destroy(p); } } guard{plan};
-
-    const uint64_t dev_cigar_cap = want_cigar ? std::min<uint64_t>(plan->cigar_bound, std::max<uint64_t>(cigar_cap, 2)) : 0;
+    PhaseTrace tr;
+    // start the sequence upload first; the host-side planning below overlaps the DMA
     TRY(c->d_q.ensure(q1 - q0 + 64));
     TRY(c->d_t.ensure(t1 - t0 + 64));
-    TRY(c->d_score.ensure(n * 4));
-    TRY(c->d_tb.ensure(n * 4));
-    if (want_cigar) { TRY(c->d_cigar.ensure(dev_cigar_cap + 16)); TRY(c->d_cigar_off.ensure((n + 1) * 8)); }
     cudaStream_t st = c->stream;
     if (q1 > q0) CU(cudaMemcpyAsync(c->d_q.p, q_buf + q0, q1 - q0, cudaMemcpyHostToDevice, st));
     if (t1 > t0) CU(cudaMemcpyAsync(c->d_t.p, t_buf + t0, t1 - t0, cudaMemcpyHostToDevice, st));
     c->h2d_bytes += (q1 - q0) + (t1 - t0);
+    tr.mark("enqueue-h2d");
+    if (!c->host_plan) {
+        c->host_plan = new (std::nothrow) b200_align_plan();
+        if (!c->host_plan) return fail(B200_E_NOMEM, "out of host memory");
+        c->host_plan->ctx = c;
+    }
+    b200_align_plan* plan = c->host_plan;   // recycled: its device and host buffers keep their capacity
+    TRY(plan_build(plan, c, n, q_off, t_off, true, false, type, match, mismatch, gap, want_cigar ? 1 : 0));
+    tr.mark("plan");
+
+    const uint64_t dev_cigar_cap = want_cigar ? std::min<uint64_t>(plan->cigar_bound, std::max<uint64_t>(cigar_cap, 2)) : 0;
+    TRY(c->d_score.ensure(n * 4));
+    TRY(c->d_tb.ensure(n * 4));
+    if (want_cigar) { TRY(c->d_cigar.ensure(dev_cigar_cap + 16)); TRY(c->d_cigar_off.ensure((n + 1) * 8)); }
+    if (tr.on) { cudaStreamSynchronize(st); tr.mark("alloc+h2d"); }
     TRY(b200_align_plan_run(plan, c->d_q.as<char>(), c->d_t.as<char>(), c->d_score.as<int32_t>(),
                             c->d_tb.as<uint32_t>(), want_cigar ? c->d_cigar.as<char>() : nullptr,
                             want_cigar ? c->d_cigar_off.as<uint64_t>() : nullptr, dev_cigar_cap, st));
+    if (tr.on) { cudaStreamSynchronize(st); tr.mark("run"); }
     CU(cudaMemcpyAsync(score, c->d_score.p, n * 4, cudaMemcpyDeviceToHost, st));
     c->d2h_bytes += n * 4;
     if (target_begin) { CU(cudaMemcpyAsync(target_begin, c->d_tb.p, n * 4, cudaMemcpyDeviceToHost, st)); c->d2h_bytes += n * 4; }
@@ -669,6 +785,7 @@ extern "C" int b200_align_batch_packed(b200_ctx* c, size_t n, const char* q_buf,
         c->d2h_bytes += (n + 1) * 8 + total;
     }
     CU(cudaStreamSynchronize(st));
+    tr.mark("d2h");
     return B200_OK;
 }
 
