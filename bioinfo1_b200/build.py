@@ -60,6 +60,12 @@ def build_all(verbose=False, force=False):
         if force or _newer(out2, cpp_src + hdrs + [out]):
             _run(["g++", "-O2", "-std=c++17", "-Wall", "-fPIC", "-shared", "-I", INCLUDE, "-o", out2] + cpp_src +
                  ["-L", HERE, "-lb200map", "-Wl,-rpath,$ORIGIN"], verbose)
+    test_src = os.path.join(ROOT, "tests", "cpp", "dropin_test.cpp")
+    if cpp_src and os.path.exists(test_src):
+        exe = os.path.join(ROOT, "tests", "cpp", "dropin_test")
+        if force or _newer(exe, [test_src, lib_path("libteam_b200.so")] + hdrs):
+            _run(["g++", "-O1", "-std=c++17", "-Wall", "-I", INCLUDE, "-o", exe, test_src, "-L", HERE, "-lteam_b200",
+                  "-lb200map", "-Wl,-rpath," + HERE], verbose)
     return out
 
 

@@ -63,3 +63,15 @@ def test_product_does_not_reference_the_oracle():
                 if re.search(r"oracle[/_.]|liboracle|libref", open(os.path.join(dirpath, f), errors="replace").read()):
                     bad.append(f)
     assert not bad, bad
+
+
+def test_cpp_dropin_library_exports_the_reference_symbols():
+    """Itanium-ABI names a caller compiled against the reference headers links to."""
+    import subprocess
+    out = subprocess.run(["nm", "-D", "--defined-only", build.lib_path("libteam_b200.so")], capture_output=True,
+                         text=True, check=True).stdout
+    for sym in ("_ZN4team5AlignEPKcjS1_jNS_13AlignmentTypeEiiiPNSt7__cxx1112basic_stringIcSt11char_traitsIcESaIcEEEPj",
+                "_ZN4team4KMERC1Eb", "_ZN4team4KMER8MinimizeEPKcjjj", "_ZN4team4KMER23GetMinimizerFrequenciesEv",
+                "_ZN4team4KMER19GetUniqueMinimizersEv", "_ZN4team4KMER19SetFrequenciesCountEb",
+                "_ZN4team4KMER23MappSeqCharPointerToBitEPKcj", "_ZN4team4KMER17ReverseComplementERKNSt7__cxx1112basic_stringIcSt11char_traitsIcESaIcEEE"):
+        assert sym in out, sym

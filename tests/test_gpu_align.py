@@ -196,3 +196,11 @@ def test_short_kernel_ragged_lengths_and_fallback(ctx):
     qb2, qo2 = seqgen.pack_arrays(qs2)
     tb2, to2 = seqgen.pack_arrays(ts2)
     _check_packed_vs_oracle(ctx, qb2, qo2, tb2, to2, 0, 3, -2, -4, 11)
+
+
+def test_cpp_dropin_wrappers():
+    """tests/cpp/dropin_test.cpp: a caller written against the reference headers, linked to our library."""
+    import subprocess
+    exe = os.path.join(ROOT, "tests", "cpp", "dropin_test")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "dropin_test: OK" in r.stdout, r.stdout + r.stderr
