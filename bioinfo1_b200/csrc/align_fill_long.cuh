@@ -1,0 +1,263 @@
+// align_fill_long.cuh -- K2: the long-pair DP fill (BASELINE configs 4/5: 8-10 kb reads).
+//
+// One WARP per STRIPE of a pair. A stripe is 32 lanes x 32 rows = 1024 query rows; lane L owns rows
+// [s*1024 + 32L + 1, s*1024 + 32L + 32] and at step t works on column j = t - L + 1, so the warp
+// sweeps anti-diagonal wavefronts: the dependency on the lane above travels by __shfl_up_sync,
+// the dependency on the stripe above through a boundary row in global memory (L2) plus a progress
+// counter, so the stripes of one long pair run concurrently on different warps (and SMs).
+//
+// Arithmetic: the int32 version of align_fill_short.cuh's tagged moving frame (bit-exact
+// restatement of team_alignment.cpp:104-114). Cell value Y = 4*H - 4*gap*j + 1; candidates
+//     diagonal Y(i-1,j-1) + 4(s-gap)+1 -> tag 2,  left Y(i,j-1) -> tag 1,  up Y(i-1,j) + 4gap-1 -> tag 0
+// so one signed max yields maximum, tie order (diagonal > left > up) and direction. Per cell:
+//     PRMT (substitution byte -> sign-extended int32), VIADDMNMX x2, LOP3, IMAD x2
+// = 3 alu-pipe + 2 fma-pipe + 1 PRMT issue slots, with no 16-bit range limit.
+//
+// Direction layout (klass kClassLong): 32 rows x 1 column = two 32-bit words;
+//   word k of (block rb32, column j) = dirs[dir_off + (rb32 * pitch + (j-1)) * 2 + k], pitch even;
+//   row 16k+x of the block sits at bits [2*(15-x), 2*(15-x)+1] as TAG (2 diag, 1 left, 0 up).
+// Each lane stores two columns at a time as one 16-byte vector.
+//
+// Eligibility (capi.cu): pure ACGT content (run-time flags; others fall back to the generic
+// kernel), |4(s-gap)+1| <= 127, type global or semiGlobal.
+#pragma once
+#include "align_fill_short.cuh"
+#include "common.cuh"
+
+namespace b200 {
+
+constexpr int kLongRows = 32;   // rows per lane
+
+struct LongConsts {
+    uint32_t tab_diff, tab_mis;   // byte tables as in ShortConsts
+    int cu;                       // 4*gap - 1
+    uint32_t mask, one, four;     // ~3, 1, 4 passed through the constant bank (see ShortConsts)
+    int gap, init;
+};
+
+__host__ inline LongConsts make_long_consts(const Scores& sc, int type) {
+    LongConsts k;
+    const int sm = 4 * (sc.match - sc.gap) + 1, sx = 4 * (sc.mismatch - sc.gap) + 1;
+    k.tab_diff = ((uint32_t)(uint8_t)(int8_t)sm) ^ ((uint32_t)(uint8_t)(int8_t)sx);
+    k.tab_mis = ((uint32_t)(uint8_t)(int8_t)sx) * 0x01010101u;
+    k.cu = 4 * sc.gap - 1;
+    k.mask = 0xfffffffcu; k.one = 1u; k.four = 4u;
+    k.gap = sc.gap;
+    k.init = (type == 0) ? sc.gap : 0;
+    return k;
+}
+
+// Work unit = one STRIPE of one pair. Stripes are handed out in (pair, stripe) order from an atomic
+// counter, so a long pair is swept by as many warps as it has stripes, pipelined: stripe s+1 trails
+// stripe s by about one chunk of columns. The bottom row of every stripe is parked in its own global
+// row (never reused inside a run, so there is no overwrite hazard) together with a progress counter
+// the consumer polls once per chunk. Forward progress: a stripe only ever waits for the stripe
+// before it in the hand-out order, which is already running on a resident warp.
+struct StripeResult {      // per stripe, reduced per pair by finalize_long_kernel
+    int colbest; uint32_t coli;     // semi: best of the last column inside this stripe (H units), smallest i
+    int rowbest; uint32_t rowj;     // semi: best of row Q (last stripe only), smallest j
+    int final_h; uint32_t pad;      // global: H(Q,T) (last stripe only)
+};
+
+constexpr int kLongChunk = 64;     // columns between progress publications / polls
+
+template <int TYPE>
+__global__ void __launch_bounds__(128)
+fill_long_kernel(const uint32_t* __restrict__ qpk, const uint32_t* __restrict__ tpk,
+                 const PairDesc* __restrict__ pairs, const uint32_t* __restrict__ work, uint32_t n_work,
+                 const uint32_t* __restrict__ task_off, const uint64_t* __restrict__ bnd_off,
+                 uint32_t* __restrict__ work_counter, const uint8_t* __restrict__ flags, LongConsts K,
+                 uint32_t* __restrict__ dirs, int32_t* bnd, uint32_t* progress,
+                 StripeResult* __restrict__ results, uint32_t* __restrict__ stall_flag) {
+    constexpr int R = kLongRows;
+    constexpr int STRIPE = R * kWarp;
+    const int lane = threadIdx.x & 31;
+    const uint32_t MASK = K.mask, ONE = K.one, FOUR = K.four;
+    const int frame = 4 * (K.init - K.gap);   // border row 0 in the moving frame: Y(0,j) = frame*j + 1
+    const uint32_t n_tasks = task_off[n_work];
+
+    for (;;) {
+        uint32_t task = 0;
+        if (lane == 0) task = atomicAdd(work_counter, 1u);
+        task = __shfl_sync(kFull, task, 0);
+        if (task >= n_tasks) break;
+        // which pair owns this stripe: last k with task_off[k] <= task
+        uint32_t lo = 0, hi = n_work;
+        while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (task_off[mid] <= task) lo = mid; else hi = mid; }
+        const uint32_t k = lo, s = task - task_off[k];
+        const uint32_t p = work[k];
+        if (flags[p]) continue;   // not pure ACGT: the generic kernel owns the whole pair
+        const PairDesc pd = pairs[p];
+        const uint32_t Q = pd.Q, T = pd.T;
+        const uint32_t* qw = qpk + (pd.q_off >> 4) + p;
+        const uint32_t* tw_base = tpk + (pd.t_off >> 4) + p;
+        const uint32_t n_stripes = div_up(Q, STRIPE);
+        const uint32_t lq = ((Q - 1) / R) % kWarp, rq = (Q - 1) % R;   // lane / register of row Q
+        const uint32_t row_pitch = T + 4;
+        int32_t* row_out = bnd + bnd_off[k] + (uint64_t)s * row_pitch;
+        const int32_t* row_in = row_out - row_pitch;             // written by stripe s-1 (valid when s > 0)
+        volatile uint32_t* prog_out = progress + task;
+        volatile uint32_t* prog_in = progress + task - 1;
+
+        const uint32_t rows_here = min((uint32_t)STRIPE, Q - s * STRIPE);
+        const uint32_t lanes_used = div_up(rows_here, R);
+        const bool last_stripe = (s + 1 == n_stripes);
+        const uint32_t i0 = s * STRIPE + lane * R;
+        const bool lane_on = (uint32_t)lane < lanes_used;
+        const uint32_t rows_valid = lane_on ? min((uint32_t)R, Q - i0) : 0;
+
+        int colbest = INT_MIN; uint32_t coli = 0;
+        int rowbest = INT_MIN; uint32_t rowj = 0;
+        if (TYPE == 2) {
+            if (s == 0 && lane == 0) { colbest = 0; coli = 0; }               // H(0,T) = 0 comes first
+            if (last_stripe && lane == (int)lq) { rowbest = 0; rowj = 0; }    // H(Q,0) = 0
+        }
+
+        uint32_t sel[R];
+        int Y[R];
+        {
+            const uint32_t q0 = lane_on ? qw[i0 >> 4] : 0u, q1 = lane_on ? qw[(i0 >> 4) + 1] : 0u;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const uint32_t c = ((r < 16 ? q0 : q1) >> (2 * (r & 15))) & 3u;
+                sel[r] = c * 0x1111u + 0x8880u;   // byte0 = tab[c], bytes 1..3 = its sign
+                Y[r] = 4 * (int)((i0 + 1 + r) * (uint32_t)K.init) + 1;   // column 0, frame 0
+            }
+        }
+        int up_prev = 4 * (int)(i0 * (uint32_t)K.init) + 1;   // Y(i0, 0)
+        uint32_t tw = 0, tw_next = lane_on ? tw_base[0] : 0u;
+        int b_next = 0, b_next2 = 0;                          // lane 0: boundary values two columns early
+        uint32_t dw0 = 0, dw1 = 0;                            // direction words of the previous (even) column
+        uint32_t* drow = dirs ? dirs + pd.dir_off + (uint64_t)(s * kWarp + lane) * pd.pitch * 2 : nullptr;
+
+        const uint32_t steps = T + lanes_used - 1;
+        for (uint32_t st0 = 0; st0 < steps; st0 += kLongChunk) {
+            const uint32_t st1 = min(steps, st0 + kLongChunk);
+            if (s > 0) {
+                // lane 0 will read boundary columns up to st1 + 2 during this chunk
+                const uint32_t need = min(T, st1 + 2);
+                if (lane == 0) {
+                    uint32_t spins = 0;
+                    while (*prog_in < need) {
+                        __nanosleep(64);
+                        if (++spins > (1u << 25)) { atomicExch(stall_flag, 1u); break; }   // never hang the device
+                    }
+                    __threadfence();
+                    if (st0 == 0) { b_next = __ldcg(row_in + 1); b_next2 = __ldcg(row_in + min(2u, T)); }
+                }
+                __syncwarp();
+            }
+            for (uint32_t st = st0; st < st1; ++st) {
+                const int j = (int)st - lane + 1;
+                int from_above = __shfl_up_sync(kFull, Y[R - 1], 1);
+                const bool active = lane_on && j >= 1 && j <= (int)T;
+                if (active) {
+                    if (lane == 0) {
+                        if (s == 0) from_above = frame * j + 1;
+                        else {
+                            from_above = b_next; b_next = b_next2;
+                            if ((uint32_t)j + 2 <= T) b_next2 = __ldcg(row_in + j + 2);
+                        }
+                    }
+                    if (((j - 1) & 15) == 0) { tw = tw_next; tw_next = tw_base[((j - 1) >> 4) + 1]; }
+                    const uint32_t c = tw & 3u;
+                    tw >>= 2;
+                    const uint32_t tab = K.tab_mis ^ (K.tab_diff << (8 * c));
+                    int up = from_above, dg = up_prev;
+                    up_prev = from_above;
+                    uint32_t accZ = 0, accY = 0, w0 = 0, w1 = 0;
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        const int S = (int)prmt(tab, 0u, sel[r]);
+                        const int m1 = __viaddmax_s32(dg, S, Y[r]);
+                        const int Z = __viaddmax_s32(up, K.cu, m1);
+                        dg = Y[r];
+                        Y[r] = (int)lop3_and_or((uint32_t)Z, MASK, ONE);
+                        up = Y[r];
+                        accZ = accZ * FOUR + (uint32_t)Z;
+                        accY = accY * FOUR + (uint32_t)Y[r];
+                        if (r == 15) { w0 = accZ - accY + 0x55555555u; accZ = 0; accY = 0; }
+                        if (r == 31) { w1 = accZ - accY + 0x55555555u; }
+                    }
+                    if (lane == kWarp - 1 && !last_stripe) __stcg(row_out + j, Y[R - 1]);
+                    if (TYPE == 2 && last_stripe && lane == (int)lq) {
+                        int yq = Y[0];
+#pragma unroll
+                        for (int r = 1; r < R; ++r) if ((uint32_t)r == rq) yq = Y[r];
+                        const int hq = ((yq - 1) >> 2) + K.gap * j;   // back to H units
+                        if (hq > rowbest) { rowbest = hq; rowj = (uint32_t)j; }
+                    }
+                    if (drow) {
+                        const uint32_t cidx = (uint32_t)(j - 1);
+                        if (cidx & 1u) {
+                            __stcs(reinterpret_cast<uint4*>(drow + (uint64_t)(cidx - 1) * 2), make_uint4(dw0, dw1, w0, w1));
+                        } else if (cidx + 1 == T) {
+                            __stcs(reinterpret_cast<uint2*>(drow + (uint64_t)cidx * 2), make_uint2(w0, w1));
+                        } else { dw0 = w0; dw1 = w1; }
+                    }
+                }
+            }
+            if (!last_stripe && lane == kWarp - 1) {
+                // columns 1 .. st1-31 of the bottom row are written: publish them
+                __threadfence();
+                const int done = (int)st1 - (kWarp - 1);
+                *prog_out = (uint32_t)max(0, min(done, (int)T));
+            }
+        }
+        // column T of this lane's rows is in Y[] (frame T): back to H units for the end-cell rules
+        int final_h = 0;
+        if (TYPE == 0 && last_stripe && lane == (int)lq) {
+            int yq = Y[0];
+#pragma unroll
+            for (int r = 1; r < R; ++r) if ((uint32_t)r == rq) yq = Y[r];
+            final_h = ((yq - 1) >> 2) + K.gap * (int)T;
+        }
+        if (TYPE == 2) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int h = ((Y[r] - 1) >> 2) + K.gap * (int)T;
+                if ((uint32_t)r < rows_valid && h > colbest) { colbest = h; coli = i0 + 1 + r; }
+            }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                const int ob = __shfl_xor_sync(kFull, colbest, o);
+                const uint32_t oi = __shfl_xor_sync(kFull, coli, o);
+                if (ob > colbest || (ob == colbest && oi < coli)) { colbest = ob; coli = oi; }
+            }
+        }
+        final_h = __shfl_sync(kFull, final_h, (int)lq);
+        rowbest = __shfl_sync(kFull, rowbest, (int)lq);
+        rowj = __shfl_sync(kFull, rowj, (int)lq);
+        if (lane == 0) results[task] = StripeResult{colbest, coli, rowbest, rowj, final_h, 0u};
+    }
+}
+
+// One thread per pair of the long class: combine the per-stripe candidates with the reference's
+// tie rules (team_alignment.cpp:117-118, :265-278) and handle pairs without inner cells.
+template <int TYPE>
+__global__ void finalize_long_kernel(const PairDesc* __restrict__ pairs, const uint32_t* __restrict__ work,
+                                     uint32_t n_work, const uint32_t* __restrict__ task_off,
+                                     const uint8_t* __restrict__ flags, const StripeResult* __restrict__ results,
+                                     int init, int32_t* __restrict__ score, uint32_t* __restrict__ end_i,
+                                     uint32_t* __restrict__ end_j) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_work) return;
+    const uint32_t p = work[k];
+    if (flags[p]) return;
+    const uint32_t Q = pairs[p].Q, T = pairs[p].T;
+    if (Q == 0 || T == 0) {
+        if (TYPE == 0) { score[p] = (int)((Q + T) * (uint32_t)init); end_i[p] = Q; end_j[p] = T; }
+        else { score[p] = 0; end_i[p] = 0; end_j[p] = T; }
+        return;
+    }
+    const uint32_t t0 = task_off[k], t1 = task_off[k + 1];
+    if (TYPE == 0) { score[p] = results[t1 - 1].final_h; end_i[p] = Q; end_j[p] = T; return; }
+    int colbest = INT_MIN; uint32_t coli = 0;
+    for (uint32_t t = t0; t < t1; ++t)   // stripes in row order, strict '>' keeps the smallest i
+        if (results[t].colbest > colbest) { colbest = results[t].colbest; coli = results[t].coli; }
+    const StripeResult last = results[t1 - 1];
+    if (last.rowbest > colbest) { score[p] = last.rowbest; end_i[p] = Q; end_j[p] = last.rowj; }
+    else { score[p] = colbest; end_i[p] = coli; end_j[p] = T; }
+}
+
+}  // namespace b200

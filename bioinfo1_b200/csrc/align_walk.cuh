@@ -50,6 +50,7 @@ walk_kernel(const PairDesc* __restrict__ pairs, const uint32_t* __restrict__ wor
     }
     const uint32_t* base = dirs + pd.dir_off;
     const bool is_short = (pd.klass & 0xffu) == kClassShort;
+    const bool is_long = (pd.klass & 0xffu) == kClassLong;
     const uint32_t s_lane = (pd.klass >> 8) & 31u, s_shift = ((pd.klass >> 16) & 1u) * 16u;
     // cache of the last direction word: an 'up' move usually stays inside the same word
     uint32_t cw = 0;
@@ -67,6 +68,10 @@ walk_kernel(const PairDesc* __restrict__ pairs, const uint32_t* __restrict__ wor
             const uint32_t b = (i - 1) >> 5, rr = (i - 1) & 31u;
             at = (((uint64_t)b * pd.pitch + (j - 1)) * 32 + s_lane) * 4 + (rr >> 3);
             sh = s_shift + 2 * (7 - (rr & 7u));
+        } else if (is_long) {   // see align_fill_long.cuh
+            const uint32_t b = (i - 1) >> 5, rr = (i - 1) & 31u;
+            at = ((uint64_t)b * pd.pitch + (j - 1)) * 2 + (rr >> 4);
+            sh = 2 * (15 - (rr & 15u));
         } else {
             const uint32_t rb = (i - 1) / kRowsPerWord, r = (i - 1) % kRowsPerWord;
             at = (uint64_t)rb * pd.pitch + (j - 1);
@@ -74,7 +79,7 @@ walk_kernel(const PairDesc* __restrict__ pairs, const uint32_t* __restrict__ wor
         }
         if (at != cw_at) { cw = __ldg(base + at); cw_at = at; }
         uint32_t code = (cw >> sh) & 3u;
-        if (is_short) code = (code == 3u) ? 3u : 2u - code;   // stored as tag: 2 diag, 1 left, 0 up
+        if (is_short || is_long) code = (code == 3u) ? 3u : 2u - code;   // stored as tag: 2 diag, 1 left, 0 up
         if (TYPE == 1 && code == 3) break;
         push(code, 1);
         if (code == 0) { --i; --j; }

@@ -20,6 +20,7 @@
 
 #include "../../include/b200map.h"
 #include "align_fill_generic.cuh"
+#include "align_fill_long.cuh"
 #include "align_fill_short.cuh"
 #include "align_walk.cuh"
 #include "common.cuh"
@@ -106,7 +107,7 @@ struct b200_ctx {
     int sm_count = 148;
     cudaStream_t stream = nullptr;
     // workspaces shared by every plan run on this context (one run at a time per context)
-    DevBuf dirs, bnd, bnd_short, qpk, tpk, counter, end_i, end_j, runs, n_runs, cigar_len, scan_tmp, flags, total;
+    DevBuf dirs, bnd, bnd_short, progress, stripe_res, qpk, tpk, counter, end_i, end_j, runs, n_runs, cigar_len, scan_tmp, flags, total;
     // staging for the host-buffer entry points
     DevBuf d_q, d_t, d_score, d_tb, d_cigar, d_cigar_off, d_seq, d_hash, d_pos, d_flag;
     HostBuf h_q, h_t, h_off;
@@ -189,7 +190,7 @@ extern "C" void b200_ctx_destroy(b200_ctx* c) {
     if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
     for (auto& sp : c->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     for (auto e : c->event_pool) cudaEventDestroy(e);
-    for (DevBuf* b : {&c->dirs, &c->bnd, &c->bnd_short, &c->qpk, &c->tpk, &c->counter, &c->end_i, &c->end_j, &c->runs, &c->n_runs,
+    for (DevBuf* b : {&c->dirs, &c->bnd, &c->bnd_short, &c->progress, &c->stripe_res, &c->qpk, &c->tpk, &c->counter, &c->end_i, &c->end_j, &c->runs, &c->n_runs,
                       &c->cigar_len, &c->scan_tmp, &c->flags, &c->total, &c->d_q, &c->d_t, &c->d_score, &c->d_tb,
                       &c->d_cigar, &c->d_cigar_off, &c->d_seq, &c->d_hash, &c->d_pos, &c->d_flag})
         b->release();
@@ -258,7 +259,7 @@ struct b200_align_plan {
     bool want_cigar = false;
     uint64_t cells = 0, cigar_bound = 0, run_slots = 0, q_bytes = 0, t_bytes = 0;
     uint32_t max_T = 0, max_Q = 0, max_T_short = 0, max_Q_short = 0;
-    size_t n_short = 0;
+    size_t n_short = 0, n_long = 0;   // the work order is [short..., long..., generic...]
     std::vector<Wave> waves;
     std::vector<PairDesc> h_pairs;     // kept for the non-ACGT fallback (content is only known at run time)
     std::vector<uint32_t> h_order;
@@ -266,11 +267,14 @@ struct b200_align_plan {
     bool uniform = false;              // every pair has the same (Q,T): descriptors were built on the device
     uint32_t uQ = 0, uT = 0;
     uint64_t u_qbase = 0, u_tbase = 0;
-    DevBuf d_pairs, d_work, d_groups, d_fix_work;
+    DevBuf d_pairs, d_work, d_groups, d_fix_work, d_task_off, d_bnd_off;
+    uint64_t max_long_bnd_words = 0;   // boundary rows of the largest long wave
+    uint32_t max_long_tasks = 0;
 
     void reset() {
+        max_long_bnd_words = 0; max_long_tasks = 0;
         n = 0; cells = cigar_bound = run_slots = q_bytes = t_bytes = 0;
-        max_T = max_Q = max_T_short = max_Q_short = 0; n_short = 0;
+        max_T = max_Q = max_T_short = max_Q_short = 0; n_short = n_long = 0;
         waves.clear(); h_pairs.clear(); h_order.clear(); patched = false; uniform = false;
     }
 };
@@ -319,6 +323,8 @@ extern "C" void b200_align_plan_destroy(b200_align_plan* p) {
     p->d_work.release();
     p->d_groups.release();
     p->d_fix_work.release();
+    p->d_task_off.release();
+    p->d_bnd_off.release();
     delete p;
 }
 extern "C" uint64_t b200_align_plan_cells(const b200_align_plan* p) { return p ? p->cells : 0; }
@@ -335,6 +341,17 @@ static bool short_scores_ok(const Scores& sc, int type) {
     const long sm = 4l * ((long)sc.match - sc.gap) + 1, sx = 4l * ((long)sc.mismatch - sc.gap) + 1;
     return fits8((int)sm) && fits8((int)sx) && std::abs((long)sc.gap) < 4000 && std::abs((long)sc.match) < 4000 &&
            std::abs((long)sc.mismatch) < 4000;
+}
+static inline uint64_t long_dir_words(uint32_t Q, uint32_t T) {
+    return (uint64_t)div_up(Q, kLongRows) * ((T + 1u) & ~1u) * 2;
+}
+// The int32 tagged wavefront kernel (align_fill_long.cuh): global / semiGlobal, int8 table entries.
+static bool long_scores_ok(const Scores& sc, int type) {
+    if (type == 1) return false;
+    auto fits8 = [](long v) { return v >= -128 && v <= 127; };
+    const long sm = 4l * ((long)sc.match - sc.gap) + 1, sx = 4l * ((long)sc.mismatch - sc.gap) + 1;
+    return fits8(sm) && fits8(sx) && std::abs((long)sc.gap) < (1 << 20) && std::abs((long)sc.match) < (1 << 20) &&
+           std::abs((long)sc.mismatch) < (1 << 20);
 }
 static bool short_pair_ok(const Scores& sc, uint32_t Q, uint32_t T) {
     const long mx = std::max({std::abs((long)sc.match), std::abs((long)sc.mismatch), std::abs((long)sc.gap), 1l});
@@ -391,7 +408,8 @@ static int plan_build(b200_align_plan* p, b200_ctx* ctx, size_t n, const uint64_
 
     std::vector<PairDesc>& pairs = p->h_pairs;
     pairs.resize(n);
-    std::vector<uint32_t> short_list, generic_list;
+    std::vector<uint32_t> short_list, long_list, generic_list;
+    const bool long_scores = !ctx->force_generic && long_scores_ok(p->sc, type);
     for (size_t i = 0; i < n; ++i) {
         const uint64_t ql = q_off[i + 1] - q_off[i], tl = t_off[i + 1] - t_off[i];
         if (q_off[i + 1] < q_off[i] || t_off[i + 1] < t_off[i] || ql > 0x3fffffffull || tl > 0x3fffffffull)
@@ -409,11 +427,13 @@ static int plan_build(b200_align_plan* p, b200_ctx* ctx, size_t n, const uint64_
         p->max_T = std::max(p->max_T, d.T);
         p->max_Q = std::max(p->max_Q, d.Q);
         if (short_scores && short_pair_ok(p->sc, d.Q, d.T)) short_list.push_back((uint32_t)i);
+        else if (long_scores) long_list.push_back((uint32_t)i);
         else generic_list.push_back((uint32_t)i);
     }
     // thread-per-pair only pays off when there are enough pairs to occupy the machine
     if (short_list.size() < 8192) {
-        generic_list.insert(generic_list.end(), short_list.begin(), short_list.end());
+        std::vector<uint32_t>& dst = long_scores ? long_list : generic_list;
+        dst.insert(dst.end(), short_list.begin(), short_list.end());
         short_list.clear();
     }
     auto cells_of = [&](uint32_t a) { return (uint64_t)pairs[a].Q * pairs[a].T; };
@@ -426,8 +446,10 @@ static int plan_build(b200_align_plan* p, b200_ctx* ctx, size_t n, const uint64_
     if (!is_sorted_desc(short_list, short_key))
         std::stable_sort(short_list.begin(), short_list.end(), [&](uint32_t a, uint32_t b) { return short_key(a) > short_key(b); });
     // warp-per-pair classes: largest first so the dynamic scheduler's tail is made of small pairs
-    if (!is_sorted_desc(generic_list, cells_of))
-        std::stable_sort(generic_list.begin(), generic_list.end(), [&](uint32_t a, uint32_t b) { return cells_of(a) > cells_of(b); });
+    for (std::vector<uint32_t>* lst : {&long_list, &generic_list})
+        if (!is_sorted_desc(*lst, cells_of))
+            std::stable_sort(lst->begin(), lst->end(), [&](uint32_t a, uint32_t b) { return cells_of(a) > cells_of(b); });
+    p->n_long = long_list.size();
 
     std::vector<uint32_t>& order = p->h_order;
     order.reserve(n);
@@ -460,25 +482,54 @@ static int plan_build(b200_align_plan* p, b200_ctx* ctx, size_t n, const uint64_
         }
         if (cur.count) p->waves.push_back(cur);
     }
-    {   // generic waves
-        Wave cur{kClassGeneric, (uint32_t)order.size(), 0, 0, 0};
-        for (uint32_t idx : generic_list) {
+    for (int pass = 0; pass < 2; ++pass) {   // warp-per-pair waves: long class, then generic
+        const uint32_t klass = pass == 0 ? kClassLong : kClassGeneric;
+        Wave cur{klass, (uint32_t)order.size(), 0, 0, 0};
+        for (uint32_t idx : (pass == 0 ? long_list : generic_list)) {
             PairDesc& d = pairs[idx];
-            const uint64_t words = p->want_cigar ? generic_dir_words(d.Q, d.T) : 0;
+            const uint64_t words = !p->want_cigar ? 0 : (pass == 0 ? long_dir_words(d.Q, d.T) : generic_dir_words(d.Q, d.T));
             if (cur.count && cur.dir_words + words > budget_words) {
                 p->waves.push_back(cur);
-                cur = Wave{kClassGeneric, (uint32_t)order.size(), 0, 0, 0};
+                cur = Wave{klass, (uint32_t)order.size(), 0, 0, 0};
             }
+            d.klass = klass;
+            if (pass == 0) d.pitch = (d.T + 1u) & ~1u;
             d.dir_off = cur.dir_words;
-            cur.dir_words += words;
+            cur.dir_words += (words + 3) & ~3ull;
             ++cur.count;
             order.push_back(idx);
         }
         if (cur.count) p->waves.push_back(cur);
     }
 
+    // long class: stripe hand-out tables, one (count+1)-entry slice per wave, at [wave.first + wave#]
+    std::vector<uint32_t> task_off;
+    std::vector<uint64_t> bnd_off;
+    for (Wave& wv : p->waves) {
+        if (wv.klass != kClassLong) continue;
+        wv.first_group = (uint32_t)task_off.size();   // reused as the slice start
+        uint32_t t = 0; uint64_t b = 0;
+        for (uint32_t w = wv.first; w < wv.first + wv.count; ++w) {
+            const PairDesc& d = pairs[order[w]];
+            task_off.push_back(t); bnd_off.push_back(b);
+            const uint32_t ns = (d.Q && d.T) ? div_up(d.Q, kLongRows * kWarp) : 0;
+            t += ns; b += (uint64_t)ns * (d.T + 4);
+        }
+        task_off.push_back(t); bnd_off.push_back(b);
+        p->max_long_tasks = std::max(p->max_long_tasks, t);
+        p->max_long_bnd_words = std::max(p->max_long_bnd_words, b);
+    }
     int rc = p->d_pairs.ensure(std::max<size_t>(1, n) * sizeof(PairDesc));
     if (rc == B200_OK) rc = p->d_work.ensure(std::max<size_t>(1, n) * sizeof(uint32_t));
+    if (rc == B200_OK && !task_off.empty()) {
+        rc = p->d_task_off.ensure(task_off.size() * 4);
+        if (rc == B200_OK) rc = p->d_bnd_off.ensure(bnd_off.size() * 8);
+        if (rc == B200_OK) {
+            cudaError_t e = cudaMemcpyAsync(p->d_task_off.p, task_off.data(), task_off.size() * 4, cudaMemcpyHostToDevice, ctx->stream);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(p->d_bnd_off.p, bnd_off.data(), bnd_off.size() * 8, cudaMemcpyHostToDevice, ctx->stream);
+            if (e != cudaSuccess) rc = fail(B200_E_CUDA, std::string("plan upload: ") + cudaGetErrorString(e));
+        }
+    }
     if (rc == B200_OK) rc = p->d_groups.ensure(std::max<size_t>(1, groups.size()) * sizeof(ShortGroup));
     if (rc == B200_OK && n) {
         cudaError_t e = cudaMemcpyAsync(p->d_pairs.p, pairs.data(), n * sizeof(PairDesc), cudaMemcpyHostToDevice, ctx->stream);
@@ -555,6 +606,39 @@ static int launch_fill_short(b200_align_plan* p, const Wave& wv, const RunBufs& 
     return B200_OK;
 }
 
+static int launch_fill_long(b200_align_plan* p, const Wave& wv, const RunBufs& rb) {
+    b200_ctx* c = p->ctx;
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fill_long_kernel<0>, 128, 0));
+    per_sm = std::max(per_sm, 1);
+    const uint32_t* d_task_off = p->d_task_off.as<uint32_t>() + wv.first_group;
+    const uint64_t* d_bnd_off = p->d_bnd_off.as<uint64_t>() + wv.first_group;
+    // every CTA must be resident: stripes wait (poll) on the stripe handed out just before them
+    const int n_blocks = (int)std::min<uint64_t>((uint64_t)c->sm_count * per_sm, div_up64(std::max(p->max_long_tasks, 1u), 4));
+    TRY(c->bnd.ensure((p->max_long_bnd_words + 8) * sizeof(int32_t)));
+    TRY(c->progress.ensure(((size_t)p->max_long_tasks + 8) * 4));
+    TRY(c->stripe_res.ensure(((size_t)p->max_long_tasks + 8) * sizeof(StripeResult)));
+    CU(cudaMemsetAsync(c->counter.p, 0, 64, rb.st));
+    CU(cudaMemsetAsync(c->counter.as<uint32_t>() + 24, 0, 4, rb.st));
+    CU(cudaMemsetAsync(c->progress.p, 0, ((size_t)p->max_long_tasks + 8) * 4, rb.st));
+    const LongConsts K = make_long_consts(p->sc, p->type);
+    const uint32_t* d_work = p->d_work.as<uint32_t>() + wv.first;
+    prof_begin(c, rb.st, 0);
+#define LONGK(TY)                                                                                                      \
+    fill_long_kernel<TY><<<n_blocks, 128, 0, rb.st>>>(c->qpk.as<uint32_t>(), c->tpk.as<uint32_t>(), p->d_pairs.as<PairDesc>(), \
+        d_work, wv.count, d_task_off, d_bnd_off, c->counter.as<uint32_t>(), c->flags.as<uint8_t>(), K, rb.dirs,        \
+        c->bnd.as<int32_t>(), c->progress.as<uint32_t>(), c->stripe_res.as<StripeResult>(),                            \
+        c->counter.as<uint32_t>() + 24);                                                                               \
+    finalize_long_kernel<TY><<<(unsigned)div_up64(wv.count, 128), 128, 0, rb.st>>>(p->d_pairs.as<PairDesc>(), d_work,  \
+        wv.count, d_task_off, c->flags.as<uint8_t>(), c->stripe_res.as<StripeResult>(), K.init, rb.score,              \
+        c->end_i.as<uint32_t>(), c->end_j.as<uint32_t>())
+    if (p->type == 0) { LONGK(0); } else { LONGK(2); }
+#undef LONGK
+    prof_end(c, rb.st);
+    c->kernel_launches += 2;
+    return B200_OK;
+}
+
 static int launch_walk(b200_align_plan* p, const uint32_t* d_work, uint32_t count, const RunBufs& rb) {
     b200_ctx* c = p->ctx;
     if (!count) return B200_OK;
@@ -600,20 +684,21 @@ extern "C" int b200_align_plan_run(b200_align_plan* p, const char* d_q_buf, cons
 
     // classify every pair; short-class pairs also get the 2-bit copies their kernel reads
     prof_begin(c, st, 3);
-    if (p->n_short) {
+    const size_t n_packed = p->n_short + p->n_long;   // classes that read the 2-bit copies
+    if (n_packed) {
         TRY(c->qpk.ensure((p->q_bytes / 16 + n + p->max_Q / 16 + 72) * 4));
         TRY(c->tpk.ensure((p->t_bytes / 16 + n + p->max_T / 16 + 72) * 4));
         CU(cudaMemsetAsync(d_nflag, 0, 4, st));
         CU(cudaMemsetAsync(c->flags.p, 0, n + 4, st));
-        const uint32_t wpp = std::max(1u, div_up(std::max(p->max_Q_short, p->max_T_short), 16));
-        dim3 grid((unsigned)div_up64((uint64_t)p->n_short * wpp, 256), 2);
+        const uint32_t wpp = std::max(1u, div_up(p->n_long ? std::max(p->max_Q, p->max_T) : std::max(p->max_Q_short, p->max_T_short), 16));
+        dim3 grid((unsigned)div_up64((uint64_t)n_packed * wpp, 256), 2);
         pack_kernel<<<grid, 256, 0, st>>>(rb.dq, rb.dt, p->d_pairs.as<PairDesc>(), p->d_work.as<uint32_t>(),
-            (uint32_t)p->n_short, wpp, c->flags.as<uint8_t>(), c->qpk.as<uint32_t>(), c->tpk.as<uint32_t>(), d_nflag);
+            (uint32_t)n_packed, wpp, c->flags.as<uint8_t>(), c->qpk.as<uint32_t>(), c->tpk.as<uint32_t>(), d_nflag);
         c->kernel_launches++;
     }
-    if (n > p->n_short) {   // the warp-per-pair classes only need the flags
-        classify_kernel<<<(unsigned)div_up64((n - p->n_short) * 32, 256), 256, 0, st>>>(
-            rb.dq, rb.dt, p->d_pairs.as<PairDesc>(), p->d_work.as<uint32_t>() + p->n_short, (uint32_t)(n - p->n_short),
+    if (n > n_packed) {   // the generic class only needs the flags
+        classify_kernel<<<(unsigned)div_up64((n - n_packed) * 32, 256), 256, 0, st>>>(
+            rb.dq, rb.dt, p->d_pairs.as<PairDesc>(), p->d_work.as<uint32_t>() + n_packed, (uint32_t)(n - n_packed),
             c->flags.as<uint8_t>());
         c->kernel_launches++;
     }
@@ -626,7 +711,7 @@ extern "C" int b200_align_plan_run(b200_align_plan* p, const char* d_q_buf, cons
     std::vector<uint64_t> wave_words(p->waves.size());
     for (size_t k = 0; k < p->waves.size(); ++k) wave_words[k] = p->waves[k].dir_words;
     bool any_fix = false;
-    if (p->n_short) {
+    if (n_packed) {
         uint32_t n_flagged = 0;
         CU(cudaMemcpyAsync(&n_flagged, d_nflag, 4, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
@@ -638,7 +723,7 @@ extern "C" int b200_align_plan_run(b200_align_plan* p, const char* d_q_buf, cons
             std::vector<PairDesc> patched;
             for (size_t k = 0; k < p->waves.size(); ++k) {
                 const Wave& wv = p->waves[k];
-                if (wv.klass != kClassShort) continue;
+                if (wv.klass == kClassGeneric) continue;
                 for (uint32_t w = wv.first; w < wv.first + wv.count; ++w) {
                     const uint32_t idx = p->h_order[w];
                     if (!h_flags[idx]) continue;
@@ -672,8 +757,9 @@ extern "C" int b200_align_plan_run(b200_align_plan* p, const char* d_q_buf, cons
     for (size_t k = 0; k < p->waves.size(); ++k) {
         const Wave& wv = p->waves[k];
         const uint32_t* work = p->d_work.as<uint32_t>() + wv.first;
-        if (wv.klass == kClassShort) {
-            TRY(launch_fill_short(p, wv, rb));
+        if (wv.klass != kClassGeneric) {
+            if (wv.klass == kClassShort) TRY(launch_fill_short(p, wv, rb));
+            else TRY(launch_fill_long(p, wv, rb));
             if (!fix[k].empty()) {
                 TRY(p->d_fix_work.ensure(fix[k].size() * 4));
                 CU(cudaMemcpyAsync(p->d_fix_work.p, fix[k].data(), fix[k].size() * 4, cudaMemcpyHostToDevice, st));
@@ -712,6 +798,12 @@ extern "C" int b200_align_plan_run(b200_align_plan* p, const char* d_q_buf, cons
         c->kernel_launches++;
     }
     CU(cudaGetLastError());
+    if (p->n_long) {
+        uint32_t stalled = 0;
+        CU(cudaMemcpyAsync(&stalled, c->counter.as<uint32_t>() + 24, 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        if (stalled) return fail(B200_E_CUDA, "long-pair kernel: a stripe gave up waiting for its predecessor");
+    }
     prof_collect(c, st);
     return B200_OK;
 }
