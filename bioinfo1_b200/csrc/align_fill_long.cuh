@@ -61,6 +61,15 @@ struct StripeResult {      // per stripe, reduced per pair by finalize_long_kern
 
 constexpr int kLongChunk = 64;     // columns between progress publications / polls
 
+__device__ __forceinline__ uint32_t ld_acquire(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 template <int TYPE>
 __global__ void __launch_bounds__(128)
 fill_long_kernel(const uint32_t* __restrict__ qpk, const uint32_t* __restrict__ tpk,
@@ -96,8 +105,8 @@ fill_long_kernel(const uint32_t* __restrict__ qpk, const uint32_t* __restrict__ 
         const uint32_t row_pitch = T + 4;
         int32_t* row_out = bnd + bnd_off[k] + (uint64_t)s * row_pitch;
         const int32_t* row_in = row_out - row_pitch;             // written by stripe s-1 (valid when s > 0)
-        volatile uint32_t* prog_out = progress + task;
-        volatile uint32_t* prog_in = progress + task - 1;
+        uint32_t* prog_out = progress + task;
+        const uint32_t* prog_in = progress + task - 1;
 
         const uint32_t rows_here = min((uint32_t)STRIPE, Q - s * STRIPE);
         const uint32_t lanes_used = div_up(rows_here, R);
@@ -126,39 +135,47 @@ fill_long_kernel(const uint32_t* __restrict__ qpk, const uint32_t* __restrict__ 
         }
         int up_prev = 4 * (int)(i0 * (uint32_t)K.init) + 1;   // Y(i0, 0)
         uint32_t tw = 0, tw_next = lane_on ? tw_base[0] : 0u;
-        int b_next = 0, b_next2 = 0;                          // lane 0: boundary values two columns early
         uint32_t dw0 = 0, dw1 = 0;                            // direction words of the previous (even) column
         uint32_t* drow = dirs ? dirs + pd.dir_off + (uint64_t)(s * kWarp + lane) * pd.pitch * 2 : nullptr;
 
+        // Boundary row of the stripe above: the 64 values a chunk needs are fetched ONE CHUNK EARLY,
+        // coalesced, two per lane, and handed to lane 0 by a shuffle at each step -- no load latency
+        // is ever on the critical path of a step.
+        int nxt0 = 0, nxt1 = 0, cur0 = 0, cur1 = 0;
+        auto wait_for = [&](uint32_t need) {   // stripe above has published at least `need` columns
+            if (lane == 0) {
+                uint32_t spins = 0;
+                while (ld_acquire(prog_in) < need) {
+                    __nanosleep(64);
+                    if (++spins > (1u << 25)) { atomicExch(stall_flag, 1u); break; }   // never hang the device
+                }
+            }
+            __syncwarp();
+        };
+        auto fetch = [&](uint32_t first_col) {   // columns first_col + lane and first_col + 32 + lane
+            const uint32_t c0 = first_col + lane, c1 = c0 + 32;
+            nxt0 = c0 <= T ? __ldcg(row_in + c0) : 0;
+            nxt1 = c1 <= T ? __ldcg(row_in + c1) : 0;
+        };
         const uint32_t steps = T + lanes_used - 1;
+        if (s > 0) { wait_for(min(T, (uint32_t)kLongChunk)); fetch(1); }
         for (uint32_t st0 = 0; st0 < steps; st0 += kLongChunk) {
             const uint32_t st1 = min(steps, st0 + kLongChunk);
-            if (s > 0) {
-                // lane 0 will read boundary columns up to st1 + 2 during this chunk
-                const uint32_t need = min(T, st1 + 2);
-                if (lane == 0) {
-                    uint32_t spins = 0;
-                    while (*prog_in < need) {
-                        __nanosleep(64);
-                        if (++spins > (1u << 25)) { atomicExch(stall_flag, 1u); break; }   // never hang the device
-                    }
-                    __threadfence();
-                    if (st0 == 0) { b_next = __ldcg(row_in + 1); b_next2 = __ldcg(row_in + min(2u, T)); }
-                }
-                __syncwarp();
+            cur0 = nxt0; cur1 = nxt1;
+            if (s > 0 && st0 + kLongChunk < T) {   // lane 0 still has columns beyond this chunk
+                wait_for(min(T, st0 + 2 * kLongChunk));
+                fetch(st0 + kLongChunk + 1);
             }
+#pragma unroll 2
             for (uint32_t st = st0; st < st1; ++st) {
                 const int j = (int)st - lane + 1;
-                int from_above = __shfl_up_sync(kFull, Y[R - 1], 1);
+                const int above = __shfl_up_sync(kFull, Y[R - 1], 1);
+                const uint32_t src = st - st0;
+                const int bval = (s == 0) ? frame * (int)(st + 1) + 1
+                                          : __shfl_sync(kFull, src < 32 ? cur0 : cur1, (int)(src & 31u));
+                const int from_above = lane == 0 ? bval : above;
                 const bool active = lane_on && j >= 1 && j <= (int)T;
                 if (active) {
-                    if (lane == 0) {
-                        if (s == 0) from_above = frame * j + 1;
-                        else {
-                            from_above = b_next; b_next = b_next2;
-                            if ((uint32_t)j + 2 <= T) b_next2 = __ldcg(row_in + j + 2);
-                        }
-                    }
                     if (((j - 1) & 15) == 0) { tw = tw_next; tw_next = tw_base[((j - 1) >> 4) + 1]; }
                     const uint32_t c = tw & 3u;
                     tw >>= 2;
@@ -198,10 +215,9 @@ fill_long_kernel(const uint32_t* __restrict__ qpk, const uint32_t* __restrict__ 
                 }
             }
             if (!last_stripe && lane == kWarp - 1) {
-                // columns 1 .. st1-31 of the bottom row are written: publish them
-                __threadfence();
+                // columns 1 .. st1-31 of the bottom row are written (all by this lane): publish them
                 const int done = (int)st1 - (kWarp - 1);
-                *prog_out = (uint32_t)max(0, min(done, (int)T));
+                st_release(prog_out, (uint32_t)max(0, min(done, (int)T)));
             }
         }
         // column T of this lane's rows is in Y[] (frame T): back to H units for the end-cell rules
