@@ -141,6 +141,97 @@ def cpu_arm(args, qb, qo, tb, to, typ, threads, budget_s, kind_pref="reference")
     return chk, n, cells, one_step
 
 
+def extra_workloads(ctx, capi, torch, dev, peaks):
+    """Secondary, device-resident measurements on rank 0 (not the headline): the long-pair kernels on
+    ONT-like pairs (BASELINE configs 4/5 shapes, bounded counts) and MinimizeBatch (config 3 shape)."""
+    import ctypes as C
+    import seqgen
+    L = capi.lib()
+    res = {}
+    st = torch.cuda.current_stream()
+
+    def run_align(tag, qs, ts, typ, steps=3):
+        qb, qo = seqgen.pack_arrays(qs)
+        tb, to = seqgen.pack_arrays(ts)
+        n = len(qs)
+        d_q, d_t = torch.from_numpy(qb).to(dev), torch.from_numpy(tb).to(dev)
+        plan = C.c_void_p()
+        capi.check(L.b200_align_plan_create(ctx.h, n, qo.ctypes.data, to.ctypes.data, typ, 1, -1, -1, 1, C.byref(plan)))
+        cells = int(L.b200_align_plan_cells(plan))
+        cap = int(L.b200_align_plan_cigar_bound(plan))
+        d_s = torch.empty(n, dtype=torch.int32, device=dev)
+        d_b = torch.empty(n, dtype=torch.int32, device=dev)
+        d_c = torch.empty(cap, dtype=torch.uint8, device=dev)
+        d_o = torch.empty(n + 1, dtype=torch.int64, device=dev)
+
+        def step():
+            capi.check(L.b200_align_plan_run(plan, d_q.data_ptr(), d_t.data_ptr(), d_s.data_ptr(), d_b.data_ptr(),
+                                             d_c.data_ptr(), d_o.data_ptr(), cap, st.cuda_stream))
+        for _ in range(2):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        for _ in range(steps):
+            step()
+        e1.record(st)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        ctx.set_option("profile", 1); ctx.set_option("reset_counters", 1)
+        step()
+        torch.cuda.synchronize()
+        fill_ms = ctx.counter("fill_ns") / 1e6
+        walk_ms = ctx.counter("walk_ns") / 1e6
+        ctx.set_option("profile", 0)
+        L.b200_align_plan_destroy(plan)
+        ops = 11 if typ == 1 else 9
+        res[tag] = {"pairs": n, "cells": cells, "alignment": TYPE_NAMES[typ], "gcups": cells / ms / 1e6, "ms_per_step": ms,
+                    "fill_ms": fill_ms, "walk_ms": walk_ms, "fill_gcups": cells / fill_ms / 1e6,
+                    "roofline_frac_int_alu": cells * ops / (fill_ms * 1e-3) / 1e12 / peaks["int_tops"],
+                    "ops_per_cell": ops}
+
+    base_q, base_t = seqgen.ont_like_pairs(4242, 256, mean_len=8000)
+    run_align("semiglobal_ont8kb_2048pairs", (base_q * 8), (base_t * 8), 2)
+    fq, ft = seqgen.ont_like_pairs(4343, 64, fixed=10000)
+    run_align("local_10kbx10kb_512pairs", fq * 8, ft * 8, 1, steps=2)
+
+    # MinimizeBatch, k=15 w=5: a 4.6 Mbp reference (both strands) and ONT-like reads
+    rng = np.random.default_rng(1)
+    ref = seqgen.random_dna(rng, 4_600_000)
+    reads, _ = seqgen.ont_like_pairs(2, 256, mean_len=8000)
+    reads = reads * 16
+    for tag, seqs in (("minimize_ref_4.6Mbp_x2", [ref, ref[::-1].copy()]), ("minimize_4096_ont_reads", reads)):
+        buf, off = seqgen.pack_arrays(seqs)
+        d_buf = torch.from_numpy(buf).to(dev)
+        plan = C.c_void_p()
+        capi.check(L.b200_min_plan_create(ctx.h, len(seqs), off.ctypes.data, 15, 5, None, C.byref(plan)))
+        tot = int(L.b200_min_plan_tuples(plan))
+        d_h = torch.empty(tot, dtype=torch.int32, device=dev)
+        d_p = torch.empty(tot, dtype=torch.int32, device=dev)
+        d_f = torch.empty(tot, dtype=torch.uint8, device=dev)
+
+        def mstep():
+            capi.check(L.b200_min_plan_run(plan, d_buf.data_ptr(), d_h.data_ptr(), d_p.data_ptr(), d_f.data_ptr(),
+                                           st.cuda_stream))
+        for _ in range(3):
+            mstep()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        for _ in range(10):
+            mstep()
+        e1.record(st)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        bases = int(off[-1])
+        alg_bytes = bases + 9 * tot
+        L.b200_min_plan_destroy(plan)
+        res[tag] = {"bases": bases, "tuples": tot, "ms": ms, "gbases_per_s": bases / ms / 1e6,
+                    "hbm_gbs": alg_bytes / ms / 1e6, "roofline_frac_hbm": alg_bytes / ms / 1e6 / peaks["hbm_gbs"],
+                    "algorithmic_bytes": alg_bytes}
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -153,6 +244,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--device-only", action="store_true", help="skip the e2e and CPU arms (kernel tuning runs)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary workloads (configs 3/4/5 shapes)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -326,6 +418,11 @@ def main():
         sc, tbeg, _ = chk.align_batch(qb, qo[:2049], tb, to[:2049], args.type)
         assert np.array_equal(sc, h_score.numpy()[:2048]), "GPU scores differ from the CPU reference"
     L.b200_align_plan_destroy(plan)
+    if rank == 0 and not args.no_extra:
+        try:
+            out["extra"] = extra_workloads(ctx, capi, torch, dev, peaks)
+        except Exception as e:  # the headline line must survive a failure of the side measurements
+            out["extra"] = {"error": repr(e)}
     if rank == 0:
         print(json.dumps(out))
     if world > 1:

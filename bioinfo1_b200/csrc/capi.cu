@@ -662,7 +662,7 @@ extern "C" int b200_align_plan_run(b200_align_plan* p, const char* d_q_buf, cons
     if (p->want_cigar && (!d_cigar_off || (!d_cigar && cigar_cap))) return fail(B200_E_ARG, "plan wants CIGARs but no buffers given");
     if (!d_score) return fail(B200_E_ARG, "d_score is null");
     TRY(set_device(c));
-    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    cudaStream_t st = (cudaStream_t)stream;   // used as given: 0 is the CUDA default stream
     if (n == 0) {
         if (d_cigar_off) CU(cudaMemsetAsync(d_cigar_off, 0, sizeof(uint64_t), st));
         return B200_OK;
@@ -990,7 +990,7 @@ extern "C" int b200_min_plan_run(b200_min_plan* p, const char* d_buf, uint32_t* 
     if (!d_buf || !d_hash || !d_pos || !d_flag) return fail(B200_E_ARG, "null device buffer");
     b200_ctx* c = p->ctx;
     TRY(set_device(c));
-    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    cudaStream_t st = (cudaStream_t)stream;   // used as given: 0 is the CUDA default stream
     if (p->smem_bytes > 48 * 1024)
         CU(cudaFuncSetAttribute(minimize_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes));
     minimize_kernel<0><<<(unsigned)p->n_tiles, kMinThreads, p->smem_bytes, st>>>(

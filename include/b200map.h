@@ -89,7 +89,7 @@ int b200_align_batch_packed(b200_ctx* ctx, size_t n,
 /* Device-resident path. The plan is built from lengths only (host offsets), owns the
  * per-pair descriptors and the wave schedule, and can be run any number of times on
  * sequences already in HBM. All `d_*` pointers are device memory; `stream` is a
- * cudaStream_t (NULL = the context's own stream). `d_target_begin`, `d_cigar`,
+ * cudaStream_t used as given (0 = the CUDA default stream). `d_target_begin`, `d_cigar`,
  * `d_cigar_off` may be NULL when the plan was created with want_cigar = 0.
  * On return the work is enqueued and, if want_cigar, the total CIGAR byte count has been
  * checked against cigar_cap (that check synchronises `stream` once). */
