@@ -19,7 +19,7 @@
 // Each lane stores two columns at a time as one 16-byte vector.
 //
 // Eligibility (capi.cu): pure ACGT content (run-time flags; others fall back to the generic
-// kernel), |4(s-gap)+1| <= 127, type global or semiGlobal.
+// kernel), |4(s-gap)+1| <= 127. Local alignments take a second, one-stripe pass (locate_long_kernel).
 #pragma once
 #include "align_fill_short.cuh"
 #include "common.cuh"
@@ -117,6 +117,7 @@ fill_long_kernel(const uint32_t* __restrict__ qpk, const uint32_t* __restrict__ 
 
         int colbest = INT_MIN; uint32_t coli = 0;
         int rowbest = INT_MIN; uint32_t rowj = 0;
+        int lbest = INT_MIN;                         // local: best H seen by this lane
         if (TYPE == 2) {
             if (s == 0 && lane == 0) { colbest = 0; coli = 0; }               // H(0,T) = 0 comes first
             if (last_stripe && lane == (int)lq) { rowbest = 0; rowj = 0; }    // H(Q,0) = 0
@@ -183,11 +184,13 @@ fill_long_kernel(const uint32_t* __restrict__ qpk, const uint32_t* __restrict__ 
                     int up = from_above, dg = up_prev;
                     up_prev = from_above;
                     uint32_t accZ = 0, accY = 0, w0 = 0, w1 = 0;
+                    const int clampv = 3 - 4 * K.gap * j;   // local: H = 0 with the stop tag, in this column's frame
 #pragma unroll
                     for (int r = 0; r < R; ++r) {
                         const int S = (int)prmt(tab, 0u, sel[r]);
                         const int m1 = __viaddmax_s32(dg, S, Y[r]);
-                        const int Z = __viaddmax_s32(up, K.cu, m1);
+                        int Z = __viaddmax_s32(up, K.cu, m1);
+                        if (TYPE == 1) Z = max(Z, clampv);   // clamp at 0 (team_alignment.cpp:185), tag 3 = stop
                         dg = Y[r];
                         Y[r] = (int)lop3_and_or((uint32_t)Z, MASK, ONE);
                         up = Y[r];
@@ -197,6 +200,20 @@ fill_long_kernel(const uint32_t* __restrict__ qpk, const uint32_t* __restrict__ 
                         if (r == 31) { w1 = accZ - accY + 0x55555555u; }
                     }
                     if (lane == kWarp - 1 && !last_stripe) __stcg(row_out + j, Y[R - 1]);
+                    if (TYPE == 1) {   // running maximum (value only; the cell is located by a second pass)
+                        int cm;
+                        if (rows_valid == (uint32_t)R) {
+                            int t8[8];
+#pragma unroll
+                            for (int q4 = 0; q4 < 8; ++q4) t8[q4] = max(max(Y[4 * q4], Y[4 * q4 + 1]), max(Y[4 * q4 + 2], Y[4 * q4 + 3]));
+                            cm = max(max(max(t8[0], t8[1]), max(t8[2], t8[3])), max(max(t8[4], t8[5]), max(t8[6], t8[7])));
+                        } else {
+                            cm = INT_MIN;
+#pragma unroll
+                            for (int r = 0; r < R; ++r) if ((uint32_t)r < rows_valid) cm = max(cm, Y[r]);
+                        }
+                        lbest = max(lbest, ((cm - 1) >> 2) + K.gap * j);
+                    }
                     if (TYPE == 2 && last_stripe && lane == (int)lq) {
                         int yq = Y[0];
 #pragma unroll
@@ -241,6 +258,11 @@ fill_long_kernel(const uint32_t* __restrict__ qpk, const uint32_t* __restrict__ 
                 if (ob > colbest || (ob == colbest && oi < coli)) { colbest = ob; coli = oi; }
             }
         }
+        if (TYPE == 1) {
+#pragma unroll
+            for (int o = 16; o; o >>= 1) lbest = max(lbest, __shfl_xor_sync(kFull, lbest, o));
+            colbest = lbest;   // stripe maximum travels in the colbest slot
+        }
         final_h = __shfl_sync(kFull, final_h, (int)lq);
         rowbest = __shfl_sync(kFull, rowbest, (int)lq);
         rowj = __shfl_sync(kFull, rowj, (int)lq);
@@ -263,10 +285,20 @@ __global__ void finalize_long_kernel(const PairDesc* __restrict__ pairs, const u
     const uint32_t Q = pairs[p].Q, T = pairs[p].T;
     if (Q == 0 || T == 0) {
         if (TYPE == 0) { score[p] = (int)((Q + T) * (uint32_t)init); end_i[p] = Q; end_j[p] = T; }
+        else if (TYPE == 1) { score[p] = 0; end_i[p] = 0; end_j[p] = 0; }
         else { score[p] = 0; end_i[p] = 0; end_j[p] = T; }
         return;
     }
     const uint32_t t0 = task_off[k], t1 = task_off[k + 1];
+    if (TYPE == 1) {
+        int M = INT_MIN; uint32_t sfirst = 0;
+        for (uint32_t t = t0; t < t1; ++t) if (results[t].colbest > M) { M = results[t].colbest; sfirst = t - t0; }
+        score[p] = M;
+        // M == 0: the reference's strict '>' scan keeps the very first cell (team_alignment.cpp:186-192)
+        if (M <= 0) { end_i[p] = 1; end_j[p] = 1; }
+        else { end_i[p] = 0x80000000u | sfirst; end_j[p] = 0; }   // to be resolved by locate_long_kernel
+        return;
+    }
     if (TYPE == 0) { score[p] = results[t1 - 1].final_h; end_i[p] = Q; end_j[p] = T; return; }
     int colbest = INT_MIN; uint32_t coli = 0;
     for (uint32_t t = t0; t < t1; ++t)   // stripes in row order, strict '>' keeps the smallest i
@@ -274,6 +306,107 @@ __global__ void finalize_long_kernel(const PairDesc* __restrict__ pairs, const u
     const StripeResult last = results[t1 - 1];
     if (last.rowbest > colbest) { score[p] = last.rowbest; end_i[p] = Q; end_j[p] = last.rowj; }
     else { score[p] = colbest; end_i[p] = coli; end_j[p] = T; }
+}
+
+// Local alignments, second pass: fill_long_kernel<1> only tracks the VALUE of the maximum; this
+// kernel re-sweeps the first stripe that attains it (one warp per pair, no direction output, the
+// stripe's top boundary row is still in the boundary buffer) and finds the first cell in row-major
+// order whose score equals the maximum -- exactly the cell the reference's running strict '>'
+// comparison keeps (team_alignment.cpp:186-192).
+__global__ void __launch_bounds__(128)
+locate_long_kernel(const uint32_t* __restrict__ qpk, const uint32_t* __restrict__ tpk,
+                   const PairDesc* __restrict__ pairs, const uint32_t* __restrict__ work, uint32_t n_work,
+                   const uint64_t* __restrict__ bnd_off, const uint8_t* __restrict__ flags, LongConsts K,
+                   const int32_t* __restrict__ bnd, const int32_t* __restrict__ score,
+                   uint32_t* __restrict__ end_i, uint32_t* __restrict__ end_j) {
+    constexpr int R = kLongRows;
+    constexpr int STRIPE = R * kWarp;
+    const int lane = threadIdx.x & 31;
+    const uint32_t k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (k >= n_work) return;
+    const uint32_t p = work[k];
+    if (flags[p]) return;
+    const uint32_t marker = end_i[p];
+    if (!(marker & 0x80000000u)) return;
+    const uint32_t s = marker & 0x7fffffffu;
+    const int M = score[p];
+    const PairDesc pd = pairs[p];
+    const uint32_t Q = pd.Q, T = pd.T;
+    const uint32_t* qw = qpk + (pd.q_off >> 4) + p;
+    const uint32_t* tw_base = tpk + (pd.t_off >> 4) + p;
+    const int32_t* row_in = bnd + bnd_off[k] + (uint64_t)s * (T + 4) - (T + 4);
+    const uint32_t MASK = K.mask, ONE = K.one;
+    const int frame = -4 * K.gap;   // local: init = 0
+
+    const uint32_t rows_here = min((uint32_t)STRIPE, Q - s * STRIPE);
+    const uint32_t lanes_used = div_up(rows_here, R);
+    const uint32_t i0 = s * STRIPE + lane * R;
+    const bool lane_on = (uint32_t)lane < lanes_used;
+    const uint32_t rows_valid = lane_on ? min((uint32_t)R, Q - i0) : 0;
+    uint32_t sel[R];
+    int Y[R];
+    {
+        const uint32_t q0 = lane_on ? qw[i0 >> 4] : 0u, q1 = lane_on ? qw[(i0 >> 4) + 1] : 0u;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const uint32_t c = ((r < 16 ? q0 : q1) >> (2 * (r & 15))) & 3u;
+            sel[r] = c * 0x1111u + 0x8880u;
+            Y[r] = 1;
+        }
+    }
+    int up_prev = 1;
+    uint32_t tw = 0, tw_next = lane_on ? tw_base[0] : 0u;
+    uint32_t bi = 0xffffffffu, bj = 0;
+    int nxt0 = 0, nxt1 = 0, cur0 = 0, cur1 = 0;
+    auto fetch = [&](uint32_t first_col) {
+        const uint32_t c0 = first_col + lane, c1 = c0 + 32;
+        nxt0 = c0 <= T ? __ldcg(row_in + c0) : 0;
+        nxt1 = c1 <= T ? __ldcg(row_in + c1) : 0;
+    };
+    const uint32_t steps = T + lanes_used - 1;
+    if (s > 0) fetch(1);
+    for (uint32_t st0 = 0; st0 < steps; st0 += kLongChunk) {
+        const uint32_t st1 = min(steps, st0 + kLongChunk);
+        cur0 = nxt0; cur1 = nxt1;
+        if (s > 0 && st0 + kLongChunk < T) fetch(st0 + kLongChunk + 1);
+        for (uint32_t st = st0; st < st1; ++st) {
+            const int j = (int)st - lane + 1;
+            const int above = __shfl_up_sync(kFull, Y[R - 1], 1);
+            const uint32_t src = st - st0;
+            const int bval = (s == 0) ? frame * (int)(st + 1) + 1
+                                      : __shfl_sync(kFull, src < 32 ? cur0 : cur1, (int)(src & 31u));
+            const int from_above = lane == 0 ? bval : above;
+            const bool active = lane_on && j >= 1 && j <= (int)T;
+            if (active) {
+                if (((j - 1) & 15) == 0) { tw = tw_next; tw_next = tw_base[((j - 1) >> 4) + 1]; }
+                const uint32_t c = tw & 3u;
+                tw >>= 2;
+                const uint32_t tab = K.tab_mis ^ (K.tab_diff << (8 * c));
+                int up = from_above, dg = up_prev;
+                up_prev = from_above;
+                const int clampv = 3 - 4 * K.gap * j;
+                const int targetY = 4 * M - 4 * K.gap * j + 1;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const int S = (int)prmt(tab, 0u, sel[r]);
+                    const int m1 = __viaddmax_s32(dg, S, Y[r]);
+                    int Z = __viaddmax_s32(up, K.cu, m1);
+                    Z = max(Z, clampv);
+                    dg = Y[r];
+                    Y[r] = (int)lop3_and_or((uint32_t)Z, MASK, ONE);
+                    up = Y[r];
+                    const uint32_t i = i0 + 1 + r;
+                    if (Y[r] == targetY && (uint32_t)r < rows_valid && i < bi) { bi = i; bj = (uint32_t)j; }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        const uint32_t oi = __shfl_xor_sync(kFull, bi, o), oj = __shfl_xor_sync(kFull, bj, o);
+        if (oi < bi) { bi = oi; bj = oj; }
+    }
+    if (lane == 0) { end_i[p] = bi; end_j[p] = bj; }
 }
 
 }  // namespace b200

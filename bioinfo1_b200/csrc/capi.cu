@@ -347,7 +347,7 @@ static inline uint64_t long_dir_words(uint32_t Q, uint32_t T) {
 }
 // The int32 tagged wavefront kernel (align_fill_long.cuh): global / semiGlobal, int8 table entries.
 static bool long_scores_ok(const Scores& sc, int type) {
-    if (type == 1) return false;
+    (void)type;
     auto fits8 = [](long v) { return v >= -128 && v <= 127; };
     const long sm = 4l * ((long)sc.match - sc.gap) + 1, sx = 4l * ((long)sc.mismatch - sc.gap) + 1;
     return fits8(sm) && fits8(sx) && std::abs((long)sc.gap) < (1 << 20) && std::abs((long)sc.match) < (1 << 20) &&
@@ -632,7 +632,13 @@ static int launch_fill_long(b200_align_plan* p, const Wave& wv, const RunBufs& r
     finalize_long_kernel<TY><<<(unsigned)div_up64(wv.count, 128), 128, 0, rb.st>>>(p->d_pairs.as<PairDesc>(), d_work,  \
         wv.count, d_task_off, c->flags.as<uint8_t>(), c->stripe_res.as<StripeResult>(), K.init, rb.score,              \
         c->end_i.as<uint32_t>(), c->end_j.as<uint32_t>())
-    if (p->type == 0) { LONGK(0); } else { LONGK(2); }
+    if (p->type == 0) { LONGK(0); } else if (p->type == 2) { LONGK(2); } else {
+        LONGK(1);
+        locate_long_kernel<<<(unsigned)div_up64((uint64_t)wv.count * 32, 128), 128, 0, rb.st>>>(
+            c->qpk.as<uint32_t>(), c->tpk.as<uint32_t>(), p->d_pairs.as<PairDesc>(), d_work, wv.count, d_bnd_off,
+            c->flags.as<uint8_t>(), K, c->bnd.as<int32_t>(), rb.score, c->end_i.as<uint32_t>(), c->end_j.as<uint32_t>());
+        c->kernel_launches++;
+    }
 #undef LONGK
     prof_end(c, rb.st);
     c->kernel_launches += 2;

@@ -204,3 +204,20 @@ def test_cpp_dropin_wrappers():
     exe = os.path.join(ROOT, "tests", "cpp", "dropin_test")
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "dropin_test: OK" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("typ", [0, 1, 2])
+def test_generic_kernel_forced_on_plain_dna(ctx, typ):
+    """The int32 byte-compare kernel is the fallback of every fast path: keep it covered on ACGT input."""
+    rng = np.random.default_rng(31 + typ)
+    qs, ts = [], []
+    for n in (40, 300, 700, 1100):
+        t = seqgen.random_dna(rng, n)
+        qs.append(seqgen.mutate(rng, t, sub=0.04, ins=0.04, dele=0.04).tobytes())
+        ts.append(t.tobytes())
+    ctx.set_option("force_generic", 1)
+    try:
+        _check_batch(ctx, qs, ts, typ)
+    finally:
+        ctx.set_option("force_generic", 0)
+    _check_batch(ctx, qs, ts, typ)   # and the fast path on the same input
