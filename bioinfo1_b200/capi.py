@@ -62,6 +62,11 @@ def lib():
         L.b200_min_plan_out_off.argtypes = [vp]
         L.b200_min_plan_out_off.restype = C.POINTER(u64)
         L.b200_min_plan_run.argtypes = [vp, vp, vp, vp, vp, vp]
+        L.b200_index_build.argtypes = [vp, vp, u64, u32, u32, C.c_double, C.POINTER(vp)]
+        L.b200_index_destroy.argtypes = [vp]
+        L.b200_index_destroy.restype = None
+        L.b200_index_stats.argtypes = [vp, vp]
+        L.b200_map_batch.argtypes = [vp, vp, sz, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, u64]
         _lib = L
     return _lib
 
@@ -154,6 +159,46 @@ class Context:
         h, p, f, ooff = self.minimize_packed(buf, off, k, w, is_fwd)
         return [(h[int(ooff[i]):int(ooff[i + 1])], p[int(ooff[i]):int(ooff[i + 1])], f[int(ooff[i]):int(ooff[i + 1])])
                 for i in range(len(seqs))]
+
+
+MAPPING_DTYPE = np.dtype([("mapped", np.uint32), ("strand_fwd", np.uint32), ("q_begin", np.uint32),
+                          ("q_end", np.uint32), ("t_begin", np.uint32), ("t_end", np.uint32), ("score", np.int32),
+                          ("target_begin", np.uint32)])
+
+
+class Index:
+    """b200_index: the reference's minimizer index (team_mapper.cpp:412-477) resident on the GPU."""
+
+    def __init__(self, ctx, ref: bytes, k=15, w=5, f=0.001):
+        self.ctx = ctx
+        self.h = C.c_void_p()
+        self._ref = np.frombuffer(ref, dtype=np.uint8)
+        check(lib().b200_index_build(ctx.h, self._ref.ctypes.data, len(ref), k, w, float(f), C.byref(self.h)))
+        self.ref_len = len(ref)
+
+    def stats(self):
+        a = np.zeros(6, dtype=np.uint64)
+        check(lib().b200_index_stats(self.h, a.ctypes.data))
+        return a
+
+    def close(self):
+        if self.h:
+            lib().b200_index_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def map_batch(self, reads, fastq_semantics=True, typ=0, match=1, mismatch=-1, gap=-1, want_cigar=True):
+        """list of bytes -> (structured array of MAPPING_DTYPE, list of cigar bytes | None)"""
+        buf, off = pack(reads)
+        n = len(reads)
+        out = np.zeros(max(n, 1), dtype=MAPPING_DTYPE)
+        cap = int(2 * (int(off[-1]) + n) + 64) * 2 if want_cigar else 0
+        cig = np.empty(max(cap, 1), dtype=np.uint8)
+        coff = np.zeros(n + 1, dtype=np.uint64)
+        check(lib().b200_map_batch(self.ctx.h, self.h, n, buf.ctypes.data, off.ctypes.data, 1 if fastq_semantics else 0,
+                                   typ, match, mismatch, gap, 1 if want_cigar else 0, out.ctypes.data,
+                                   cig.ctypes.data if want_cigar else None, coff.ctypes.data if want_cigar else None, cap))
+        cigs = [bytes(cig[int(coff[i]):int(coff[i + 1])]) for i in range(n)] if want_cigar else None
+        return out[:n], cigs
 
 
 def align_batch_pointers(device, queries, targets, typ, match=1, mismatch=-1, gap=-1, want_cigar=True):

@@ -98,8 +98,8 @@ fill_long_kernel(const uint32_t* __restrict__ qpk, const uint32_t* __restrict__ 
         if (flags[p]) continue;   // not pure ACGT: the generic kernel owns the whole pair
         const PairDesc pd = pairs[p];
         const uint32_t Q = pd.Q, T = pd.T;
-        const uint32_t* qw = qpk + (pd.q_off >> 4) + p;
-        const uint32_t* tw_base = tpk + (pd.t_off >> 4) + p;
+        const uint32_t* qw = qpk + pd.qpk_off;
+        const uint32_t* tw_base = tpk + pd.tpk_off;
         const uint32_t n_stripes = div_up(Q, STRIPE);
         const uint32_t lq = ((Q - 1) / R) % kWarp, rq = (Q - 1) % R;   // lane / register of row Q
         const uint32_t row_pitch = T + 4;
@@ -332,8 +332,8 @@ locate_long_kernel(const uint32_t* __restrict__ qpk, const uint32_t* __restrict_
     const int M = score[p];
     const PairDesc pd = pairs[p];
     const uint32_t Q = pd.Q, T = pd.T;
-    const uint32_t* qw = qpk + (pd.q_off >> 4) + p;
-    const uint32_t* tw_base = tpk + (pd.t_off >> 4) + p;
+    const uint32_t* qw = qpk + pd.qpk_off;
+    const uint32_t* tw_base = tpk + pd.tpk_off;
     const int32_t* row_in = bnd + bnd_off[k] + (uint64_t)s * (T + 4) - (T + 4);
     const uint32_t MASK = K.mask, ONE = K.one;
     const int frame = -4 * K.gap;   // local: init = 0

@@ -27,7 +27,7 @@ constexpr int kShortRows = 32;       // rows per register block
 constexpr int kShortThreads = 64;    // 2 warps per CTA, every warp independent
 
 // Sequences packed 2 bits per base, 16 bases per word, base k of a word at bits [2k, 2k+1].
-// Codes: A=0 C=1 G=2 T=3. Pair p's query words start at (q_off >> 4) + p (see pack_kernel).
+// Codes: A=0 C=1 T=2 G=3. Pair p's query words start at PairDesc::qpk_off (see pack_kernel).
 __device__ __forceinline__ uint32_t acgt_code(uint32_t c) { return (c >> 1) & 3u; }  // A=0 C=1 T=2 G=3 on ASCII
 // (ASCII: A=0x41 -> 0, C=0x43 -> 1, G=0x47 -> 3, T=0x54 -> 2; any bijection works for equality.)
 
@@ -58,7 +58,7 @@ pack_kernel(const uint8_t* __restrict__ qbuf, const uint8_t* __restrict__ tbuf,
         other |= !(c == 'A' || c == 'C' || c == 'G' || c == 'T');
         word |= acgt_code(c) << (2 * b);
     }
-    ((which ? tpk + (pd.t_off >> 4) : qpk + (pd.q_off >> 4)) + p)[w] = word;
+    (which ? tpk + pd.tpk_off : qpk + pd.qpk_off)[w] = word;
     if (dash || other) {
         const uint32_t f = (dash ? kFlagDash : 0u) | (other ? kFlagNonACGT : 0u);
         uint32_t* word32 = reinterpret_cast<uint32_t*>(flags + (p & ~3u));
@@ -157,13 +157,13 @@ fill_short_kernel(const uint32_t* __restrict__ qpk, const uint32_t* __restrict__
         if (wa < n_work) {
             pA = work[wa];
             const PairDesc d = pairs[pA];
-            if (flags[pA] == 0) { QA = d.Q; TA = d.T; qwA = qpk + (d.q_off >> 4) + pA; twA = tpk + (d.t_off >> 4) + pA; }
+            if (flags[pA] == 0) { QA = d.Q; TA = d.T; qwA = qpk + d.qpk_off; twA = tpk + d.tpk_off; }
             else pA = 0xffffffffu;   // not pure ACGT: the generic kernel owns it
         }
         if (wb < n_work) {
             pB = work[wb];
             const PairDesc d = pairs[pB];
-            if (flags[pB] == 0) { QB = d.Q; TB = d.T; qwB = qpk + (d.q_off >> 4) + pB; twB = tpk + (d.t_off >> 4) + pB; }
+            if (flags[pB] == 0) { QB = d.Q; TB = d.T; qwB = qpk + d.qpk_off; twB = tpk + d.tpk_off; }
             else pB = 0xffffffffu;
         }
         const bool liveA = QA && TA, liveB = QB && TB;   // has inner cells

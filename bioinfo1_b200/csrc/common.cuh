@@ -20,11 +20,13 @@ struct PairDesc {
     uint64_t t_off;    // byte offset of the target in the target buffer
     uint64_t dir_off;  // word offset of this pair's direction matrix inside the wave buffer
     uint64_t run_off;  // element offset of this pair's run slots inside the run scratch
+    uint64_t qpk_off;  // word offset of the query's 2-bit copy (16 bases per word) in the packed query buffer
+    uint64_t tpk_off;  // same for the target
     uint32_t Q, T;
     uint32_t pitch;    // words per row block
     uint32_t klass;    // bits 0-7 kernel class (kClass*), short class: bits 8-12 lane, bit 16 half
 };
-static_assert(sizeof(PairDesc) == 48, "PairDesc layout");
+static_assert(sizeof(PairDesc) == 64, "PairDesc layout");
 
 constexpr uint32_t kClassGeneric = 0;  // align_fill_generic.cuh layout: word(rb, j) = dirs[dir_off + rb*pitch + j-1]
 constexpr uint32_t kClassShort = 1;    // align_fill_short.cuh layout, pitch = column count of the 64-pair group

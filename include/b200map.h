@@ -132,6 +132,40 @@ const uint64_t* b200_min_plan_out_off(const b200_min_plan* plan); /* host array,
 int b200_min_plan_run(b200_min_plan* plan, const char* d_buf, uint32_t* d_hash, uint32_t* d_pos,
                       uint8_t* d_flag, void* stream);
 
+/* ------------------------------------------------------------------ mapper ("next" rows) ---- */
+
+/* The reference's minimizer index (team_mapper.cpp:412-477): Minimize(reference) and
+ * Minimize(reverse complement), per strand the distinct (hash, position) pairs, optionally without
+ * the `f`-fraction most frequent forward hashes. Built on the GPU (MinimizeBatch + radix sort +
+ * unique); the reference and its reverse complement stay resident in HBM for the Align step.
+ * With f > 0 ties at the ban cut are broken by (count desc, hash asc): the reference's own order
+ * there is implementation-defined (std::sort over unordered_map iteration order, :437-450). */
+typedef struct b200_index b200_index;
+int b200_index_build(b200_ctx* ctx, const char* ref, uint64_t ref_len, uint32_t k, uint32_t w, double f,
+                     b200_index** out);
+void b200_index_destroy(b200_index* index);
+/* what[0..5] = tuples fwd, tuples rev, distinct (hash,pos) fwd, distinct rev, indexed fwd, indexed rev */
+int b200_index_stats(const b200_index* index, uint64_t what[6]);
+
+typedef struct b200_mapping {
+    uint32_t mapped;     /* 0: no chain found (the reference prints nothing for the read) */
+    uint32_t strand_fwd; /* 1 '+', 0 '-' */
+    uint32_t q_begin, q_end; /* inclusive, 0-based, in the read (team_mapper.cpp:653-654) */
+    uint32_t t_begin, t_end; /* inclusive, 0-based, in the chosen strand's coordinates (:655-656) */
+    int32_t score;
+    uint32_t target_begin;
+} b200_mapping;
+
+/* The per-read loop of the reference mapper (team_mapper.cpp:596-700 for FASTA input, :710-790 for
+ * FASTQ input) for a packed batch of reads: Minimize -> remove_duplicates -> seed lookup -> FindLIS
+ * on both strands -> region -> Align. `fastq_semantics` selects the seed-lookup flavour (:716-729
+ * when non-zero; the FASTA flavour :627-638 consults the reverse index only for hashes that are also
+ * in the forward index). `cigar_off` (n+1) / `cigar_buf` may be NULL when want_cigar is 0; unmapped
+ * reads get an empty CIGAR slice. */
+int b200_map_batch(b200_ctx* ctx, const b200_index* index, size_t n, const char* reads_buf,
+                   const uint64_t* reads_off, int fastq_semantics, int type, int match, int mismatch, int gap,
+                   int want_cigar, b200_mapping* out, char* cigar_buf, uint64_t* cigar_off, uint64_t cigar_cap);
+
 #ifdef __cplusplus
 }
 #endif
