@@ -3,6 +3,7 @@ C++ drop-in wrappers. Outputs land next to this file so they travel with gpurun 
 
     libb200map.so   CUDA kernels + the C ABI of include/b200map.h          (csrc/capi.cu)
     libteam_b200.so team::Align / team::KMER drop-in wrappers over the ABI (csrc/team_*.cpp)
+    b200_mapper     the <team>_mapper command line (csrc/b200_mapper.cpp)
 """
 import os
 import shutil
@@ -60,6 +61,12 @@ def build_all(verbose=False, force=False):
         if force or _newer(out2, cpp_src + hdrs + [out]):
             _run(["g++", "-O2", "-std=c++17", "-Wall", "-fPIC", "-shared", "-I", INCLUDE, "-o", out2] + cpp_src +
                  ["-L", HERE, "-lb200map", "-Wl,-rpath,$ORIGIN"], verbose)
+    cli_src = os.path.join(CSRC, "b200_mapper.cpp")
+    if os.path.exists(cli_src):
+        exe = os.path.join(HERE, "b200_mapper")
+        if force or _newer(exe, [cli_src, out] + hdrs):
+            _run(["g++", "-O2", "-std=c++17", "-Wall", "-pthread", "-I", INCLUDE, "-o", exe, cli_src, "-L", HERE, "-lb200map",
+                  "-Wl,-rpath,$ORIGIN"], verbose)
     test_src = os.path.join(ROOT, "tests", "cpp", "dropin_test.cpp")
     if cpp_src and os.path.exists(test_src):
         exe = os.path.join(ROOT, "tests", "cpp", "dropin_test")

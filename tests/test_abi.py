@@ -75,3 +75,18 @@ def test_cpp_dropin_library_exports_the_reference_symbols():
                 "_ZN4team4KMER19GetUniqueMinimizersEv", "_ZN4team4KMER19SetFrequenciesCountEb",
                 "_ZN4team4KMER23MappSeqCharPointerToBitEPKcj", "_ZN4team4KMER17ReverseComplementERKNSt7__cxx1112basic_stringIcSt11char_traitsIcESaIcEEE"):
         assert sym in out, sym
+
+
+def test_cli_help_version_and_usage_errors_without_a_device():
+    import subprocess
+    exe = os.path.join(ROOT, "bioinfo1_b200", "b200_mapper")
+    r = subprocess.run([exe, "--version"], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip() == "toolForGenomeAllignment v3.1.0"
+    r = subprocess.run([exe, "-h"], capture_output=True, text=True)
+    assert r.returncode == 0 and "Usage" in r.stdout and "-k KMER" in r.stdout
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 1 and "Not enough arguments" in r.stderr
+    r = subprocess.run([exe, "only_one_file"], capture_output=True, text=True)
+    assert r.returncode == 1 and "two input files" in r.stderr.lower()
+    r = subprocess.run([exe, "-a", "bogus", "a", "b"], capture_output=True, text=True)
+    assert r.returncode == 1 and "Expected Alignment type" in r.stderr

@@ -86,3 +86,25 @@ def test_gpu_mapper_vs_cpu_oracle_fresh_reads(ctx):
                            t_begin=int(res[i]["t_begin"]), t_end=int(res[i]["t_end"]), score=int(res[i]["score"]), cigar=cigs[i])
                 assert got == exp, (i, f, fastq)
         idx.close()
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+def test_cli_stdout_is_byte_identical_to_the_reference_mapper(case):
+    """bioinfo1_b200/b200_mapper with the reference's own command lines: stdout must match byte for byte."""
+    import subprocess
+    exe = os.path.join(ROOT, "bioinfo1_b200", "b200_mapper")
+    r = subprocess.run([exe] + case["argv"], cwd=GOLD, capture_output=True, timeout=300)
+    assert r.returncode == 0, r.stderr.decode(errors="replace")
+    with open(os.path.join(GOLD, case["name"] + ".paf"), "rb") as f:
+        assert r.stdout == f.read()
+
+
+def test_cli_statistics_go_to_stderr_and_two_gpus_option_is_accepted():
+    import subprocess
+    exe = os.path.join(ROOT, "bioinfo1_b200", "b200_mapper")
+    argv = ["-a", "semiGlobal", "-c", "-f", "0", "-s", "--gpus", "2", "ref.fa", "reads.fq"]
+    r = subprocess.run([exe] + argv, cwd=GOLD, capture_output=True, timeout=300)
+    assert r.returncode == 0
+    with open(os.path.join(GOLD, "synth_fq_semi_c.paf"), "rb") as f:
+        assert r.stdout == f.read()          # stdout carries PAF only
+    assert b"N50 length" in r.stderr and b"Number of distinct minimizers" in r.stderr
