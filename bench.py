@@ -195,9 +195,34 @@ def extra_workloads(ctx, capi, torch, dev, peaks):
     fq, ft = seqgen.ont_like_pairs(4343, 64, fixed=10000)
     run_align("local_10kbx10kb_512pairs", fq * 8, ft * 8, 1, steps=2)
 
-    # MinimizeBatch, k=15 w=5: a 4.6 Mbp reference (both strands) and ONT-like reads
+    # end-to-end mapping (BASELINE config 4 shape, bounded read count): 4.6 Mbp random reference, ONT-like reads
+    # drawn from both strands at ~12 % indel-heavy error; index build timed separately from the per-read pipeline
     rng = np.random.default_rng(1)
     ref = seqgen.random_dna(rng, 4_600_000)
+    comp = bytes.maketrans(b"ACGT", b"TGCA")
+    mreads = []
+    for i in range(512):
+        Lr = int(np.clip(rng.lognormal(np.log(8000) - 0.125, 0.5), 1000, 40000))
+        s0 = int(rng.integers(0, len(ref) - Lr))
+        q = seqgen.mutate(rng, ref[s0:s0 + Lr], sub=0.024, ins=0.048, dele=0.048).tobytes()
+        mreads.append(q.translate(comp)[::-1] if i % 2 else q)
+    mreads = mreads * 4
+    t0 = time.perf_counter()
+    index = capi.Index(ctx, ref.tobytes(), 15, 5, 0.001)
+    torch.cuda.synchronize()
+    t_index = time.perf_counter() - t0
+    index.map_batch(mreads[:64], True, 2, 1, -1, -1, True)   # warm-up
+    t0 = time.perf_counter()
+    mres, _ = index.map_batch(mreads, True, 2, 1, -1, -1, True)
+    torch.cuda.synchronize()
+    t_map = time.perf_counter() - t0
+    res["map_2048_ont_reads_4.6Mbp_ref"] = {
+        "reads": len(mreads), "bases": int(sum(len(r) for r in mreads)), "mapped": int(mres["mapped"].sum()),
+        "index_build_s": t_index, "map_s": t_map, "mapped_reads_per_s": float(mres["mapped"].sum()) / t_map,
+        "note": "host buffers in, PAF fields + CIGAR out (b200_map_batch), semiGlobal, k=15 w=5 f=0.001"}
+    index.close()
+
+    # MinimizeBatch, k=15 w=5: the reference (both strands) and ONT-like reads
     reads, _ = seqgen.ont_like_pairs(2, 256, mean_len=8000)
     reads = reads * 16
     for tag, seqs in (("minimize_ref_4.6Mbp_x2", [ref, ref[::-1].copy()]), ("minimize_4096_ont_reads", reads)):
