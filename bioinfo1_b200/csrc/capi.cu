@@ -119,6 +119,8 @@ struct b200_ctx {
     int64_t force_generic = 0;
     int64_t chunk_pairs = 0;
     b200_align_plan* host_plan = nullptr;   // recycled by the host-buffer entry points
+    cudaStream_t copy_stream = nullptr;     // uploads of the host-buffer entry points (overlap with kernels)
+    std::vector<cudaEvent_t> copy_events;
     int64_t profile = 0;   // 1 = bracket kernels with CUDA events (adds a sync per run)
     // counters
     int64_t kernel_launches = 0, h2d_bytes = 0, d2h_bytes = 0;
@@ -191,6 +193,8 @@ extern "C" void b200_ctx_destroy(b200_ctx* c) {
     cudaSetDevice(c->device);
     if (c->host_plan) { b200_align_plan_destroy(c->host_plan); c->host_plan = nullptr; }
     if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    for (auto e : c->copy_events) cudaEventDestroy(e);
     for (auto& sp : c->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     for (auto e : c->event_pool) cudaEventDestroy(e);
     for (DevBuf* b : {&c->dirs, &c->bnd, &c->bnd_short, &c->progress, &c->stripe_res, &c->qpk, &c->tpk, &c->counter, &c->end_i, &c->end_j, &c->runs, &c->n_runs,
@@ -267,8 +271,10 @@ struct b200_align_plan {
     std::vector<PairDesc> h_pairs;     // kept for the non-ACGT fallback (content is only known at run time)
     std::vector<uint32_t> h_order;
     bool patched = false;              // d_pairs currently holds run-specific fallback descriptors
+    std::vector<cudaEvent_t> wave_events;   // optional, per wave: "this wave's sequence bytes are resident" (host pipeline)
     bool uniform = false;              // every pair has the same (Q,T): descriptors were built on the device
     uint32_t uQ = 0, uT = 0;
+    uint64_t u_groups_per_wave = 1;
     uint64_t u_qbase = 0, u_tbase = 0;
     DevBuf d_pairs, d_work, d_groups, d_fix_work, d_task_off, d_bnd_off;
     uint64_t max_long_bnd_words = 0;   // boundary rows of the largest long wave
@@ -278,7 +284,7 @@ struct b200_align_plan {
         max_long_bnd_words = 0; max_long_tasks = 0;
         n = 0; cells = cigar_bound = run_slots = q_bytes = t_bytes = qpk_words = tpk_words = 0;
         max_T = max_Q = max_T_short = max_Q_short = 0; n_short = n_long = 0;
-        waves.clear(); h_pairs.clear(); h_order.clear(); patched = false; uniform = false;
+        waves.clear(); h_pairs.clear(); h_order.clear(); patched = false; uniform = false; wave_events.clear();
     }
 };
 
@@ -286,14 +292,15 @@ struct b200_align_plan {
 // affine function of the pair index, so they are generated on the device instead of being built on
 // the host and copied (48 B per pair).
 __global__ void build_uniform_plan_kernel(uint32_t n, uint32_t Q, uint32_t T, uint64_t q_base, uint64_t t_base,
-                                          uint64_t words_per_group, PairDesc* __restrict__ pairs,
+                                          uint64_t words_per_group, uint32_t groups_per_wave,
+                                          PairDesc* __restrict__ pairs,
                                           uint32_t* __restrict__ work, ShortGroup* __restrict__ groups) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     PairDesc d;
     d.q_off = q_base + (uint64_t)i * Q;
     d.t_off = t_base + (uint64_t)i * T;
-    d.dir_off = (uint64_t)(i >> 6) * words_per_group;
+    d.dir_off = (uint64_t)((i >> 6) % groups_per_wave) * words_per_group;   // relative to the wave's buffer
     d.run_off = (uint64_t)i * ((uint64_t)Q + T + 1);
     d.qpk_off = (uint64_t)i * (Q / 16 + 2);
     d.tpk_off = (uint64_t)i * (T / 16 + 2);
@@ -313,7 +320,7 @@ static void materialize_uniform_host(b200_align_plan* p) {   // only needed by t
     for (size_t i = 0; i < p->n; ++i) {
         PairDesc& d = p->h_pairs[i];
         d.q_off = p->u_qbase + i * p->uQ; d.t_off = p->u_tbase + i * p->uT;
-        d.dir_off = (i >> 6) * wpg; d.run_off = i * ((uint64_t)p->uQ + p->uT + 1);
+        d.dir_off = ((i >> 6) % p->u_groups_per_wave) * wpg; d.run_off = i * ((uint64_t)p->uQ + p->uT + 1);
         d.qpk_off = i * (uint64_t)(p->uQ / 16 + 2); d.tpk_off = i * (uint64_t)(p->uT / 16 + 2);
         d.Q = p->uQ; d.T = p->uT; d.pitch = p->uT;
         const uint32_t slot = (uint32_t)(i & 63u);
@@ -369,7 +376,8 @@ static int plan_finish(b200_align_plan* p, b200_ctx* ctx, bool short_scores, boo
 // Fills `p` (fresh or recycled) for a batch. `rebase`: offsets are taken relative to q_off[0] /
 // t_off[0] (the host entry points copy only the referenced byte range to the device).
 static int plan_build(b200_align_plan* p, b200_ctx* ctx, size_t n, const uint64_t* q_off, const uint64_t* t_off,
-                      bool rebase, bool sync, int type, int match, int mismatch, int gap, int want_cigar) {
+                      bool rebase, bool sync, int type, int match, int mismatch, int gap, int want_cigar,
+                      size_t chunk_pairs = 0) {
     if (type < 0 || type > 2) return fail(B200_E_TYPE, "Unknown AlignmentType provided.");
     if (n > 0xfffffff0ull) return fail(B200_E_ARG, "batch too large");
     TRY(set_device(ctx));
@@ -391,8 +399,11 @@ static int plan_build(b200_align_plan* p, b200_ctx* ctx, size_t n, const uint64_
             uni = (q_off[i + 1] - q_off[i] == Q0) & (t_off[i + 1] - t_off[i] == T0);
         const uint64_t n_groups = div_up64(n, 64);
         const uint64_t wpg = p->want_cigar ? (uint64_t)div_up((uint32_t)Q0, kShortRows) * T0 * 128 : 0;
-        if (uni && n_groups * wpg <= budget_words) {
-            p->uniform = true; p->uQ = (uint32_t)Q0; p->uT = (uint32_t)T0;
+        // uniform batches may be cut into equal chunks (whole 64-pair groups) so that the host entry point can
+        // overlap the upload of chunk c+1 with the kernels of chunk c
+        const uint64_t groups_per_wave = chunk_pairs ? std::max<uint64_t>(1, chunk_pairs / 64) : n_groups;
+        if (uni && std::min(n_groups, groups_per_wave) * wpg <= budget_words) {
+            p->uniform = true; p->uQ = (uint32_t)Q0; p->uT = (uint32_t)T0; p->u_groups_per_wave = groups_per_wave;
             p->u_qbase = q_off[0] - qb; p->u_tbase = t_off[0] - tb;
             p->run_slots = n * (Q0 + T0 + 1);
             p->qpk_words = n * (Q0 / 16 + 2); p->tpk_words = n * (T0 / 16 + 2);
@@ -401,12 +412,16 @@ static int plan_build(b200_align_plan* p, b200_ctx* ctx, size_t n, const uint64_
             p->max_T = p->max_T_short = (uint32_t)T0;
             p->max_Q = p->max_Q_short = (uint32_t)Q0;
             p->n_short = n;
-            p->waves.push_back(Wave{kClassShort, 0, (uint32_t)n, 0, n_groups * wpg});
+            for (uint64_t g0 = 0; g0 < n_groups; g0 += groups_per_wave) {
+                const uint64_t g1 = std::min(n_groups, g0 + groups_per_wave);
+                const uint64_t first = g0 * 64, last = std::min<uint64_t>(n, g1 * 64);
+                p->waves.push_back(Wave{kClassShort, (uint32_t)first, (uint32_t)(last - first), (uint32_t)g0, (g1 - g0) * wpg});
+            }
             TRY(p->d_pairs.ensure(n * sizeof(PairDesc)));
             TRY(p->d_work.ensure(n * sizeof(uint32_t)));
             TRY(p->d_groups.ensure(n_groups * sizeof(ShortGroup)));
             build_uniform_plan_kernel<<<(unsigned)div_up64(n, 256), 256, 0, ctx->stream>>>(
-                (uint32_t)n, p->uQ, p->uT, p->u_qbase, p->u_tbase, wpg, p->d_pairs.as<PairDesc>(),
+                (uint32_t)n, p->uQ, p->uT, p->u_qbase, p->u_tbase, wpg, (uint32_t)groups_per_wave, p->d_pairs.as<PairDesc>(),
                 p->d_work.as<uint32_t>(), p->d_groups.as<ShortGroup>());
             ctx->kernel_launches++;
             CU(cudaGetLastError());
@@ -713,89 +728,82 @@ extern "C" int b200_align_plan_run(b200_align_plan* p, const char* d_q_buf, cons
     }
     uint32_t* d_nflag = c->counter.as<uint32_t>() + 16;
 
-    // classify every pair; short-class pairs also get the 2-bit copies their kernel reads
-    prof_begin(c, st, 3);
     const size_t n_packed = p->n_short + p->n_long;   // classes that read the 2-bit copies
     if (n_packed) {
         TRY(c->qpk.ensure((p->qpk_words + p->max_Q / 16 + 72) * 4));
         TRY(c->tpk.ensure((p->tpk_words + p->max_T / 16 + 72) * 4));
-        CU(cudaMemsetAsync(d_nflag, 0, 4, st));
         CU(cudaMemsetAsync(c->flags.p, 0, n + 4, st));
-        const uint32_t wpp = std::max(1u, div_up(p->n_long ? std::max(p->max_Q, p->max_T) : std::max(p->max_Q_short, p->max_T_short), 16));
-        dim3 grid((unsigned)div_up64((uint64_t)n_packed * wpp, 256), 2);
-        pack_kernel<<<grid, 256, 0, st>>>(rb.dq, rb.dt, p->d_pairs.as<PairDesc>(), p->d_work.as<uint32_t>(),
-            (uint32_t)n_packed, wpp, c->flags.as<uint8_t>(), c->qpk.as<uint32_t>(), c->tpk.as<uint32_t>(), d_nflag);
-        c->kernel_launches++;
     }
-    if (n > n_packed) {   // the generic class only needs the flags
-        classify_kernel<<<(unsigned)div_up64((n - n_packed) * 32, 256), 256, 0, st>>>(
-            rb.dq, rb.dt, p->d_pairs.as<PairDesc>(), p->d_work.as<uint32_t>() + n_packed, (uint32_t)(n - n_packed),
-            c->flags.as<uint8_t>());
-        c->kernel_launches++;
-    }
-    prof_end(c, st);
-
-    // Pairs planned for the short kernel that turn out not to be pure ACGT fall back to the generic
-    // kernel; their direction matrices go behind the wave's own region. Content-dependent, hence
-    // decided here (one 4-byte read-back) and not in the plan.
-    std::vector<std::vector<uint32_t>> fix(p->waves.size());
-    std::vector<uint64_t> wave_words(p->waves.size());
-    for (size_t k = 0; k < p->waves.size(); ++k) wave_words[k] = p->waves[k].dir_words;
-    bool any_fix = false;
-    if (n_packed) {
-        uint32_t n_flagged = 0;
-        CU(cudaMemcpyAsync(&n_flagged, d_nflag, 4, cudaMemcpyDeviceToHost, st));
+    if (p->patched) {   // a previous run (other content) left fallback descriptors behind
+        materialize_uniform_host(p);
+        CU(cudaMemcpyAsync(p->d_pairs.p, p->h_pairs.data(), n * sizeof(PairDesc), cudaMemcpyHostToDevice, st));
         CU(cudaStreamSynchronize(st));
-        if (n_flagged) {
-            materialize_uniform_host(p);
-            std::vector<uint8_t> h_flags(n);
-            CU(cudaMemcpyAsync(h_flags.data(), c->flags.p, n, cudaMemcpyDeviceToHost, st));
-            CU(cudaStreamSynchronize(st));
-            std::vector<PairDesc> patched;
-            for (size_t k = 0; k < p->waves.size(); ++k) {
-                const Wave& wv = p->waves[k];
-                if (wv.klass == kClassGeneric) continue;
-                for (uint32_t w = wv.first; w < wv.first + wv.count; ++w) {
-                    const uint32_t idx = p->h_order[w];
-                    if (!h_flags[idx]) continue;
-                    if (patched.empty()) patched = p->h_pairs;
-                    PairDesc& d = patched[idx];
-                    d.klass = kClassGeneric;
-                    d.pitch = (d.T + 3u) & ~3u;
-                    d.dir_off = (wave_words[k] + 3) & ~3ull;
-                    wave_words[k] = d.dir_off + (p->want_cigar ? generic_dir_words(d.Q, d.T) : 0);
-                    fix[k].push_back(idx);
-                    any_fix = true;
-                }
-            }
-            if (any_fix) {
-                CU(cudaMemcpyAsync(p->d_pairs.p, patched.data(), n * sizeof(PairDesc), cudaMemcpyHostToDevice, st));
-                CU(cudaStreamSynchronize(st));   // `patched` is pageable and about to go out of scope
-                p->patched = true;
-            }
-        }
-        if (!any_fix && p->patched) {
-            materialize_uniform_host(p);
-            CU(cudaMemcpyAsync(p->d_pairs.p, p->h_pairs.data(), n * sizeof(PairDesc), cudaMemcpyHostToDevice, st));
-            CU(cudaStreamSynchronize(st));
-            p->patched = false;
-        }
+        p->patched = false;
     }
-    for (uint64_t w : wave_words) max_dir_words = std::max(max_dir_words, w);
     if (p->want_cigar) TRY(c->dirs.ensure(std::max<uint64_t>(max_dir_words, 4) * 4 + 64));
-    rb.dirs = p->want_cigar ? c->dirs.as<uint32_t>() : nullptr;
+    std::vector<PairDesc> patched;   // run-specific descriptors, only materialised if a fallback is needed
+    std::vector<uint8_t> h_flags;
 
+    // Waves run back to back on `st`. A wave = classify (+ 2-bit pack) -> fill -> traceback walk; when the
+    // host entry point pipelines the upload, wave k first waits for the event that marks its bytes as resident.
     for (size_t k = 0; k < p->waves.size(); ++k) {
         const Wave& wv = p->waves[k];
         const uint32_t* work = p->d_work.as<uint32_t>() + wv.first;
+        if (k < p->wave_events.size() && p->wave_events[k]) CU(cudaStreamWaitEvent(st, p->wave_events[k], 0));
+        std::vector<uint32_t> fix;   // pairs of this wave that must fall back to the generic kernel
+        uint64_t wave_words = wv.dir_words;
+        prof_begin(c, st, 3);
+        if (wv.klass != kClassGeneric) {
+            CU(cudaMemsetAsync(d_nflag, 0, 4, st));
+            const uint32_t wpp = std::max(1u, div_up(wv.klass == kClassLong ? std::max(p->max_Q, p->max_T)
+                                                                           : std::max(p->max_Q_short, p->max_T_short), 16));
+            dim3 grid((unsigned)div_up64((uint64_t)wv.count * wpp, 256), 2);
+            pack_kernel<<<grid, 256, 0, st>>>(rb.dq, rb.dt, p->d_pairs.as<PairDesc>(), work, wv.count, wpp,
+                                              c->flags.as<uint8_t>(), c->qpk.as<uint32_t>(), c->tpk.as<uint32_t>(), d_nflag);
+        } else {
+            classify_kernel<<<(unsigned)div_up64((uint64_t)wv.count * 32, 256), 256, 0, st>>>(
+                rb.dq, rb.dt, p->d_pairs.as<PairDesc>(), work, wv.count, c->flags.as<uint8_t>());
+        }
+        prof_end(c, st);
+        c->kernel_launches++;
+        if (wv.klass != kClassGeneric) {
+            // Pairs planned for a 2-bit kernel that turn out not to be pure ACGT fall back to the generic kernel;
+            // their direction matrices go behind the wave's own region. Content-dependent, hence decided here
+            // (one 4-byte read-back per wave) and not in the plan.
+            uint32_t n_flagged = 0;
+            CU(cudaMemcpyAsync(&n_flagged, d_nflag, 4, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            if (n_flagged) {
+                materialize_uniform_host(p);
+                h_flags.resize(n);
+                CU(cudaMemcpyAsync(h_flags.data(), c->flags.p, n, cudaMemcpyDeviceToHost, st));
+                CU(cudaStreamSynchronize(st));
+                if (patched.empty()) patched = p->h_pairs;
+                for (uint32_t w = wv.first; w < wv.first + wv.count; ++w) {
+                    const uint32_t idx = p->h_order[w];
+                    if (!h_flags[idx]) continue;
+                    PairDesc& d = patched[idx];
+                    d.klass = kClassGeneric;
+                    d.pitch = (d.T + 3u) & ~3u;
+                    d.dir_off = (wave_words + 3) & ~3ull;
+                    wave_words = d.dir_off + (p->want_cigar ? generic_dir_words(d.Q, d.T) : 0);
+                    fix.push_back(idx);
+                }
+                CU(cudaMemcpyAsync(p->d_pairs.p, patched.data(), n * sizeof(PairDesc), cudaMemcpyHostToDevice, st));
+                CU(cudaStreamSynchronize(st));
+                p->patched = true;
+                if (p->want_cigar) TRY(c->dirs.ensure(std::max<uint64_t>(wave_words, 4) * 4 + 64));
+            }
+        }
+        rb.dirs = p->want_cigar ? c->dirs.as<uint32_t>() : nullptr;
         if (wv.klass != kClassGeneric) {
             if (wv.klass == kClassShort) TRY(launch_fill_short(p, wv, rb));
             else TRY(launch_fill_long(p, wv, rb));
-            if (!fix[k].empty()) {
-                TRY(p->d_fix_work.ensure(fix[k].size() * 4));
-                CU(cudaMemcpyAsync(p->d_fix_work.p, fix[k].data(), fix[k].size() * 4, cudaMemcpyHostToDevice, st));
+            if (!fix.empty()) {
+                TRY(p->d_fix_work.ensure(fix.size() * 4));
+                CU(cudaMemcpyAsync(p->d_fix_work.p, fix.data(), fix.size() * 4, cudaMemcpyHostToDevice, st));
                 CU(cudaStreamSynchronize(st));
-                TRY(launch_fill_generic(p, p->d_fix_work.as<uint32_t>(), (uint32_t)fix[k].size(), rb));
+                TRY(launch_fill_generic(p, p->d_fix_work.as<uint32_t>(), (uint32_t)fix.size(), rb));
             }
         } else {
             TRY(launch_fill_generic(p, work, wv.count, rb));
@@ -870,13 +878,26 @@ extern "C" int b200_align_batch_packed(b200_ctx* c, size_t n, const char* q_buf,
     const uint64_t q0 = q_off[0], q1 = q_off[n], t0 = t_off[0], t1 = t_off[n];
     if (((q1 > q0) && !q_buf) || ((t1 > t0) && !t_buf)) return fail(B200_E_ARG, "null sequence buffer");
     PhaseTrace tr;
-    // start the sequence upload first; the host-side planning below overlaps the DMA
+    // Start the sequence upload first, in kPipe byte slices on a separate copy stream with an event after
+    // each slice: the host-side planning below overlaps the DMA, and the plan's waves (for uniform batches,
+    // equal chunks of pairs) start as soon as the slice holding their last byte has landed.
     TRY(c->d_q.ensure(q1 - q0 + 64));
     TRY(c->d_t.ensure(t1 - t0 + 64));
     cudaStream_t st = c->stream;
-    if (q1 > q0) CU(cudaMemcpyAsync(c->d_q.p, q_buf + q0, q1 - q0, cudaMemcpyHostToDevice, st));
-    if (t1 > t0) CU(cudaMemcpyAsync(c->d_t.p, t_buf + t0, t1 - t0, cudaMemcpyHostToDevice, st));
-    c->h2d_bytes += (q1 - q0) + (t1 - t0);
+    constexpr int kPipe = 8;
+    if (!c->copy_stream) CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    while (c->copy_events.size() < (size_t)kPipe) {
+        cudaEvent_t e; CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        c->copy_events.push_back(e);
+    }
+    const uint64_t qn = q1 - q0, tn = t1 - t0;
+    for (int s = 0; s < kPipe; ++s) {
+        const uint64_t qa = qn * s / kPipe, qb = qn * (s + 1) / kPipe, ta = tn * s / kPipe, tb = tn * (s + 1) / kPipe;
+        if (qb > qa) CU(cudaMemcpyAsync(c->d_q.as<char>() + qa, q_buf + q0 + qa, qb - qa, cudaMemcpyHostToDevice, c->copy_stream));
+        if (tb > ta) CU(cudaMemcpyAsync(c->d_t.as<char>() + ta, t_buf + t0 + ta, tb - ta, cudaMemcpyHostToDevice, c->copy_stream));
+        CU(cudaEventRecord(c->copy_events[s], c->copy_stream));
+    }
+    c->h2d_bytes += qn + tn;
     tr.mark("enqueue-h2d");
     if (!c->host_plan) {
         c->host_plan = new (std::nothrow) b200_align_plan();
@@ -884,7 +905,20 @@ extern "C" int b200_align_batch_packed(b200_ctx* c, size_t n, const char* q_buf,
         c->host_plan->ctx = c;
     }
     b200_align_plan* plan = c->host_plan;   // recycled: its device and host buffers keep their capacity
-    TRY(plan_build(plan, c, n, q_off, t_off, true, false, type, match, mismatch, gap, want_cigar ? 1 : 0));
+    // four chunks: smaller ones start earlier but under-fill the GPU (fill and walk kernels lose efficiency)
+    const size_t chunk_pairs = c->chunk_pairs > 0 ? (size_t)c->chunk_pairs : std::max<size_t>(8192, (n / 4 + 63) & ~(size_t)63);
+    TRY(plan_build(plan, c, n, q_off, t_off, true, false, type, match, mismatch, gap, want_cigar ? 1 : 0, chunk_pairs));
+    // which upload slice does each wave have to wait for
+    plan->wave_events.assign(plan->waves.size(), c->copy_events[kPipe - 1]);
+    if (plan->uniform) {
+        for (size_t k = 0; k < plan->waves.size(); ++k) {
+            const uint64_t last_pair = (uint64_t)plan->waves[k].first + plan->waves[k].count;   // exclusive
+            const uint64_t qe = last_pair * plan->uQ, te = last_pair * plan->uT;                // bytes needed (exclusive)
+            int need = 0;
+            while (need < kPipe - 1 && (qn * (need + 1) / kPipe < qe || tn * (need + 1) / kPipe < te)) ++need;
+            plan->wave_events[k] = c->copy_events[need];
+        }
+    }
     tr.mark("plan");
 
     const uint64_t dev_cigar_cap = want_cigar ? std::min<uint64_t>(plan->cigar_bound, std::max<uint64_t>(cigar_cap, 2)) : 0;
