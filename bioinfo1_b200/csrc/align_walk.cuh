@@ -22,13 +22,18 @@ __device__ __forceinline__ uint32_t dec_digits(uint32_t v) {
     return d;
 }
 
+// `spread` (power of two, 1..32): only every spread-th lane of a warp owns a pair. Small batches of long
+// pairs are latency-bound pointer chases with divergent paths; spreading them over more warps and SMs
+// shortens the critical path, large batches use every lane (spread = 1).
 template <int TYPE>
 __global__ void __launch_bounds__(128)
-walk_kernel(const PairDesc* __restrict__ pairs, const uint32_t* __restrict__ work, uint32_t n_work,
+walk_kernel(const PairDesc* __restrict__ pairs, const uint32_t* __restrict__ work, uint32_t n_work, uint32_t spread,
             const uint32_t* __restrict__ dirs, const uint32_t* __restrict__ end_i,
             const uint32_t* __restrict__ end_j, uint32_t* __restrict__ runs,
             uint32_t* __restrict__ n_runs, uint32_t* __restrict__ cigar_len) {
-    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid % spread) return;
+    const uint32_t w = tid / spread;
     if (w >= n_work) return;
     const uint32_t p = work[w];
     const PairDesc pd = pairs[p];
@@ -49,42 +54,41 @@ walk_kernel(const PairDesc* __restrict__ pairs, const uint32_t* __restrict__ wor
         else if (j == T && i < Q) push(2, Q - i);
     }
     const uint32_t* base = dirs + pd.dir_off;
-    const bool is_short = (pd.klass & 0xffu) == kClassShort;
-    const bool is_long = (pd.klass & 0xffu) == kClassLong;
+    const uint32_t klass = pd.klass & 0xffu;
     const uint32_t s_lane = (pd.klass >> 8) & 31u, s_shift = ((pd.klass >> 16) & 1u) * 16u;
+    const uint64_t pitch = pd.pitch;
     // cache of the last direction word: an 'up' move usually stays inside the same word
     uint32_t cw = 0;
     uint64_t cw_at = ~0ull;
-    for (;;) {
-        if (TYPE == 1) {
-            if (i == 0 || j == 0) break;  // border score is 0
-        } else {
-            if (i == 0) { if (j) push(1, j); break; }   // row 0: parents point left
-            if (j == 0) { push(2, i); break; }          // column 0: parents point up
-        }
+    while (i != 0 && j != 0) {
         uint64_t at;
         uint32_t sh;
-        if (is_short) {   // see align_fill_short.cuh
-            const uint32_t b = (i - 1) >> 5, rr = (i - 1) & 31u;
-            at = (((uint64_t)b * pd.pitch + (j - 1)) * 32 + s_lane) * 4 + (rr >> 3);
-            sh = s_shift + 2 * (7 - (rr & 7u));
-        } else if (is_long) {   // see align_fill_long.cuh
-            const uint32_t b = (i - 1) >> 5, rr = (i - 1) & 31u;
-            at = ((uint64_t)b * pd.pitch + (j - 1)) * 2 + (rr >> 4);
-            sh = 2 * (15 - (rr & 15u));
-        } else {
-            const uint32_t rb = (i - 1) / kRowsPerWord, r = (i - 1) % kRowsPerWord;
-            at = (uint64_t)rb * pd.pitch + (j - 1);
-            sh = 2 * r;
+        const uint32_t i1 = i - 1, j1 = j - 1;
+        if (klass == kClassLong) {            // align_fill_long.cuh: 2 words per (32-row block, column)
+            at = ((uint64_t)(i1 >> 5) * pitch + j1) * 2 + ((i1 >> 4) & 1u);
+            sh = 2 * (15 - (i1 & 15u));
+        } else if (klass == kClassShort) {    // align_fill_short.cuh: uint4 per (32-row block, column, lane)
+            at = (((uint64_t)(i1 >> 5) * pitch + j1) * 32 + s_lane) * 4 + ((i1 >> 3) & 3u);
+            sh = s_shift + 2 * (7 - (i1 & 7u));
+        } else {                              // align_fill_generic.cuh: 1 word per (16-row block, column)
+            at = (uint64_t)(i1 / kRowsPerWord) * pitch + j1;
+            sh = 2 * (i1 % kRowsPerWord);
         }
         if (at != cw_at) { cw = __ldg(base + at); cw_at = at; }
         uint32_t code = (cw >> sh) & 3u;
-        if (is_short || is_long) code = (code == 3u) ? 3u : 2u - code;   // stored as tag: 2 diag, 1 left, 0 up
+        if (klass != kClassGeneric) code = (code == 3u) ? 3u : 2u - code;   // stored as tag: 2 diag, 1 left, 0 up
         if (TYPE == 1 && code == 3) break;
-        push(code, 1);
-        if (code == 0) { --i; --j; }
-        else if (code == 1) { --j; }
-        else { --i; }
+        if (code == cur_op) ++cur_n;
+        else {
+            if (cur_n) { out[nr++] = (cur_n << 2) | cur_op; bytes += dec_digits(cur_n) + 1; }
+            cur_op = code; cur_n = 1;
+        }
+        i -= (code != 1u);   // diagonal and up consume a query row
+        j -= (code != 2u);   // diagonal and left consume a target column
+    }
+    if (TYPE != 1) {   // the borders: row 0 points left ('I'), column 0 points up ('D') (reference :83-92)
+        if (i == 0 && j) push(1, j);
+        else if (j == 0 && i) push(2, i);
     }
     if (cur_n) { out[nr++] = (cur_n << 2) | cur_op; bytes += dec_digits(cur_n) + 1; }
     if (nr == 0) bytes = 2;  // "1\0"

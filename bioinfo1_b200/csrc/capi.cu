@@ -688,9 +688,12 @@ static int launch_fill_long(b200_align_plan* p, const Wave& wv, const RunBufs& r
 static int launch_walk(b200_align_plan* p, const uint32_t* d_work, uint32_t count, const RunBufs& rb) {
     b200_ctx* c = p->ctx;
     if (!count) return B200_OK;
-    const unsigned wb = (unsigned)div_up64(count, 128);
+    // few pairs: give each its own quarter-warp or warp so the divergent pointer chases do not serialise
+    uint32_t spread = 1;
+    while (spread < 32 && (uint64_t)count * spread * 2 <= (uint64_t)c->sm_count * 512) spread *= 2;
+    const unsigned wb = (unsigned)div_up64((uint64_t)count * spread, 128);
     prof_begin(c, rb.st, 1);
-#define WALK(TY) walk_kernel<TY><<<wb, 128, 0, rb.st>>>(p->d_pairs.as<PairDesc>(), d_work, count, rb.dirs, c->end_i.as<uint32_t>(), \
+#define WALK(TY) walk_kernel<TY><<<wb, 128, 0, rb.st>>>(p->d_pairs.as<PairDesc>(), d_work, count, spread, rb.dirs, c->end_i.as<uint32_t>(), \
         c->end_j.as<uint32_t>(), c->runs.as<uint32_t>(), c->n_runs.as<uint32_t>(), c->cigar_len.as<uint32_t>())
     switch (p->type) { case 0: WALK(0); break; case 1: WALK(1); break; default: WALK(2); break; }
 #undef WALK
