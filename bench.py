@@ -59,7 +59,7 @@ def load_peaks():
 
 class ClockSampler:
     """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -67,11 +67,16 @@ class ClockSampler:
         self.index = index
         self.proc = None
         self.lines = []
+        self.t_begin = None   # wall-clock window of interest (set by mark_begin / stop)
+
+    def mark_begin(self):
+        import datetime
+        self.t_begin = datetime.datetime.now()
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "10"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -90,12 +95,21 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        import datetime
+        t_end = datetime.datetime.now()
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
+            if self.t_begin is not None:   # keep only samples taken while the GPU was under our load
+                try:
+                    ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f")
+                    if ts < self.t_begin or ts > t_end:
+                        continue
+                except ValueError:
+                    pass
             try:
                 sm.append(float(f[1])); mx = float(f[2])
             except ValueError:
@@ -319,6 +333,8 @@ def main():
     n = args.pairs
     ctx = capi.Context(local_rank)
     L = capi.lib()
+    sampler = ClockSampler(local_rank)   # nvidia-smi needs ~0.1 s to start: launch it before the uploads
+    sampler.start()
 
     # ---- device-resident arm ---------------------------------------------------------
     d_q = torch.from_numpy(qb).to(dev)
@@ -344,8 +360,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    sampler = ClockSampler(local_rank)   # samples from the warm-up on: the whole window is under load
-    sampler.start()
+    sampler.mark_begin()   # the sampler has been running since start-up; count samples from the warm-up on
     for _ in range(args.warmup):
         step_device()
     barrier()

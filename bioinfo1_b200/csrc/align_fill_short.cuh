@@ -49,14 +49,32 @@ pack_kernel(const uint8_t* __restrict__ qbuf, const uint8_t* __restrict__ tbuf,
     if (w * 16 >= len) return;
     const uint8_t* s = (which ? tbuf + pd.t_off : qbuf + pd.q_off) + w * 16;
     const uint32_t nb = min(16u, len - w * 16);
+    // 16 bases = up to five aligned 32-bit words; realign with funnel shifts (the buffers are padded, so
+    // reading the aligned words around the sequence is safe), then 4 bases per word in parallel.
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(s);
+    const uint32_t* aw = reinterpret_cast<const uint32_t*>(addr & ~(uintptr_t)3);
+    const uint32_t shb = (uint32_t)(addr & 3u) * 8u;
+    uint32_t raw[5];
+#pragma unroll
+    for (int q = 0; q < 5; ++q) raw[q] = ((uint32_t)q * 4u < (uint32_t)(addr & 3u) + nb) ? __ldg(aw + q) : 0x41414141u;
     uint32_t word = 0;
     bool dash = false, other = false;
 #pragma unroll
-    for (uint32_t b = 0; b < 16; ++b) {
-        const uint32_t c = b < nb ? (uint32_t)s[b] : (uint32_t)'A';
-        dash |= (c == '-');
-        other |= !(c == 'A' || c == 'C' || c == 'G' || c == 'T');
-        word |= acgt_code(c) << (2 * b);
+    for (int q = 0; q < 4; ++q) {
+        uint32_t v = __funnelshift_r(raw[q], raw[q + 1], shb);      // bases 4q .. 4q+3, base 4q in the low byte
+        const uint32_t valid = nb > 4u * q ? min(4u, nb - 4u * q) : 0u;
+        if (valid < 4u) v = (valid == 0u) ? 0x41414141u : ((v & (0xffffffffu >> (8u * (4u - valid)))) | (0x41414141u << (8u * valid)));
+        const uint32_t c4 = (v >> 1) & 0x03030303u;                 // A=0 C=1 T=2 G=3 per byte
+        // valid iff re-encoding the codes gives the bytes back: letters[code] with letters = "ACTG"
+        const uint32_t sel = (c4 & 0x3u) | ((c4 >> 4) & 0x30u) | ((c4 >> 8) & 0x300u) | ((c4 >> 12) & 0x3000u);   // one nibble per base
+        const uint32_t back = __byte_perm(0x47544341u, 0u, sel);
+        if (back != v) {
+            other = true;
+#pragma unroll
+            for (int bb = 0; bb < 4; ++bb) dash |= (((v >> (8 * bb)) & 0xffu) == (uint32_t)'-');
+        }
+        const uint32_t c8 = (c4 | (c4 >> 6) | (c4 >> 12) | (c4 >> 18)) & 0xffu;     // four 2-bit codes
+        word |= c8 << (8 * q);
     }
     (which ? tpk + pd.tpk_off : qpk + pd.qpk_off)[w] = word;
     if (dash || other) {
