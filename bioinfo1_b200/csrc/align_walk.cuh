@@ -5,12 +5,21 @@
 //   :287-302 (semiGlobal), border parents :83-92 (column 0 -> up 'D', row 0 -> left 'I'),
 //   semiGlobal tail pad :306-315, run-length encoding :145-160, empty path => "1\0".
 //
-// Two kernels, one thread per pair:
-//   walk_kernel  follows the directions from the end cell and records the runs it meets
-//                (in walk order, i.e. reversed) as packed (count << 2 | op) words, plus the
-//                byte length of the final CIGAR text;
-//   emit_kernel  (after an exclusive scan of the lengths) prints the runs back to front
-//                into the pair's slice of the CIGAR buffer.
+// Kernels:
+//   walk_kernel       one THREAD per pair (short class: the 64 pairs of a group share their
+//                     direction lines, so neighbouring lanes coalesce): follows the directions
+//                     from the end cell and records the runs it meets (in walk order, i.e.
+//                     reversed) as packed (count << 2 | op) words, plus the byte length of the
+//                     final CIGAR text;
+//   walk_tile_kernel  one WARP per pair (long / generic classes): a traceback is a chain of
+//                     dependent loads, ~1 us each from HBM, so a 16 k-step path costs ~15 ms
+//                     however many pairs run in parallel. The warp instead fetches the whole
+//                     (row block x 32 columns) tile around the current cell with one coalesced
+//                     load into shared memory (128-512 contiguous bytes in the fill kernels'
+//                     layouts), prefetches the three tiles the path can enter next into L2, and
+//                     walks inside the tile from shared memory: one HBM round trip per ~32 steps;
+//   emit_kernel       (after an exclusive scan of the lengths) prints the runs back to front
+//                     into the pair's slice of the CIGAR buffer.
 #pragma once
 #include "common.cuh"
 
@@ -67,6 +76,10 @@ walk_kernel(const PairDesc* __restrict__ pairs, const uint32_t* __restrict__ wor
         if (klass == kClassLong) {            // align_fill_long.cuh: 2 words per (32-row block, column)
             at = ((uint64_t)(i1 >> 5) * pitch + j1) * 2 + ((i1 >> 4) & 1u);
             sh = 2 * (15 - (i1 & 15u));
+        } else if (klass == kClassLong16) {   // align_fill_long16.cuh: 4 words per (64-row block, slot)
+            const uint32_t half = (i1 >> 5) & 1u;
+            at = ((uint64_t)(i1 >> 6) * pitch + j1 + half) * 4 + ((i1 >> 3) & 3u);
+            sh = 16 * half + 2 * (7 - (i1 & 7u));
         } else if (klass == kClassShort) {    // align_fill_short.cuh: uint4 per (32-row block, column, lane)
             at = (((uint64_t)(i1 >> 5) * pitch + j1) * 32 + s_lane) * 4 + ((i1 >> 3) & 3u);
             sh = s_shift + 2 * (7 - (i1 & 7u));
@@ -94,6 +107,118 @@ walk_kernel(const PairDesc* __restrict__ pairs, const uint32_t* __restrict__ wor
     if (nr == 0) bytes = 2;  // "1\0"
     n_runs[p] = nr;
     cigar_len[p] = bytes;
+}
+
+// ---- warp-per-pair tile walker ------------------------------------------------------------
+struct RunWriter {   // the run list under construction (every lane tracks it, lane 0 stores)
+    uint32_t* out;
+    uint32_t nr, bytes, cur_op, cur_n;
+    bool writer;
+    __device__ __forceinline__ void flush() {
+        if (cur_n) { if (writer) out[nr] = (cur_n << 2) | cur_op; ++nr; bytes += dec_digits(cur_n) + 1; }
+    }
+    __device__ __forceinline__ void push(uint32_t op, uint32_t cnt) {
+        if (op == cur_op) { cur_n += cnt; return; }
+        flush();
+        cur_op = op; cur_n = cnt;
+    }
+};
+
+// Tile geometry of a direction layout: 2^RL rows per row block, WPC words per column slot.
+template <uint32_t KLASS> struct TileShape;
+template <> struct TileShape<kClassGeneric> { static constexpr uint32_t RL = 4, WPC = 1; };
+template <> struct TileShape<kClassLong>    { static constexpr uint32_t RL = 5, WPC = 2; };
+template <> struct TileShape<kClassLong16>  { static constexpr uint32_t RL = 6, WPC = 4; };
+
+constexpr int kWalkTileWords = 128;   // shared-memory words per warp (the largest tile: 64 rows x 32 slots)
+
+// Walks from (i, j) until a border (or, local, a stop cell) is reached. All lanes run the same
+// scalar walk on the shared tile; returns with i == 0, j == 0 or the stop cell.
+template <int TYPE, uint32_t KLASS>
+__device__ __forceinline__ void walk_tiles(const PairDesc& pd, const uint32_t* __restrict__ base, uint32_t& i, uint32_t& j,
+                                           uint32_t* tile, RunWriter& rw, int lane) {
+    constexpr uint32_t RL = TileShape<KLASS>::RL, WPC = TileShape<KLASS>::WPC;
+    const uint64_t pitch = pd.pitch;
+    const uint64_t n_rb = ((uint64_t)pd.Q + (1u << RL) - 1) >> RL;
+    const uint64_t last_word = n_rb * pitch * WPC - 1;   // last word of this pair's matrix
+    bool stop = false;
+    while (i != 0 && j != 0 && !stop) {
+        const uint32_t rb = (i - 1) >> RL;
+        const uint32_t cb = (j - 1 + (KLASS == kClassLong16 ? ((i - 1) >> 5) & 1u : 0u)) >> 5;
+        const uint64_t tbase = ((uint64_t)rb * pitch + (uint64_t)cb * 32) * WPC;
+        __syncwarp();
+        if ((uint64_t)cb * 32 + lane < pitch) {
+            const uint32_t* src = base + tbase + (uint32_t)lane * WPC;
+            if (WPC == 1) tile[lane] = __ldg(src);
+            else if (WPC == 2) *reinterpret_cast<uint2*>(tile + 2 * lane) = __ldg(reinterpret_cast<const uint2*>(src));
+            else *reinterpret_cast<uint4*>(tile + 4 * lane) = __ldg(reinterpret_cast<const uint4*>(src));
+        }
+        // the path leaves this tile to the left, upwards or diagonally: pull those tiles towards L2 now
+        if (lane < 3 * (int)(WPC + 1)) {
+            const int which = lane / (int)(WPC + 1), line = lane % (int)(WPC + 1);
+            const bool go_left = which != 1, go_up = which != 0;
+            if ((!go_left || cb > 0) && (!go_up || rb > 0)) {
+                const uint64_t nb = ((uint64_t)(rb - (go_up ? 1u : 0u)) * pitch + (uint64_t)(cb - (go_left ? 1u : 0u)) * 32) * WPC;
+                const uint64_t w = min(nb + (uint64_t)line * 32, last_word);
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(base + w));
+            }
+        }
+        __syncwarp();
+        for (;;) {
+            if (i == 0 || j == 0) break;
+            const uint32_t i1 = i - 1, j1 = j - 1;
+            if ((i1 >> RL) != rb) break;
+            uint32_t slot, widx, sh;
+            if (KLASS == kClassGeneric) { slot = j1; widx = slot & 31u; sh = 2 * (i1 & 15u); }
+            else if (KLASS == kClassLong) { slot = j1; widx = (slot & 31u) * 2 + ((i1 >> 4) & 1u); sh = 2 * (15 - (i1 & 15u)); }
+            else { const uint32_t half = (i1 >> 5) & 1u; slot = j1 + half; widx = (slot & 31u) * 4 + ((i1 >> 3) & 3u); sh = 16 * half + 2 * (7 - (i1 & 7u)); }
+            if ((slot >> 5) != cb) break;
+            uint32_t code = (tile[widx] >> sh) & 3u;
+            if (KLASS != kClassGeneric) code = (code == 3u) ? 3u : 2u - code;   // stored as tag: 2 diag, 1 left, 0 up
+            if (TYPE == 1 && code == 3) { stop = true; break; }
+            if (code == rw.cur_op) ++rw.cur_n;
+            else { rw.flush(); rw.cur_op = code; rw.cur_n = 1; }
+            i -= (code != 1u);   // diagonal and up consume a query row
+            j -= (code != 2u);   // diagonal and left consume a target column
+        }
+    }
+}
+
+template <int TYPE>
+__global__ void __launch_bounds__(128)
+walk_tile_kernel(const PairDesc* __restrict__ pairs, const uint32_t* __restrict__ work, uint32_t n_work,
+                 const uint32_t* __restrict__ dirs, const uint32_t* __restrict__ end_i,
+                 const uint32_t* __restrict__ end_j, uint32_t* __restrict__ runs,
+                 uint32_t* __restrict__ n_runs, uint32_t* __restrict__ cigar_len) {
+    __shared__ __align__(16) uint32_t tiles[4][kWalkTileWords];
+    const int lane = threadIdx.x & 31;
+    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w >= n_work) return;
+    const uint32_t p = work[w];
+    const PairDesc pd = pairs[p];
+    const uint32_t klass = pd.klass & 0xffu;
+    if (klass == kClassShort) return;   // walk_kernel's
+    const uint32_t Q = pd.Q, T = pd.T;
+    uint32_t i = end_i[p], j = end_j[p];
+    RunWriter rw{runs + pd.run_off, 0, 0, 3, 0, lane == 0};
+    if (TYPE == 2) {  // the pad is the tail of the text, so it is the first thing a backward walk meets
+        if (i == Q && j < T) rw.push(1, T - j);
+        else if (j == T && i < Q) rw.push(2, Q - i);
+    }
+    uint32_t* tile = tiles[threadIdx.x >> 5];
+    const uint32_t* base = dirs + pd.dir_off;
+    if (klass == kClassLong16) walk_tiles<TYPE, kClassLong16>(pd, base, i, j, tile, rw, lane);
+    else if (klass == kClassLong) walk_tiles<TYPE, kClassLong>(pd, base, i, j, tile, rw, lane);
+    else walk_tiles<TYPE, kClassGeneric>(pd, base, i, j, tile, rw, lane);
+    if (TYPE != 1) {   // the borders: row 0 points left ('I'), column 0 points up ('D') (reference :83-92)
+        if (i == 0 && j) rw.push(1, j);
+        else if (j == 0 && i) rw.push(2, i);
+    }
+    rw.flush();
+    if (lane == 0) {
+        n_runs[p] = rw.nr;
+        cigar_len[p] = rw.nr == 0 ? 2u : rw.bytes;  // empty path: "1\0"
+    }
 }
 
 // Score-only batches still owe the caller target_begin (reference :119-121, :197-199, :283-285).

@@ -23,6 +23,7 @@
 #include "../../include/b200map.h"
 #include "align_fill_generic.cuh"
 #include "align_fill_long.cuh"
+#include "align_fill_long16.cuh"
 #include "align_fill_short.cuh"
 #include "align_walk.cuh"
 #include "common.cuh"
@@ -117,6 +118,7 @@ struct b200_ctx {
     // options
     int64_t dir_budget_bytes = 48ll << 30;
     int64_t force_generic = 0;
+    int64_t long16 = 1;                     // 0 = long pairs stay on the int32 kernel (align_fill_long.cuh)
     int64_t chunk_pairs = 0;
     b200_align_plan* host_plan = nullptr;   // recycled by the host-buffer entry points
     cudaStream_t copy_stream = nullptr;     // uploads of the host-buffer entry points (overlap with kernels)
@@ -210,6 +212,7 @@ extern "C" int b200_ctx_set_option(b200_ctx* c, const char* key, int64_t value) 
     const std::string k(key);
     if (k == "dir_budget_bytes") c->dir_budget_bytes = std::max<int64_t>(value, 1 << 20);
     else if (k == "force_generic") c->force_generic = value;
+    else if (k == "long16") c->long16 = value;
     else if (k == "chunk_pairs") c->chunk_pairs = value;
     else if (k == "profile") c->profile = value;
     else if (k == "reset_counters") {
@@ -264,6 +267,7 @@ struct b200_align_plan {
     int type = 0;
     Scores sc{};
     bool want_cigar = false;
+    bool long16 = false;               // long class runs on the packed int16x2 kernel (align_fill_long16.cuh)
     uint64_t cells = 0, cigar_bound = 0, run_slots = 0, q_bytes = 0, t_bytes = 0, qpk_words = 0, tpk_words = 0;
     uint32_t max_T = 0, max_Q = 0, max_T_short = 0, max_Q_short = 0;
     size_t n_short = 0, n_long = 0;   // the work order is [short..., long..., generic...]
@@ -366,6 +370,23 @@ static bool long_scores_ok(const Scores& sc, int type) {
     return fits8(sm) && fits8(sx) && std::abs((long)sc.gap) < (1 << 20) && std::abs((long)sc.match) < (1 << 20) &&
            std::abs((long)sc.mismatch) < (1 << 20);
 }
+// The packed int16x2 wavefront kernel (align_fill_long16.cuh) keeps every 32-row block relative to a private
+// base that is re-centred every kL16Chunk columns, so what must fit in 16 bits is the spread of a block plus
+// its drift over one chunk. With g = gap, U = max(g, s_max - g, 0): neighbouring cells obey g <= dH <= U in
+// both directions (induction over team_alignment.cpp:104-114; the local clamp only tightens it), hence in the
+// moving frame Y = 4H - 4gj + 1 a vertical step changes Y by at most Dv = 4 max(|g|,|U|) + 3 and a horizontal
+// step by 0 .. Dh = 4 (U - g) + 3.
+static bool long16_scores_ok(const Scores& sc, int type) {
+    if (!long_scores_ok(sc, type)) return false;
+    const long g = sc.gap, smax = std::max(sc.match, sc.mismatch);
+    const long U = std::max({g, smax - g, 0l});
+    const long Dv = 4 * std::max(std::labs(g), std::labs(U)) + 3, Dh = 4 * (U - g) + 3;
+    return 34 * Dv + (kL16Chunk + 4) * Dh + 4 * std::labs(g) + 160 <= 30000;
+}
+static inline uint32_t long16_pitch(uint32_t T) { return (T + 2u) & ~1u; }   // slots 0..T, even
+static inline uint64_t long16_dir_words(uint32_t Q, uint32_t T) {
+    return (uint64_t)div_up(Q, kL16LaneRows) * long16_pitch(T) * 4;
+}
 static bool short_pair_ok(const Scores& sc, uint32_t Q, uint32_t T) {
     const long mx = std::max({std::abs((long)sc.match), std::abs((long)sc.mismatch), std::abs((long)sc.gap), 1l});
     return Q <= 4096 && T <= 4096 && 4l * (((long)Q + T + 2) * mx + std::abs((long)sc.gap) * T + 4) <= 32767;
@@ -452,6 +473,7 @@ static int plan_finish(b200_align_plan* p, b200_ctx* ctx, bool short_scores, boo
     std::vector<PairDesc>& pairs = p->h_pairs;
     std::vector<uint32_t> short_list, long_list, generic_list;
     const bool long_scores = !ctx->force_generic && long_scores_ok(p->sc, type);
+    p->long16 = long_scores && ctx->long16 && long16_scores_ok(p->sc, type);
     for (size_t i = 0; i < n; ++i) {
         PairDesc& d = pairs[i];
         const uint64_t ql = d.Q, tl = d.T;
@@ -527,13 +549,14 @@ static int plan_finish(b200_align_plan* p, b200_ctx* ctx, bool short_scores, boo
         Wave cur{klass, (uint32_t)order.size(), 0, 0, 0};
         for (uint32_t idx : (pass == 0 ? long_list : generic_list)) {
             PairDesc& d = pairs[idx];
-            const uint64_t words = !p->want_cigar ? 0 : (pass == 0 ? long_dir_words(d.Q, d.T) : generic_dir_words(d.Q, d.T));
+            const uint64_t words = !p->want_cigar ? 0 : (pass == 0 ? (p->long16 ? long16_dir_words(d.Q, d.T) : long_dir_words(d.Q, d.T))
+                                                                   : generic_dir_words(d.Q, d.T));
             if (cur.count && cur.dir_words + words > budget_words) {
                 p->waves.push_back(cur);
                 cur = Wave{klass, (uint32_t)order.size(), 0, 0, 0};
             }
-            d.klass = klass;
-            if (pass == 0) d.pitch = (d.T + 1u) & ~1u;
+            d.klass = (pass == 0 && p->long16) ? kClassLong16 : klass;
+            if (pass == 0) d.pitch = p->long16 ? long16_pitch(d.T) : ((d.T + 1u) & ~1u);
             d.dir_off = cur.dir_words;
             cur.dir_words += (words + 3) & ~3ull;
             ++cur.count;
@@ -552,7 +575,7 @@ static int plan_finish(b200_align_plan* p, b200_ctx* ctx, bool short_scores, boo
         for (uint32_t w = wv.first; w < wv.first + wv.count; ++w) {
             const PairDesc& d = pairs[order[w]];
             task_off.push_back(t); bnd_off.push_back(b);
-            const uint32_t ns = (d.Q && d.T) ? div_up(d.Q, kLongRows * kWarp) : 0;
+            const uint32_t ns = (d.Q && d.T) ? div_up(d.Q, p->long16 ? kL16Stripe : kLongRows * kWarp) : 0;
             t += ns; b += (uint64_t)ns * (d.T + 4);
         }
         task_off.push_back(t); bnd_off.push_back(b);
@@ -649,7 +672,8 @@ static int launch_fill_short(b200_align_plan* p, const Wave& wv, const RunBufs& 
 static int launch_fill_long(b200_align_plan* p, const Wave& wv, const RunBufs& rb) {
     b200_ctx* c = p->ctx;
     int per_sm = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fill_long_kernel<0>, 128, 0));
+    if (p->long16) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fill_long16_kernel<1>, 128, 0));
+    else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fill_long_kernel<0>, 128, 0));
     per_sm = std::max(per_sm, 1);
     const uint32_t* d_task_off = p->d_task_off.as<uint32_t>() + wv.first_group;
     const uint64_t* d_bnd_off = p->d_bnd_off.as<uint64_t>() + wv.first_group;
@@ -661,8 +685,32 @@ static int launch_fill_long(b200_align_plan* p, const Wave& wv, const RunBufs& r
     CU(cudaMemsetAsync(c->counter.p, 0, 64, rb.st));
     CU(cudaMemsetAsync(c->counter.as<uint32_t>() + 24, 0, 4, rb.st));
     CU(cudaMemsetAsync(c->progress.p, 0, ((size_t)p->max_long_tasks + 8) * 4, rb.st));
-    const LongConsts K = make_long_consts(p->sc, p->type);
     const uint32_t* d_work = p->d_work.as<uint32_t>() + wv.first;
+    if (p->long16) {
+        const ShortConsts K16 = make_short_consts(p->sc, p->type);
+        prof_begin(c, rb.st, 0);
+#define LONG16K(TY)                                                                                                    \
+    fill_long16_kernel<TY><<<n_blocks, 128, 0, rb.st>>>(c->qpk.as<uint32_t>(), c->tpk.as<uint32_t>(), p->d_pairs.as<PairDesc>(), \
+        d_work, wv.count, d_task_off, d_bnd_off, c->counter.as<uint32_t>(), c->flags.as<uint8_t>(), K16, rb.dirs,       \
+        c->bnd.as<int32_t>(), c->progress.as<uint32_t>(), c->stripe_res.as<StripeResult>(),                            \
+        c->counter.as<uint32_t>() + 24);                                                                               \
+    finalize_long_kernel<TY><<<(unsigned)div_up64(wv.count, 128), 128, 0, rb.st>>>(p->d_pairs.as<PairDesc>(), d_work,  \
+        wv.count, d_task_off, c->flags.as<uint8_t>(), c->stripe_res.as<StripeResult>(), K16.init, rb.score,            \
+        c->end_i.as<uint32_t>(), c->end_j.as<uint32_t>())
+        if (p->type == 0) { LONG16K(0); } else if (p->type == 2) { LONG16K(2); } else {
+            LONG16K(1);
+            locate_long16_kernel<<<(unsigned)div_up64((uint64_t)wv.count * 32, 128), 128, 0, rb.st>>>(
+                c->qpk.as<uint32_t>(), c->tpk.as<uint32_t>(), p->d_pairs.as<PairDesc>(), d_work, wv.count, d_task_off, d_bnd_off,
+                c->flags.as<uint8_t>(), K16, c->bnd.as<int32_t>(), c->stripe_res.as<StripeResult>(), rb.score,
+                c->end_i.as<uint32_t>(), c->end_j.as<uint32_t>());
+            c->kernel_launches++;
+        }
+#undef LONG16K
+        prof_end(c, rb.st);
+        c->kernel_launches += 2;
+        return B200_OK;
+    }
+    const LongConsts K = make_long_consts(p->sc, p->type);
     prof_begin(c, rb.st, 0);
 #define LONGK(TY)                                                                                                      \
     fill_long_kernel<TY><<<n_blocks, 128, 0, rb.st>>>(c->qpk.as<uint32_t>(), c->tpk.as<uint32_t>(), p->d_pairs.as<PairDesc>(), \
@@ -685,18 +733,27 @@ static int launch_fill_long(b200_align_plan* p, const Wave& wv, const RunBufs& r
     return B200_OK;
 }
 
-static int launch_walk(b200_align_plan* p, const uint32_t* d_work, uint32_t count, const RunBufs& rb) {
+static int launch_walk(b200_align_plan* p, uint32_t wave_klass, const uint32_t* d_work, uint32_t count, const RunBufs& rb) {
     b200_ctx* c = p->ctx;
     if (!count) return B200_OK;
-    // few pairs: give each its own quarter-warp or warp so the divergent pointer chases do not serialise
-    uint32_t spread = 1;
-    while (spread < 32 && (uint64_t)count * spread * 2 <= (uint64_t)c->sm_count * 512) spread *= 2;
-    const unsigned wb = (unsigned)div_up64((uint64_t)count * spread, 128);
     prof_begin(c, rb.st, 1);
+    if (wave_klass == kClassShort) {
+        // thread per pair; few pairs: give each its own quarter-warp or warp so the divergent pointer chases do not serialise
+        uint32_t spread = 1;
+        while (spread < 32 && (uint64_t)count * spread * 2 <= (uint64_t)c->sm_count * 512) spread *= 2;
+        const unsigned wb = (unsigned)div_up64((uint64_t)count * spread, 128);
 #define WALK(TY) walk_kernel<TY><<<wb, 128, 0, rb.st>>>(p->d_pairs.as<PairDesc>(), d_work, count, spread, rb.dirs, c->end_i.as<uint32_t>(), \
         c->end_j.as<uint32_t>(), c->runs.as<uint32_t>(), c->n_runs.as<uint32_t>(), c->cigar_len.as<uint32_t>())
-    switch (p->type) { case 0: WALK(0); break; case 1: WALK(1); break; default: WALK(2); break; }
+        switch (p->type) { case 0: WALK(0); break; case 1: WALK(1); break; default: WALK(2); break; }
 #undef WALK
+    } else {
+        // warp per pair, tile by tile (long and generic layouts)
+        const unsigned wb = (unsigned)div_up64((uint64_t)count * 32, 128);
+#define WALK(TY) walk_tile_kernel<TY><<<wb, 128, 0, rb.st>>>(p->d_pairs.as<PairDesc>(), d_work, count, rb.dirs, c->end_i.as<uint32_t>(), \
+        c->end_j.as<uint32_t>(), c->runs.as<uint32_t>(), c->n_runs.as<uint32_t>(), c->cigar_len.as<uint32_t>())
+        switch (p->type) { case 0: WALK(0); break; case 1: WALK(1); break; default: WALK(2); break; }
+#undef WALK
+    }
     prof_end(c, rb.st);
     c->kernel_launches++;
     return B200_OK;
@@ -811,7 +868,7 @@ extern "C" int b200_align_plan_run(b200_align_plan* p, const char* d_q_buf, cons
         } else {
             TRY(launch_fill_generic(p, work, wv.count, rb));
         }
-        if (p->want_cigar) TRY(launch_walk(p, work, wv.count, rb));
+        if (p->want_cigar) TRY(launch_walk(p, wv.klass, work, wv.count, rb));
     }
     CU(cudaGetLastError());
 
@@ -1323,6 +1380,7 @@ extern "C" int b200_map_batch(b200_ctx* c, const b200_index* ix, size_t n, const
     if (r1 > r0 && !reads_buf) return fail(B200_E_ARG, "null reads buffer");
     const uint32_t k = ix->k, w = ix->w;
     const uint32_t nr = (uint32_t)n;
+    PhaseTrace tr;
 
     // ---- upload reads, Minimize (read strand flag true, :599/:712)
     std::vector<uint64_t> off(n + 1);
@@ -1346,6 +1404,7 @@ extern "C" int b200_map_batch(b200_ctx* c, const b200_index* ix, size_t n, const
         &b_rof, &b_ror, &b_lis, &b_prev, &b_chf, &b_chr, &b_reg}};
     TRY(b_hash.ensure(tot * 4)); TRY(b_pos.ensure(tot * 4)); TRY(b_flag.ensure(tot));
     TRY(b200_min_plan_run(mp, c->d_q.as<char>(), b_hash.as<uint32_t>(), b_pos.as<uint32_t>(), b_flag.as<uint8_t>(), st));
+    if (tr.on) { cudaStreamSynchronize(st); tr.mark("upload+minimize"); }
 
     // ---- remove_duplicates (:28-45)
     TRY(b_keep.ensure(tot)); TRY(b_slot.ensure(tot * 4)); TRY(b_first.ensure((n + 1) * 4));
@@ -1364,6 +1423,7 @@ extern "C" int b200_map_batch(b200_ctx* c, const b200_index* ix, size_t n, const
     gather_offsets_kernel<<<(unsigned)div_up64(n + 1, 256), 256, 0, st>>>(b_slot.as<uint32_t>(), mp->d_out_off.as<uint64_t>(), nr,
                                                                           tot, n_min, b_doff.as<uint32_t>());
     c->kernel_launches += 2;
+    if (tr.on) { cudaStreamSynchronize(st); tr.mark("dedup"); }
 
     // ---- seed lookup against both strands of the index
     TRY(b_cf.ensure((size_t)n_min * 4)); TRY(b_cr.ensure((size_t)n_min * 4));
@@ -1388,6 +1448,7 @@ extern "C" int b200_map_batch(b200_ctx* c, const b200_index* ix, size_t n, const
     gather_offsets32_kernel<<<rb1, 256, 0, st>>>(b_mof.as<uint32_t>(), b_doff.as<uint32_t>(), nr, n_min, n_mf, b_rof.as<uint32_t>());
     gather_offsets32_kernel<<<rb1, 256, 0, st>>>(b_mor.as<uint32_t>(), b_doff.as<uint32_t>(), nr, n_min, n_mr, b_ror.as<uint32_t>());
     c->kernel_launches += 4;
+    if (tr.on) { cudaStreamSynchronize(st); tr.mark("seeds"); }
 
     // ---- chaining (FindLIS) per strand, strand choice, region
     const size_t n_mmax = std::max<size_t>(std::max(n_mf, n_mr), 1);
@@ -1405,6 +1466,7 @@ extern "C" int b200_map_batch(b200_ctx* c, const b200_index* ix, size_t n, const
     CU(cudaMemcpyAsync(reg.data(), b_reg.p, n * sizeof(Region), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     c->d2h_bytes += n * sizeof(Region);
+    tr.mark("chain+region");
 
     // ---- Align on the found regions (:666-678): explicit sub-ranges of the read and reference buffers
     std::vector<uint32_t> mapped;
@@ -1426,12 +1488,14 @@ extern "C" int b200_map_batch(b200_ctx* c, const b200_index* ix, size_t n, const
         d.T = g.t_end - g.t_begin + 1;
     }
     TRY(plan_finish(plan, c, !c->force_generic && short_scores_ok(plan->sc, type), true));
+    tr.mark("align-plan");
     const uint64_t dev_cap = want_cigar ? plan->cigar_bound : 0;
     TRY(c->d_score.ensure(nm * 4)); TRY(c->d_tb.ensure(nm * 4));
     if (want_cigar) { TRY(c->d_cigar.ensure(dev_cap + 16)); TRY(c->d_cigar_off.ensure((nm + 1) * 8)); }
     TRY(b200_align_plan_run(plan, c->d_q.as<char>(), ix->d_ref.as<char>(), c->d_score.as<int32_t>(), c->d_tb.as<uint32_t>(),
                             want_cigar ? c->d_cigar.as<char>() : nullptr, want_cigar ? c->d_cigar_off.as<uint64_t>() : nullptr,
                             dev_cap, st));
+    if (tr.on) { cudaStreamSynchronize(st); tr.mark("align-run"); }
     std::vector<int32_t> sc(nm);
     std::vector<uint32_t> tbg(nm);
     std::vector<uint64_t> coff(nm + 1, 0);
@@ -1463,5 +1527,6 @@ extern "C" int b200_map_batch(b200_ctx* c, const b200_index* ix, size_t n, const
         }
     }
     if (cigar_off) cigar_off[n] = at;
+    tr.mark("d2h+assemble");
     return B200_OK;
 }

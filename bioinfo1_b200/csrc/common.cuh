@@ -31,6 +31,7 @@ static_assert(sizeof(PairDesc) == 64, "PairDesc layout");
 constexpr uint32_t kClassGeneric = 0;  // align_fill_generic.cuh layout: word(rb, j) = dirs[dir_off + rb*pitch + j-1]
 constexpr uint32_t kClassShort = 1;    // align_fill_short.cuh layout, pitch = column count of the 64-pair group
 constexpr uint32_t kClassLong = 2;     // align_fill_long.cuh layout: 2 words per (32-row block, column), pitch even
+constexpr uint32_t kClassLong16 = 3;   // align_fill_long16.cuh layout: 4 words per (64-row block, slot), slot = column-1 + (row half)
 
 constexpr uint8_t kFlagDash = 1;     // pair contains a '-' byte (free gap, team_alignment.cpp:25-28)
 constexpr uint8_t kFlagNonACGT = 2;  // pair contains a byte outside "ACGT"

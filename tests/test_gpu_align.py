@@ -221,3 +221,49 @@ def test_generic_kernel_forced_on_plain_dna(ctx, typ):
     finally:
         ctx.set_option("force_generic", 0)
     _check_batch(ctx, qs, ts, typ)   # and the fast path on the same input
+
+
+# ---- K3: packed int16x2 long-pair kernel (2048-row stripes, per-block bases) --------------------
+
+@pytest.mark.parametrize("typ", [0, 1, 2])
+def test_long16_stripe_edges_and_score_range(ctx, typ):
+    """Lengths straddle the 32/64-row blocks and the 2048-row stripes; score sets run from the unit scores to
+    the largest |4(s-gap)+1| the byte tables take, where the 16-bit spread bound is tightest."""
+    rng = np.random.default_rng(500 + typ)
+    qs, ts = [], []
+    for n in (31, 33, 63, 64, 65, 127, 129, 2047, 2048, 2049, 2111, 4100, 6500):
+        t = seqgen.random_dna(rng, n)
+        q = seqgen.mutate(rng, t, sub=0.03, ins=0.05, dele=0.05)
+        qs.append(q.tobytes()); ts.append(t.tobytes())
+        qs.append(t.tobytes()[: max(1, n // 3)]); ts.append(q.tobytes())
+    qs += [b"A" * 2500, b"ACGT" * 600, b"G" * 70]
+    ts += [b"A" * 2300, b"A" * 900, b"G" * 3000]
+    _check_batch(ctx, qs, ts, typ)
+    for m, x, g in ((2, -3, -2), (10, -10, -10), (15, -16, -16), (25, -6, -6), (1, -1, 1), (0, 0, 0), (-2, 3, -1)):
+        _check_batch(ctx, qs[:12] + qs[-3:], ts[:12] + ts[-3:], typ, m, x, g)
+
+
+@pytest.mark.parametrize("typ", [0, 1, 2])
+def test_long16_large_scores_leave_int16(ctx, typ):
+    """Identical 9 kb sequences: H reaches 9000 (4H > 32767), so only the per-block bases keep the halves in
+    range, and the local clamp sits far below the representable window."""
+    rng = np.random.default_rng(600 + typ)
+    t = seqgen.random_dna(rng, 9000).tobytes()
+    q2 = seqgen.mutate(rng, np.frombuffer(t, dtype=np.uint8), sub=0.02, ins=0.01, dele=0.01).tobytes()
+    _check_batch(ctx, [t, q2, t[:5000]], [t, t, q2], typ)
+    _check_batch(ctx, [t, q2], [t, t], typ, 3, -2, -4)
+
+
+@pytest.mark.parametrize("typ", [0, 1, 2])
+def test_long32_kernel_kept_covered(ctx, typ):
+    """The int32 stripe kernel serves score sets the 16-bit bound rejects: keep it covered on the same inputs."""
+    qs, ts = seqgen.ont_like_pairs(40 + typ, 3, mean_len=2500, min_len=1800, max_len=3200)
+    qs = [q.tobytes() for q in qs] + [b"A" * 700, b"ACGT" * 300]
+    ts = [t.tobytes() for t in ts] + [b"ACGT" * 400, b"A" * 900]
+    ctx.set_option("long16", 0)
+    try:
+        _check_batch(ctx, qs, ts, typ)
+    finally:
+        ctx.set_option("long16", 1)
+    # 4(s-gap)+1 fits the byte tables, but one vertical step moves Y by 803: the 16-bit bound rejects it
+    _check_batch(ctx, qs, ts, typ, -170, -200, -200)
