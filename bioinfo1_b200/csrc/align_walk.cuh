@@ -130,56 +130,87 @@ template <> struct TileShape<kClassGeneric> { static constexpr uint32_t RL = 4, 
 template <> struct TileShape<kClassLong>    { static constexpr uint32_t RL = 5, WPC = 2; };
 template <> struct TileShape<kClassLong16>  { static constexpr uint32_t RL = 6, WPC = 4; };
 
-constexpr int kWalkTileWords = 128;   // shared-memory words per warp (the largest tile: 64 rows x 32 slots)
+constexpr uint32_t kTileSlots = 128;                    // column slots per tile
+constexpr uint32_t kTileBlocks = 2;                     // row blocks per tile: the current one and the one above
+constexpr int kWalkTileWords = kTileBlocks * kTileSlots * 4;   // shared-memory words per warp (largest layout)
 
-// Walks from (i, j) until a border (or, local, a stop cell) is reached. All lanes run the same
-// scalar walk on the shared tile; returns with i == 0, j == 0 or the stop cell.
+// Walks from (i, j) until a border (or, local, a stop cell) is reached.
+// The tile is anchored with the current cell in its bottom-right corner (row blocks rb-1..rb, the 128 slots
+// ending at the cell's slot): a mostly diagonal path gets 64-128 steps out of one HBM round trip.
+// Inside the tile the warp advances by whole RUNS: lane l looks at the cell l steps further along the
+// current direction (diagonal first), a ballot counts how far the run goes, and the run is pushed at once --
+// a CIGAR is run-length encoded anyway, and ONT-like paths average ~10 cells per run.
 template <int TYPE, uint32_t KLASS>
 __device__ __forceinline__ void walk_tiles(const PairDesc& pd, const uint32_t* __restrict__ base, uint32_t& i, uint32_t& j,
                                            uint32_t* tile, RunWriter& rw, int lane) {
     constexpr uint32_t RL = TileShape<KLASS>::RL, WPC = TileShape<KLASS>::WPC;
-    const uint64_t pitch = pd.pitch;
-    const uint64_t n_rb = ((uint64_t)pd.Q + (1u << RL) - 1) >> RL;
-    const uint64_t last_word = n_rb * pitch * WPC - 1;   // last word of this pair's matrix
+    const uint32_t pitch = pd.pitch;
+    const uint32_t n_rb = (pd.Q + (1u << RL) - 1) >> RL;
+    // tag/code of cell (i1, j1) (0-based) if it lies inside the loaded tile, else 0xff
+    uint32_t rb_base = 0, slot_lo = 0;
+    auto peek = [&](uint32_t i1, uint32_t j1) -> uint32_t {
+        const uint32_t blk = (i1 >> RL) - rb_base;
+        uint32_t slot, widx, sh;
+        if (KLASS == kClassGeneric) { slot = j1; widx = 0; sh = 2 * (i1 & 15u); }
+        else if (KLASS == kClassLong) { slot = j1; widx = (i1 >> 4) & 1u; sh = 2 * (15 - (i1 & 15u)); }
+        else { const uint32_t half = (i1 >> 5) & 1u; slot = j1 + half; widx = (i1 >> 3) & 3u; sh = 16 * half + 2 * (7 - (i1 & 7u)); }
+        const uint32_t srel = slot - slot_lo;
+        if (blk >= kTileBlocks || srel >= kTileSlots) return 0xffu;
+        uint32_t code = (tile[(blk * kTileSlots + srel) * WPC + widx] >> sh) & 3u;
+        if (KLASS != kClassGeneric) code = (code == 3u) ? 3u : 2u - code;   // stored as tag: 2 diag, 1 left, 0 up
+        return code;   // 0 diagonal, 1 left, 2 up, 3 stop
+    };
     bool stop = false;
     while (i != 0 && j != 0 && !stop) {
-        const uint32_t rb = (i - 1) >> RL;
-        const uint32_t cb = (j - 1 + (KLASS == kClassLong16 ? ((i - 1) >> 5) & 1u : 0u)) >> 5;
-        const uint64_t tbase = ((uint64_t)rb * pitch + (uint64_t)cb * 32) * WPC;
-        __syncwarp();
-        if ((uint64_t)cb * 32 + lane < pitch) {
-            const uint32_t* src = base + tbase + (uint32_t)lane * WPC;
-            if (WPC == 1) tile[lane] = __ldg(src);
-            else if (WPC == 2) *reinterpret_cast<uint2*>(tile + 2 * lane) = __ldg(reinterpret_cast<const uint2*>(src));
-            else *reinterpret_cast<uint4*>(tile + 4 * lane) = __ldg(reinterpret_cast<const uint4*>(src));
-        }
-        // the path leaves this tile to the left, upwards or diagonally: pull those tiles towards L2 now
-        if (lane < 3 * (int)(WPC + 1)) {
-            const int which = lane / (int)(WPC + 1), line = lane % (int)(WPC + 1);
-            const bool go_left = which != 1, go_up = which != 0;
-            if ((!go_left || cb > 0) && (!go_up || rb > 0)) {
-                const uint64_t nb = ((uint64_t)(rb - (go_up ? 1u : 0u)) * pitch + (uint64_t)(cb - (go_left ? 1u : 0u)) * 32) * WPC;
-                const uint64_t w = min(nb + (uint64_t)line * 32, last_word);
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(base + w));
+        {   // (re)load the tile around the current cell
+            const uint32_t i1 = i - 1;
+            const uint32_t rb = i1 >> RL;
+            const uint32_t slot = j - 1 + (KLASS == kClassLong16 ? (i1 >> 5) & 1u : 0u);
+            rb_base = rb > 0 ? rb - 1 : 0;
+            // (one spare slot to the right: in the long16 layout an 'up' move out of a low block lands one slot further)
+            slot_lo = slot + 1 >= kTileSlots - 1 ? slot + 1 - (kTileSlots - 1) : 0;
+            __syncwarp();
+#pragma unroll
+            for (uint32_t b = 0; b < kTileBlocks; ++b) {
+#pragma unroll
+                for (uint32_t q = 0; q < kTileSlots / 32; ++q) {
+                    const uint32_t srel = q * 32 + lane, sl = slot_lo + srel;
+                    if (rb_base + b < n_rb && sl < pitch) {
+                        const uint32_t* src = base + ((uint64_t)(rb_base + b) * pitch + sl) * WPC;
+                        uint32_t* dst = tile + (b * kTileSlots + srel) * WPC;
+                        if (WPC == 1) dst[0] = __ldg(src);
+                        else if (WPC == 2) *reinterpret_cast<uint2*>(dst) = __ldg(reinterpret_cast<const uint2*>(src));
+                        else *reinterpret_cast<uint4*>(dst) = __ldg(reinterpret_cast<const uint4*>(src));
+                    }
+                }
             }
+            __syncwarp();
         }
-        __syncwarp();
         for (;;) {
             if (i == 0 || j == 0) break;
-            const uint32_t i1 = i - 1, j1 = j - 1;
-            if ((i1 >> RL) != rb) break;
-            uint32_t slot, widx, sh;
-            if (KLASS == kClassGeneric) { slot = j1; widx = slot & 31u; sh = 2 * (i1 & 15u); }
-            else if (KLASS == kClassLong) { slot = j1; widx = (slot & 31u) * 2 + ((i1 >> 4) & 1u); sh = 2 * (15 - (i1 & 15u)); }
-            else { const uint32_t half = (i1 >> 5) & 1u; slot = j1 + half; widx = (slot & 31u) * 4 + ((i1 >> 3) & 3u); sh = 16 * half + 2 * (7 - (i1 & 7u)); }
-            if ((slot >> 5) != cb) break;
-            uint32_t code = (tile[widx] >> sh) & 3u;
-            if (KLASS != kClassGeneric) code = (code == 3u) ? 3u : 2u - code;   // stored as tag: 2 diag, 1 left, 0 up
-            if (TYPE == 1 && code == 3) { stop = true; break; }
-            if (code == rw.cur_op) ++rw.cur_n;
-            else { rw.flush(); rw.cur_op = code; rw.cur_n = 1; }
-            i -= (code != 1u);   // diagonal and up consume a query row
-            j -= (code != 2u);   // diagonal and left consume a target column
+            // diagonal run: lane l tests cell (i - l, j - l)
+            const uint32_t l = (uint32_t)lane;
+            uint32_t code = (i > l && j > l) ? peek(i - 1 - l, j - 1 - l) : 0xfeu;
+            const uint32_t c0 = __shfl_sync(kFull, code, 0);
+            if (c0 == 0xffu) break;                          // current cell outside the tile: reload
+            if (TYPE == 1 && c0 == 3u) { stop = true; break; }
+            uint32_t run;
+            if (c0 == 0u) {
+                run = __ffs(~__ballot_sync(kFull, code == 0u)) - 1;   // ballot has bit 0 set; all 32 set -> ffs(0) = 0 -> wraps
+                if (run > 32u) run = 32u;
+                i -= run; j -= run;
+            } else if (c0 == 1u) {                           // left run along row i: lane l tests (i, j - l)
+                code = (j > l) ? peek(i - 1, j - 1 - l) : 0xfeu;
+                run = __ffs(~__ballot_sync(kFull, code == 1u)) - 1;
+                if (run > 32u) run = 32u;
+                j -= run;
+            } else {                                         // up run along column j: lane l tests (i - l, j)
+                code = (i > l) ? peek(i - 1 - l, j - 1) : 0xfeu;
+                run = __ffs(~__ballot_sync(kFull, code == 2u)) - 1;
+                if (run > 32u) run = 32u;
+                i -= run;
+            }
+            rw.push(c0, run);
         }
     }
 }

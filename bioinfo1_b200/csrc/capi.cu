@@ -106,12 +106,23 @@ struct HostBuf {  // pinned staging
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
+// Per-wave workspaces. Two slots: consecutive waves of a run alternate between them (and between two
+// streams), so the latency-bound traceback walk of wave k overlaps the ALU-bound fill of wave k+1.
+struct WaveSlot {
+    DevBuf dirs, bnd, bnd_short, progress, stripe_res, counter, fix_work;
+    cudaEvent_t done = nullptr;
+};
+
 struct b200_ctx {
     int device = 0;
     int sm_count = 148;
     cudaStream_t stream = nullptr;
     // workspaces shared by every plan run on this context (one run at a time per context)
-    DevBuf dirs, bnd, bnd_short, progress, stripe_res, qpk, tpk, counter, end_i, end_j, runs, n_runs, cigar_len, scan_tmp, flags, total;
+    WaveSlot slot[2];
+    cudaStream_t aux_stream = nullptr;      // second wave stream of a run
+    cudaEvent_t fork_event = nullptr;
+    int64_t overlap_waves = 1;              // 0 = all waves on the caller's stream, one after the other
+    DevBuf qpk, tpk, end_i, end_j, runs, n_runs, cigar_len, scan_tmp, flags, total;
     // staging for the host-buffer entry points
     DevBuf d_q, d_t, d_score, d_tb, d_cigar, d_cigar_off, d_seq, d_hash, d_pos, d_flag;
     HostBuf h_q, h_t, h_off;
@@ -121,6 +132,9 @@ struct b200_ctx {
     int64_t long16 = 1;                     // 0 = long pairs stay on the int32 kernel (align_fill_long.cuh)
     int64_t chunk_pairs = 0;
     b200_align_plan* host_plan = nullptr;   // recycled by the host-buffer entry points
+    b200_align_plan* map_plan = nullptr;    // recycled by b200_map_batch (its device buffers keep their capacity)
+    b200_min_plan* map_min_plan = nullptr;
+    DevBuf map_buf[27];                     // b200_map_batch scratch (grow-only; cudaMalloc/cudaFree per call cost more than the kernels)
     cudaStream_t copy_stream = nullptr;     // uploads of the host-buffer entry points (overlap with kernels)
     std::vector<cudaEvent_t> copy_events;
     int64_t profile = 0;   // 1 = bracket kernels with CUDA events (adds a sync per run)
@@ -190,16 +204,26 @@ extern "C" int b200_ctx_create(int device, b200_ctx** out) {
 }
 
 extern "C" void b200_align_plan_destroy(b200_align_plan* p);
+extern "C" void b200_min_plan_destroy(b200_min_plan* p);
 extern "C" void b200_ctx_destroy(b200_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->host_plan) { b200_align_plan_destroy(c->host_plan); c->host_plan = nullptr; }
+    if (c->map_plan) { b200_align_plan_destroy(c->map_plan); c->map_plan = nullptr; }
+    if (c->map_min_plan) { b200_min_plan_destroy(c->map_min_plan); c->map_min_plan = nullptr; }
+    for (DevBuf& b : c->map_buf) b.release();
     if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     for (auto e : c->copy_events) cudaEventDestroy(e);
     for (auto& sp : c->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     for (auto e : c->event_pool) cudaEventDestroy(e);
-    for (DevBuf* b : {&c->dirs, &c->bnd, &c->bnd_short, &c->progress, &c->stripe_res, &c->qpk, &c->tpk, &c->counter, &c->end_i, &c->end_j, &c->runs, &c->n_runs,
+    if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
+    if (c->fork_event) cudaEventDestroy(c->fork_event);
+    for (WaveSlot& w : c->slot) {
+        for (DevBuf* b : {&w.dirs, &w.bnd, &w.bnd_short, &w.progress, &w.stripe_res, &w.counter, &w.fix_work}) b->release();
+        if (w.done) cudaEventDestroy(w.done);
+    }
+    for (DevBuf* b : {&c->qpk, &c->tpk, &c->end_i, &c->end_j, &c->runs, &c->n_runs,
                       &c->cigar_len, &c->scan_tmp, &c->flags, &c->total, &c->d_q, &c->d_t, &c->d_score, &c->d_tb,
                       &c->d_cigar, &c->d_cigar_off, &c->d_seq, &c->d_hash, &c->d_pos, &c->d_flag})
         b->release();
@@ -213,6 +237,7 @@ extern "C" int b200_ctx_set_option(b200_ctx* c, const char* key, int64_t value) 
     if (k == "dir_budget_bytes") c->dir_budget_bytes = std::max<int64_t>(value, 1 << 20);
     else if (k == "force_generic") c->force_generic = value;
     else if (k == "long16") c->long16 = value;
+    else if (k == "overlap_waves") c->overlap_waves = value;
     else if (k == "chunk_pairs") c->chunk_pairs = value;
     else if (k == "profile") c->profile = value;
     else if (k == "reset_counters") {
@@ -280,7 +305,7 @@ struct b200_align_plan {
     uint32_t uQ = 0, uT = 0;
     uint64_t u_groups_per_wave = 1;
     uint64_t u_qbase = 0, u_tbase = 0;
-    DevBuf d_pairs, d_work, d_groups, d_fix_work, d_task_off, d_bnd_off;
+    DevBuf d_pairs, d_work, d_groups, d_task_off, d_bnd_off;
     uint64_t max_long_bnd_words = 0;   // boundary rows of the largest long wave
     uint32_t max_long_tasks = 0;
 
@@ -339,7 +364,6 @@ extern "C" void b200_align_plan_destroy(b200_align_plan* p) {
     p->d_pairs.release();
     p->d_work.release();
     p->d_groups.release();
-    p->d_fix_work.release();
     p->d_task_off.release();
     p->d_bnd_off.release();
     delete p;
@@ -394,6 +418,14 @@ static bool short_pair_ok(const Scores& sc, uint32_t Q, uint32_t T) {
 
 static int plan_finish(b200_align_plan* p, b200_ctx* ctx, bool short_scores, bool sync);
 
+// A class whose direction matrices fit the budget runs as ONE wave (small waves under-fill the machine and
+// every wave pays its own tail). Otherwise it is cut into waves of half the budget, two of which are in
+// flight at a time (see b200_align_plan_run): the walk of wave k then overlaps the fill of wave k+1.
+static inline uint64_t wave_budget_words(const b200_ctx* ctx) { return std::max<uint64_t>((uint64_t)ctx->dir_budget_bytes / 4, 1 << 16); }
+static inline uint64_t wave_cap_words(uint64_t budget_words, uint64_t class_total_words) {
+    return class_total_words <= budget_words ? budget_words : std::max<uint64_t>(budget_words / 2, 1 << 15);
+}
+
 // Fills `p` (fresh or recycled) for a batch. `rebase`: offsets are taken relative to q_off[0] /
 // t_off[0] (the host entry points copy only the referenced byte range to the device).
 static int plan_build(b200_align_plan* p, b200_ctx* ctx, size_t n, const uint64_t* q_off, const uint64_t* t_off,
@@ -409,7 +441,7 @@ static int plan_build(b200_align_plan* p, b200_ctx* ctx, size_t n, const uint64_
     p->q_bytes = n ? q_off[n] - qb : 0;
     p->t_bytes = n ? t_off[n] - tb : 0;
     const bool short_scores = !ctx->force_generic && short_scores_ok(p->sc, type);
-    const uint64_t budget_words = (uint64_t)ctx->dir_budget_bytes / 4;
+    const uint64_t budget_words = wave_budget_words(ctx);
 
     // ---- uniform fast path -------------------------------------------------------------------
     if (n >= 8192 && short_scores) {
@@ -422,8 +454,10 @@ static int plan_build(b200_align_plan* p, b200_ctx* ctx, size_t n, const uint64_
         const uint64_t wpg = p->want_cigar ? (uint64_t)div_up((uint32_t)Q0, kShortRows) * T0 * 128 : 0;
         // uniform batches may be cut into equal chunks (whole 64-pair groups) so that the host entry point can
         // overlap the upload of chunk c+1 with the kernels of chunk c
-        const uint64_t groups_per_wave = chunk_pairs ? std::max<uint64_t>(1, chunk_pairs / 64) : n_groups;
-        if (uni && std::min(n_groups, groups_per_wave) * wpg <= budget_words) {
+        uint64_t groups_per_wave = chunk_pairs ? std::max<uint64_t>(1, chunk_pairs / 64) : n_groups;
+        if (!chunk_pairs && wpg) groups_per_wave = std::max<uint64_t>(1, std::min(n_groups, wave_cap_words(budget_words, n_groups * wpg) / wpg));
+        const uint64_t wave_words_u = std::min(n_groups, groups_per_wave) * wpg;
+        if (uni && wave_words_u <= (groups_per_wave < n_groups ? std::max<uint64_t>(budget_words / 2, 1 << 15) : budget_words)) {
             p->uniform = true; p->uQ = (uint32_t)Q0; p->uT = (uint32_t)T0; p->u_groups_per_wave = groups_per_wave;
             p->u_qbase = q_off[0] - qb; p->u_tbase = t_off[0] - tb;
             p->run_slots = n * (Q0 + T0 + 1);
@@ -469,7 +503,7 @@ static int plan_build(b200_align_plan* p, b200_ctx* ctx, size_t n, const uint64_
 static int plan_finish(b200_align_plan* p, b200_ctx* ctx, bool short_scores, bool sync) {
     const size_t n = p->n;
     const int type = p->type;
-    const uint64_t budget_words = (uint64_t)ctx->dir_budget_bytes / 4;
+    const uint64_t budget_words = wave_budget_words(ctx);
     std::vector<PairDesc>& pairs = p->h_pairs;
     std::vector<uint32_t> short_list, long_list, generic_list;
     const bool long_scores = !ctx->force_generic && long_scores_ok(p->sc, type);
@@ -519,6 +553,14 @@ static int plan_finish(b200_align_plan* p, b200_ctx* ctx, bool short_scores, boo
     p->n_short = short_list.size();
     {   // short waves, in whole groups
         Wave cur{kClassShort, 0, 0, 0, 0};
+        uint64_t class_total = 0;
+        if (p->want_cigar)
+            for (size_t g0 = 0; g0 < short_list.size(); g0 += 64) {   // sorted: the group's first pair has its largest block and column counts
+                uint32_t Qg = 0, Tg = 0;
+                for (size_t k = g0; k < std::min(short_list.size(), g0 + 64); ++k) { Qg = std::max(Qg, pairs[short_list[k]].Q); Tg = std::max(Tg, pairs[short_list[k]].T); }
+                class_total += (uint64_t)div_up(Qg, kShortRows) * Tg * 128;
+            }
+        const uint64_t cap_words = wave_cap_words(budget_words, class_total);
         for (size_t g0 = 0; g0 < short_list.size(); g0 += 64) {
             const size_t g1 = std::min(short_list.size(), g0 + 64);
             uint32_t Qg = 0, Tg = 0;
@@ -526,7 +568,7 @@ static int plan_finish(b200_align_plan* p, b200_ctx* ctx, bool short_scores, boo
             p->max_T_short = std::max(p->max_T_short, Tg);
             p->max_Q_short = std::max(p->max_Q_short, Qg);
             const uint64_t words = p->want_cigar ? (uint64_t)div_up(Qg, kShortRows) * Tg * 128 : 0;
-            if (cur.count && cur.dir_words + words > budget_words) {
+            if (cur.count && cur.dir_words + words > cap_words) {
                 p->waves.push_back(cur);
                 cur = Wave{kClassShort, (uint32_t)order.size(), 0, (uint32_t)groups.size(), 0};
             }
@@ -547,11 +589,17 @@ static int plan_finish(b200_align_plan* p, b200_ctx* ctx, bool short_scores, boo
     for (int pass = 0; pass < 2; ++pass) {   // warp-per-pair waves: long class, then generic
         const uint32_t klass = pass == 0 ? kClassLong : kClassGeneric;
         Wave cur{klass, (uint32_t)order.size(), 0, 0, 0};
+        auto words_of = [&](const PairDesc& d) -> uint64_t {
+            return !p->want_cigar ? 0 : (pass == 0 ? (p->long16 ? long16_dir_words(d.Q, d.T) : long_dir_words(d.Q, d.T))
+                                                   : generic_dir_words(d.Q, d.T));
+        };
+        uint64_t class_total = 0;
+        for (uint32_t idx : (pass == 0 ? long_list : generic_list)) class_total += (words_of(pairs[idx]) + 3) & ~3ull;
+        const uint64_t cap_words = wave_cap_words(budget_words, class_total);
         for (uint32_t idx : (pass == 0 ? long_list : generic_list)) {
             PairDesc& d = pairs[idx];
-            const uint64_t words = !p->want_cigar ? 0 : (pass == 0 ? (p->long16 ? long16_dir_words(d.Q, d.T) : long_dir_words(d.Q, d.T))
-                                                                   : generic_dir_words(d.Q, d.T));
-            if (cur.count && cur.dir_words + words > budget_words) {
+            const uint64_t words = words_of(d);
+            if (cur.count && cur.dir_words + words > cap_words) {
                 p->waves.push_back(cur);
                 cur = Wave{klass, (uint32_t)order.size(), 0, 0, 0};
             }
@@ -624,22 +672,23 @@ struct U32ToU64 {
     __host__ __device__ uint64_t operator()(const uint32_t& v) const { return (uint64_t)v; }
 };
 
-struct RunBufs {   // per-run device pointers shared by the launch helpers
+struct RunBufs {   // per-wave device pointers shared by the launch helpers
     const uint8_t *dq, *dt;
     uint32_t* dirs;
     int32_t* score;
     cudaStream_t st;
+    WaveSlot* ws;
 };
 
 static int launch_fill_generic(b200_align_plan* p, const uint32_t* d_work, uint32_t count, const RunBufs& rb) {
     b200_ctx* c = p->ctx;
     if (!count) return B200_OK;
     const int n_blocks = (int)std::min<uint64_t>((uint64_t)c->sm_count * 8, div_up64(count, 4));
-    TRY(c->bnd.ensure((size_t)n_blocks * 4 * (size_t)(p->max_T + 8) * sizeof(int32_t)));
-    CU(cudaMemsetAsync(c->counter.p, 0, 64, rb.st));
+    TRY(rb.ws->bnd.ensure((size_t)n_blocks * 4 * (size_t)(p->max_T + 8) * sizeof(int32_t)));
+    CU(cudaMemsetAsync(rb.ws->counter.p, 0, 64, rb.st));
     prof_begin(c, rb.st, 0);
 #define GEN(TY) fill_generic_kernel<TY><<<n_blocks, 128, 0, rb.st>>>(rb.dq, rb.dt, p->d_pairs.as<PairDesc>(), d_work, count, \
-        c->counter.as<uint32_t>(), c->flags.as<uint8_t>(), (uint8_t)0, (uint8_t)0, p->sc, rb.dirs, c->bnd.as<int32_t>(),     \
+        rb.ws->counter.as<uint32_t>(), c->flags.as<uint8_t>(), (uint8_t)0, (uint8_t)0, p->sc, rb.dirs, rb.ws->bnd.as<int32_t>(),     \
         p->max_T + 8, rb.score, c->end_i.as<uint32_t>(), c->end_j.as<uint32_t>())
     switch (p->type) { case 0: GEN(0); break; case 1: GEN(1); break; default: GEN(2); break; }
 #undef GEN
@@ -656,14 +705,14 @@ static int launch_fill_short(b200_align_plan* p, const Wave& wv, const RunBufs& 
     per_sm = std::max(per_sm, 1);
     const int n_blocks = (int)std::min<uint64_t>((uint64_t)c->sm_count * per_sm, div_up64(n_groups, kShortThreads / 32));
     const uint32_t bnd_cols = p->max_T_short + 4;
-    TRY(c->bnd_short.ensure((size_t)n_blocks * (kShortThreads / 32) * bnd_cols * 32 * sizeof(uint32_t)));
-    CU(cudaMemsetAsync(c->counter.p, 0, 64, rb.st));
+    TRY(rb.ws->bnd_short.ensure((size_t)n_blocks * (kShortThreads / 32) * bnd_cols * 32 * sizeof(uint32_t)));
+    CU(cudaMemsetAsync(rb.ws->counter.p, 0, 64, rb.st));
     const ShortConsts K = make_short_consts(p->sc, p->type);
     prof_begin(c, rb.st, 0);
     fill_short_kernel<0><<<n_blocks, kShortThreads, 0, rb.st>>>(
         c->qpk.as<uint32_t>(), c->tpk.as<uint32_t>(), p->d_pairs.as<PairDesc>(), p->d_work.as<uint32_t>() + wv.first,
-        wv.count, p->d_groups.as<ShortGroup>() + wv.first_group, c->counter.as<uint32_t>(), c->flags.as<uint8_t>(), K,
-        rb.dirs, c->bnd_short.as<uint32_t>(), bnd_cols, rb.score, c->end_i.as<uint32_t>(), c->end_j.as<uint32_t>());
+        wv.count, p->d_groups.as<ShortGroup>() + wv.first_group, rb.ws->counter.as<uint32_t>(), c->flags.as<uint8_t>(), K,
+        rb.dirs, rb.ws->bnd_short.as<uint32_t>(), bnd_cols, rb.score, c->end_i.as<uint32_t>(), c->end_j.as<uint32_t>());
     prof_end(c, rb.st);
     c->kernel_launches++;
     return B200_OK;
@@ -679,29 +728,29 @@ static int launch_fill_long(b200_align_plan* p, const Wave& wv, const RunBufs& r
     const uint64_t* d_bnd_off = p->d_bnd_off.as<uint64_t>() + wv.first_group;
     // every CTA must be resident: stripes wait (poll) on the stripe handed out just before them
     const int n_blocks = (int)std::min<uint64_t>((uint64_t)c->sm_count * per_sm, div_up64(std::max(p->max_long_tasks, 1u), 4));
-    TRY(c->bnd.ensure((p->max_long_bnd_words + 8) * sizeof(int32_t)));
-    TRY(c->progress.ensure(((size_t)p->max_long_tasks + 8) * 4));
-    TRY(c->stripe_res.ensure(((size_t)p->max_long_tasks + 8) * sizeof(StripeResult)));
-    CU(cudaMemsetAsync(c->counter.p, 0, 64, rb.st));
-    CU(cudaMemsetAsync(c->counter.as<uint32_t>() + 24, 0, 4, rb.st));
-    CU(cudaMemsetAsync(c->progress.p, 0, ((size_t)p->max_long_tasks + 8) * 4, rb.st));
+    TRY(rb.ws->bnd.ensure((p->max_long_bnd_words + 8) * sizeof(int32_t)));
+    TRY(rb.ws->progress.ensure(((size_t)p->max_long_tasks + 8) * 4));
+    TRY(rb.ws->stripe_res.ensure(((size_t)p->max_long_tasks + 8) * sizeof(StripeResult)));
+    CU(cudaMemsetAsync(rb.ws->counter.p, 0, 64, rb.st));
+    CU(cudaMemsetAsync(rb.ws->counter.as<uint32_t>() + 24, 0, 4, rb.st));
+    CU(cudaMemsetAsync(rb.ws->progress.p, 0, ((size_t)p->max_long_tasks + 8) * 4, rb.st));
     const uint32_t* d_work = p->d_work.as<uint32_t>() + wv.first;
     if (p->long16) {
         const ShortConsts K16 = make_short_consts(p->sc, p->type);
         prof_begin(c, rb.st, 0);
 #define LONG16K(TY)                                                                                                    \
     fill_long16_kernel<TY><<<n_blocks, 128, 0, rb.st>>>(c->qpk.as<uint32_t>(), c->tpk.as<uint32_t>(), p->d_pairs.as<PairDesc>(), \
-        d_work, wv.count, d_task_off, d_bnd_off, c->counter.as<uint32_t>(), c->flags.as<uint8_t>(), K16, rb.dirs,       \
-        c->bnd.as<int32_t>(), c->progress.as<uint32_t>(), c->stripe_res.as<StripeResult>(),                            \
-        c->counter.as<uint32_t>() + 24);                                                                               \
+        d_work, wv.count, d_task_off, d_bnd_off, rb.ws->counter.as<uint32_t>(), c->flags.as<uint8_t>(), K16, rb.dirs,       \
+        rb.ws->bnd.as<int32_t>(), rb.ws->progress.as<uint32_t>(), rb.ws->stripe_res.as<StripeResult>(),                            \
+        rb.ws->counter.as<uint32_t>() + 24);                                                                               \
     finalize_long_kernel<TY><<<(unsigned)div_up64(wv.count, 128), 128, 0, rb.st>>>(p->d_pairs.as<PairDesc>(), d_work,  \
-        wv.count, d_task_off, c->flags.as<uint8_t>(), c->stripe_res.as<StripeResult>(), K16.init, rb.score,            \
+        wv.count, d_task_off, c->flags.as<uint8_t>(), rb.ws->stripe_res.as<StripeResult>(), K16.init, rb.score,            \
         c->end_i.as<uint32_t>(), c->end_j.as<uint32_t>())
         if (p->type == 0) { LONG16K(0); } else if (p->type == 2) { LONG16K(2); } else {
             LONG16K(1);
             locate_long16_kernel<<<(unsigned)div_up64((uint64_t)wv.count * 32, 128), 128, 0, rb.st>>>(
                 c->qpk.as<uint32_t>(), c->tpk.as<uint32_t>(), p->d_pairs.as<PairDesc>(), d_work, wv.count, d_task_off, d_bnd_off,
-                c->flags.as<uint8_t>(), K16, c->bnd.as<int32_t>(), c->stripe_res.as<StripeResult>(), rb.score,
+                c->flags.as<uint8_t>(), K16, rb.ws->bnd.as<int32_t>(), rb.ws->stripe_res.as<StripeResult>(), rb.score,
                 c->end_i.as<uint32_t>(), c->end_j.as<uint32_t>());
             c->kernel_launches++;
         }
@@ -714,17 +763,17 @@ static int launch_fill_long(b200_align_plan* p, const Wave& wv, const RunBufs& r
     prof_begin(c, rb.st, 0);
 #define LONGK(TY)                                                                                                      \
     fill_long_kernel<TY><<<n_blocks, 128, 0, rb.st>>>(c->qpk.as<uint32_t>(), c->tpk.as<uint32_t>(), p->d_pairs.as<PairDesc>(), \
-        d_work, wv.count, d_task_off, d_bnd_off, c->counter.as<uint32_t>(), c->flags.as<uint8_t>(), K, rb.dirs,        \
-        c->bnd.as<int32_t>(), c->progress.as<uint32_t>(), c->stripe_res.as<StripeResult>(),                            \
-        c->counter.as<uint32_t>() + 24);                                                                               \
+        d_work, wv.count, d_task_off, d_bnd_off, rb.ws->counter.as<uint32_t>(), c->flags.as<uint8_t>(), K, rb.dirs,        \
+        rb.ws->bnd.as<int32_t>(), rb.ws->progress.as<uint32_t>(), rb.ws->stripe_res.as<StripeResult>(),                            \
+        rb.ws->counter.as<uint32_t>() + 24);                                                                               \
     finalize_long_kernel<TY><<<(unsigned)div_up64(wv.count, 128), 128, 0, rb.st>>>(p->d_pairs.as<PairDesc>(), d_work,  \
-        wv.count, d_task_off, c->flags.as<uint8_t>(), c->stripe_res.as<StripeResult>(), K.init, rb.score,              \
+        wv.count, d_task_off, c->flags.as<uint8_t>(), rb.ws->stripe_res.as<StripeResult>(), K.init, rb.score,              \
         c->end_i.as<uint32_t>(), c->end_j.as<uint32_t>())
     if (p->type == 0) { LONGK(0); } else if (p->type == 2) { LONGK(2); } else {
         LONGK(1);
         locate_long_kernel<<<(unsigned)div_up64((uint64_t)wv.count * 32, 128), 128, 0, rb.st>>>(
             c->qpk.as<uint32_t>(), c->tpk.as<uint32_t>(), p->d_pairs.as<PairDesc>(), d_work, wv.count, d_bnd_off,
-            c->flags.as<uint8_t>(), K, c->bnd.as<int32_t>(), rb.score, c->end_i.as<uint32_t>(), c->end_j.as<uint32_t>());
+            c->flags.as<uint8_t>(), K, rb.ws->bnd.as<int32_t>(), rb.score, c->end_i.as<uint32_t>(), c->end_j.as<uint32_t>());
         c->kernel_launches++;
     }
 #undef LONGK
@@ -773,11 +822,20 @@ extern "C" int b200_align_plan_run(b200_align_plan* p, const char* d_q_buf, cons
         if (d_cigar_off) CU(cudaMemsetAsync(d_cigar_off, 0, sizeof(uint64_t), st));
         return B200_OK;
     }
-    RunBufs rb{reinterpret_cast<const uint8_t*>(d_q_buf), reinterpret_cast<const uint8_t*>(d_t_buf), nullptr, d_score, st};
-
     uint64_t max_dir_words = 0;
     for (const Wave& w : p->waves) max_dir_words = std::max(max_dir_words, w.dir_words);
-    TRY(c->counter.ensure(128));
+    // Two waves in flight when there are several: wave k runs on stream (k & 1) with workspace slot (k & 1).
+    // Profiling runs stay on one stream so the event brackets time each kernel alone.
+    const bool overlap = p->waves.size() > 1 && c->overlap_waves && !c->profile;
+    const int n_slots = overlap ? 2 : 1;
+    if (overlap && !c->aux_stream) CU(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
+    if (!c->fork_event) CU(cudaEventCreateWithFlags(&c->fork_event, cudaEventDisableTiming));
+    for (int k = 0; k < n_slots; ++k) {
+        WaveSlot& ws = c->slot[k];
+        TRY(ws.counter.ensure(128));
+        if (!ws.done) CU(cudaEventCreateWithFlags(&ws.done, cudaEventDisableTiming));
+        if (p->want_cigar) TRY(ws.dirs.ensure(std::max<uint64_t>(max_dir_words, 4) * 4 + 64));
+    }
     TRY(c->flags.ensure(n + 8));
     TRY(c->end_i.ensure(n * 4));
     TRY(c->end_j.ensure(n * 4));
@@ -786,7 +844,6 @@ extern "C" int b200_align_plan_run(b200_align_plan* p, const char* d_q_buf, cons
         TRY(c->n_runs.ensure(n * 4));
         TRY(c->cigar_len.ensure(n * 4));
     }
-    uint32_t* d_nflag = c->counter.as<uint32_t>() + 16;
 
     const size_t n_packed = p->n_short + p->n_long;   // classes that read the 2-bit copies
     if (n_packed) {
@@ -800,44 +857,51 @@ extern "C" int b200_align_plan_run(b200_align_plan* p, const char* d_q_buf, cons
         CU(cudaStreamSynchronize(st));
         p->patched = false;
     }
-    if (p->want_cigar) TRY(c->dirs.ensure(std::max<uint64_t>(max_dir_words, 4) * 4 + 64));
     std::vector<PairDesc> patched;   // run-specific descriptors, only materialised if a fallback is needed
     std::vector<uint8_t> h_flags;
+    if (overlap) {   // the second stream starts after everything already queued on the caller's stream
+        CU(cudaEventRecord(c->fork_event, st));
+        CU(cudaStreamWaitEvent(c->aux_stream, c->fork_event, 0));
+    }
 
-    // Waves run back to back on `st`. A wave = classify (+ 2-bit pack) -> fill -> traceback walk; when the
-    // host entry point pipelines the upload, wave k first waits for the event that marks its bytes as resident.
+    // A wave = classify (+ 2-bit pack) -> fill -> traceback walk, in order on its stream; when the host entry
+    // point pipelines the upload, wave k first waits for the event that marks its bytes as resident.
     for (size_t k = 0; k < p->waves.size(); ++k) {
         const Wave& wv = p->waves[k];
+        WaveSlot& ws = c->slot[overlap ? (k & 1) : 0];
+        cudaStream_t wst = (overlap && (k & 1)) ? c->aux_stream : st;
+        RunBufs rb{reinterpret_cast<const uint8_t*>(d_q_buf), reinterpret_cast<const uint8_t*>(d_t_buf), nullptr, d_score, wst, &ws};
+        uint32_t* d_nflag = ws.counter.as<uint32_t>() + 16;
         const uint32_t* work = p->d_work.as<uint32_t>() + wv.first;
-        if (k < p->wave_events.size() && p->wave_events[k]) CU(cudaStreamWaitEvent(st, p->wave_events[k], 0));
+        if (k < p->wave_events.size() && p->wave_events[k]) CU(cudaStreamWaitEvent(wst, p->wave_events[k], 0));
         std::vector<uint32_t> fix;   // pairs of this wave that must fall back to the generic kernel
         uint64_t wave_words = wv.dir_words;
-        prof_begin(c, st, 3);
+        prof_begin(c, wst, 3);
         if (wv.klass != kClassGeneric) {
-            CU(cudaMemsetAsync(d_nflag, 0, 4, st));
+            CU(cudaMemsetAsync(d_nflag, 0, 4, wst));
             const uint32_t wpp = std::max(1u, div_up(wv.klass == kClassLong ? std::max(p->max_Q, p->max_T)
                                                                            : std::max(p->max_Q_short, p->max_T_short), 16));
             dim3 grid((unsigned)div_up64((uint64_t)wv.count * wpp, 256), 2);
-            pack_kernel<<<grid, 256, 0, st>>>(rb.dq, rb.dt, p->d_pairs.as<PairDesc>(), work, wv.count, wpp,
-                                              c->flags.as<uint8_t>(), c->qpk.as<uint32_t>(), c->tpk.as<uint32_t>(), d_nflag);
+            pack_kernel<<<grid, 256, 0, wst>>>(rb.dq, rb.dt, p->d_pairs.as<PairDesc>(), work, wv.count, wpp,
+                                               c->flags.as<uint8_t>(), c->qpk.as<uint32_t>(), c->tpk.as<uint32_t>(), d_nflag);
         } else {
-            classify_kernel<<<(unsigned)div_up64((uint64_t)wv.count * 32, 256), 256, 0, st>>>(
+            classify_kernel<<<(unsigned)div_up64((uint64_t)wv.count * 32, 256), 256, 0, wst>>>(
                 rb.dq, rb.dt, p->d_pairs.as<PairDesc>(), work, wv.count, c->flags.as<uint8_t>());
         }
-        prof_end(c, st);
+        prof_end(c, wst);
         c->kernel_launches++;
         if (wv.klass != kClassGeneric) {
             // Pairs planned for a 2-bit kernel that turn out not to be pure ACGT fall back to the generic kernel;
             // their direction matrices go behind the wave's own region. Content-dependent, hence decided here
             // (one 4-byte read-back per wave) and not in the plan.
             uint32_t n_flagged = 0;
-            CU(cudaMemcpyAsync(&n_flagged, d_nflag, 4, cudaMemcpyDeviceToHost, st));
-            CU(cudaStreamSynchronize(st));
+            CU(cudaMemcpyAsync(&n_flagged, d_nflag, 4, cudaMemcpyDeviceToHost, wst));
+            CU(cudaStreamSynchronize(wst));
             if (n_flagged) {
                 materialize_uniform_host(p);
                 h_flags.resize(n);
-                CU(cudaMemcpyAsync(h_flags.data(), c->flags.p, n, cudaMemcpyDeviceToHost, st));
-                CU(cudaStreamSynchronize(st));
+                CU(cudaMemcpyAsync(h_flags.data(), c->flags.p, n, cudaMemcpyDeviceToHost, wst));
+                CU(cudaStreamSynchronize(wst));
                 if (patched.empty()) patched = p->h_pairs;
                 for (uint32_t w = wv.first; w < wv.first + wv.count; ++w) {
                     const uint32_t idx = p->h_order[w];
@@ -849,28 +913,31 @@ extern "C" int b200_align_plan_run(b200_align_plan* p, const char* d_q_buf, cons
                     wave_words = d.dir_off + (p->want_cigar ? generic_dir_words(d.Q, d.T) : 0);
                     fix.push_back(idx);
                 }
-                CU(cudaMemcpyAsync(p->d_pairs.p, patched.data(), n * sizeof(PairDesc), cudaMemcpyHostToDevice, st));
-                CU(cudaStreamSynchronize(st));
+                // (descriptors of pairs owned by the other stream's wave are rewritten with identical bytes)
+                CU(cudaMemcpyAsync(p->d_pairs.p, patched.data(), n * sizeof(PairDesc), cudaMemcpyHostToDevice, wst));
+                CU(cudaStreamSynchronize(wst));
                 p->patched = true;
-                if (p->want_cigar) TRY(c->dirs.ensure(std::max<uint64_t>(wave_words, 4) * 4 + 64));
+                if (p->want_cigar) TRY(ws.dirs.ensure(std::max<uint64_t>(wave_words, 4) * 4 + 64));
             }
         }
-        rb.dirs = p->want_cigar ? c->dirs.as<uint32_t>() : nullptr;
+        rb.dirs = p->want_cigar ? ws.dirs.as<uint32_t>() : nullptr;
         if (wv.klass != kClassGeneric) {
             if (wv.klass == kClassShort) TRY(launch_fill_short(p, wv, rb));
             else TRY(launch_fill_long(p, wv, rb));
             if (!fix.empty()) {
-                TRY(p->d_fix_work.ensure(fix.size() * 4));
-                CU(cudaMemcpyAsync(p->d_fix_work.p, fix.data(), fix.size() * 4, cudaMemcpyHostToDevice, st));
-                CU(cudaStreamSynchronize(st));
-                TRY(launch_fill_generic(p, p->d_fix_work.as<uint32_t>(), (uint32_t)fix.size(), rb));
+                TRY(ws.fix_work.ensure(fix.size() * 4));
+                CU(cudaMemcpyAsync(ws.fix_work.p, fix.data(), fix.size() * 4, cudaMemcpyHostToDevice, wst));
+                CU(cudaStreamSynchronize(wst));
+                TRY(launch_fill_generic(p, ws.fix_work.as<uint32_t>(), (uint32_t)fix.size(), rb));
             }
         } else {
             TRY(launch_fill_generic(p, work, wv.count, rb));
         }
         if (p->want_cigar) TRY(launch_walk(p, wv.klass, work, wv.count, rb));
+        if (overlap) CU(cudaEventRecord(ws.done, wst));
     }
     CU(cudaGetLastError());
+    if (overlap) CU(cudaStreamWaitEvent(st, c->slot[1].done, 0));   // join: the rest runs on the caller's stream
 
     if (d_target_begin) {
         target_begin_kernel<<<(unsigned)div_up64(n, 256), 256, 0, st>>>((uint32_t)n, p->type, c->end_j.as<uint32_t>(), d_target_begin);
@@ -898,10 +965,11 @@ extern "C" int b200_align_plan_run(b200_align_plan* p, const char* d_q_buf, cons
     }
     CU(cudaGetLastError());
     if (p->n_long) {
-        uint32_t stalled = 0;
-        CU(cudaMemcpyAsync(&stalled, c->counter.as<uint32_t>() + 24, 4, cudaMemcpyDeviceToHost, st));
+        uint32_t stalled[2] = {0, 0};
+        for (int k = 0; k < n_slots; ++k)
+            CU(cudaMemcpyAsync(&stalled[k], c->slot[k].counter.as<uint32_t>() + 24, 4, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
-        if (stalled) return fail(B200_E_CUDA, "long-pair kernel: a stripe gave up waiting for its predecessor");
+        if (stalled[0] | stalled[1]) return fail(B200_E_CUDA, "long-pair kernel: a stripe gave up waiting for its predecessor");
     }
     prof_collect(c, st);
     return B200_OK;
@@ -1065,19 +1133,16 @@ extern "C" void b200_min_plan_destroy(b200_min_plan* p) {
 extern "C" uint64_t b200_min_plan_tuples(const b200_min_plan* p) { return p ? p->tuples : 0; }
 extern "C" const uint64_t* b200_min_plan_out_off(const b200_min_plan* p) { return p ? p->out_off.data() : nullptr; }
 
-extern "C" int b200_min_plan_create(b200_ctx* ctx, size_t n, const uint64_t* off, uint32_t k, uint32_t w,
-                                    const uint8_t* is_fwd, b200_min_plan** out) {
-    if (!ctx || !out || (n && !off)) return fail(B200_E_ARG, "b200_min_plan_create: null argument");
-    *out = nullptr;
+// Fills `p` (fresh or recycled: its device buffers keep their capacity) for a batch.
+static int min_plan_build(b200_min_plan* p, b200_ctx* ctx, size_t n, const uint64_t* off, uint32_t k, uint32_t w,
+                          const uint8_t* is_fwd) {
     TRY(set_device(ctx));
-    b200_min_plan* p = new (std::nothrow) b200_min_plan();
-    if (!p) return fail(B200_E_NOMEM, "out of host memory");
     p->ctx = ctx; p->n = n; p->k = k; p->w = w;
     p->out_off.assign(n + 1, 0);
     std::vector<MinTile> tiles;
     std::vector<uint8_t> fwd(std::max<size_t>(n, 1), 1);
     for (size_t i = 0; i < n; ++i) {
-        if (off[i + 1] < off[i] || off[i + 1] - off[i] > 0xfffffff0ull) { delete p; return fail(B200_E_ARG, "bad offsets"); }
+        if (off[i + 1] < off[i] || off[i + 1] - off[i] > 0xfffffff0ull) return fail(B200_E_ARG, "bad offsets");
         const uint64_t cnt = b200_minimize_count((uint32_t)(off[i + 1] - off[i]), k, w);
         p->out_off[i + 1] = p->out_off[i] + cnt;
         for (uint64_t f = 0; f < cnt; f += kMinTile) tiles.push_back(MinTile{(uint32_t)i, (uint32_t)f});
@@ -1089,20 +1154,27 @@ extern "C" int b200_min_plan_create(b200_ctx* ctx, size_t n, const uint64_t* off
     const uint64_t nx = (uint64_t)kMinTile + 2ull * w + 1;
     const uint64_t nwords = (nx + k - 1 + 15) / 16 + 1;
     p->smem_bytes = (size_t)((nwords + nx) * 4);
-    if (p->smem_bytes > 200 * 1024) { delete p; return fail(B200_E_ARG, "window/k-mer length too large for the shared-memory tile"); }
-    int rc = p->d_off.ensure((n + 1) * 8);
-    if (rc == B200_OK) rc = p->d_out_off.ensure((n + 1) * 8);
-    if (rc == B200_OK) rc = p->d_fwd.ensure(std::max<size_t>(n, 1));
-    if (rc == B200_OK) rc = p->d_tiles.ensure(std::max<size_t>(tiles.size(), 1) * sizeof(MinTile));
-    if (rc == B200_OK) {
-        cudaError_t e = cudaSuccess;
-        if (n) e = cudaMemcpyAsync(p->d_off.p, off, (n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(p->d_out_off.p, p->out_off.data(), (n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream);
-        if (e == cudaSuccess && n) e = cudaMemcpyAsync(p->d_fwd.p, fwd.data(), n, cudaMemcpyHostToDevice, ctx->stream);
-        if (e == cudaSuccess && !tiles.empty()) e = cudaMemcpyAsync(p->d_tiles.p, tiles.data(), tiles.size() * sizeof(MinTile), cudaMemcpyHostToDevice, ctx->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-        if (e != cudaSuccess) rc = fail(B200_E_CUDA, std::string("min plan upload: ") + cudaGetErrorString(e));
-    }
+    if (p->smem_bytes > 200 * 1024) return fail(B200_E_ARG, "window/k-mer length too large for the shared-memory tile");
+    TRY(p->d_off.ensure((n + 1) * 8));
+    TRY(p->d_out_off.ensure((n + 1) * 8));
+    TRY(p->d_fwd.ensure(std::max<size_t>(n, 1)));
+    TRY(p->d_tiles.ensure(std::max<size_t>(tiles.size(), 1) * sizeof(MinTile)));
+    if (n) CU(cudaMemcpyAsync(p->d_off.p, off, (n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(p->d_out_off.p, p->out_off.data(), (n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (n) CU(cudaMemcpyAsync(p->d_fwd.p, fwd.data(), n, cudaMemcpyHostToDevice, ctx->stream));
+    if (!tiles.empty()) CU(cudaMemcpyAsync(p->d_tiles.p, tiles.data(), tiles.size() * sizeof(MinTile), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));   // the sources are stack/heap temporaries
+    return B200_OK;
+}
+
+extern "C" int b200_min_plan_create(b200_ctx* ctx, size_t n, const uint64_t* off, uint32_t k, uint32_t w,
+                                    const uint8_t* is_fwd, b200_min_plan** out) {
+    if (!ctx || !out || (n && !off)) return fail(B200_E_ARG, "b200_min_plan_create: null argument");
+    *out = nullptr;
+    b200_min_plan* p = new (std::nothrow) b200_min_plan();
+    if (!p) return fail(B200_E_NOMEM, "out of host memory");
+    p->ctx = ctx;
+    const int rc = min_plan_build(p, ctx, n, off, k, w, is_fwd);
     if (rc != B200_OK) { b200_min_plan_destroy(p); return rc; }
     *out = p;
     return B200_OK;
@@ -1388,20 +1460,24 @@ extern "C" int b200_map_batch(b200_ctx* c, const b200_index* ix, size_t n, const
     TRY(c->d_q.ensure(r1 - r0 + 64));
     if (r1 > r0) CU(cudaMemcpyAsync(c->d_q.p, reads_buf + r0, r1 - r0, cudaMemcpyHostToDevice, st));
     c->h2d_bytes += r1 - r0;
-    b200_min_plan* mp = nullptr;
-    TRY(b200_min_plan_create(c, n, off.data(), k, w, nullptr, &mp));
-    struct MG { b200_min_plan* p; ~MG() { b200_min_plan_destroy(p); } } mg{mp};
+    if (!c->map_min_plan) {
+        c->map_min_plan = new (std::nothrow) b200_min_plan();
+        if (!c->map_min_plan) return fail(B200_E_NOMEM, "out of host memory");
+        c->map_min_plan->ctx = c;
+    }
+    b200_min_plan* mp = c->map_min_plan;
+    TRY(min_plan_build(mp, c, n, off.data(), k, w, nullptr));
     const uint64_t tot = mp->tuples;
     for (size_t i = 0; i < n; ++i) out[i] = b200_mapping{0, 1, 0, 0, 0, 0, 0, 0};
     if (cigar_off) for (size_t i = 0; i <= n; ++i) cigar_off[i] = 0;
     if (tot == 0) return B200_OK;
     if (tot > 0x7ffffff0ull) return fail(B200_E_ARG, "too many minimizers in one batch: split the reads");
 
-    DevBuf b_hash, b_pos, b_flag, b_keep, b_slot, b_dhash, b_dpos, b_first, b_doff, b_cf, b_cr, b_lof, b_lor, b_mof, b_mor,
-        b_mff, b_mfs, b_mrf, b_mrs, b_rof, b_ror, b_lis, b_prev, b_chf, b_chr, b_reg;
-    struct BG { std::vector<DevBuf*> v; ~BG() { for (auto* b : v) b->release(); } } bg{{&b_hash, &b_pos, &b_flag, &b_keep, &b_slot,
-        &b_dhash, &b_dpos, &b_first, &b_doff, &b_cf, &b_cr, &b_lof, &b_lor, &b_mof, &b_mor, &b_mff, &b_mfs, &b_mrf, &b_mrs,
-        &b_rof, &b_ror, &b_lis, &b_prev, &b_chf, &b_chr, &b_reg}};
+    DevBuf* mb_ = c->map_buf;
+    DevBuf &b_hash = mb_[0], &b_pos = mb_[1], &b_flag = mb_[2], &b_keep = mb_[3], &b_slot = mb_[4], &b_dhash = mb_[5], &b_dpos = mb_[6],
+           &b_first = mb_[7], &b_doff = mb_[8], &b_cf = mb_[9], &b_cr = mb_[10], &b_lof = mb_[11], &b_lor = mb_[12], &b_mof = mb_[13],
+           &b_mor = mb_[14], &b_mff = mb_[15], &b_mfs = mb_[16], &b_mrf = mb_[17], &b_mrs = mb_[18], &b_rof = mb_[19], &b_ror = mb_[20],
+           &b_lis = mb_[21], &b_prev = mb_[22], &b_chf = mb_[23], &b_chr = mb_[24], &b_reg = mb_[25], &b_pm = mb_[26];
     TRY(b_hash.ensure(tot * 4)); TRY(b_pos.ensure(tot * 4)); TRY(b_flag.ensure(tot));
     TRY(b200_min_plan_run(mp, c->d_q.as<char>(), b_hash.as<uint32_t>(), b_pos.as<uint32_t>(), b_flag.as<uint8_t>(), st));
     if (tr.on) { cudaStreamSynchronize(st); tr.mark("upload+minimize"); }
@@ -1452,13 +1528,13 @@ extern "C" int b200_map_batch(b200_ctx* c, const b200_index* ix, size_t n, const
 
     // ---- chaining (FindLIS) per strand, strand choice, region
     const size_t n_mmax = std::max<size_t>(std::max(n_mf, n_mr), 1);
-    TRY(b_lis.ensure(n_mmax * 4)); TRY(b_prev.ensure(n_mmax * 4));
+    TRY(b_lis.ensure(n_mmax * 4)); TRY(b_prev.ensure(n_mmax * 4)); TRY(b_pm.ensure(n_mmax * 4));
     TRY(b_chf.ensure(n * sizeof(ChainResult))); TRY(b_chr.ensure(n * sizeof(ChainResult))); TRY(b_reg.ensure(n * sizeof(Region)));
     const unsigned cb = (unsigned)div_up64(n * 32, 128);
     chain_kernel<<<cb, 128, 0, st>>>(b_mff.as<uint32_t>(), b_mfs.as<uint32_t>(), b_rof.as<uint32_t>(), nr, b_lis.as<uint32_t>(),
-                                     b_prev.as<int32_t>(), b_chf.as<ChainResult>());
+                                     b_prev.as<int32_t>(), b_pm.as<uint32_t>(), b_chf.as<ChainResult>());
     chain_kernel<<<cb, 128, 0, st>>>(b_mrf.as<uint32_t>(), b_mrs.as<uint32_t>(), b_ror.as<uint32_t>(), nr, b_lis.as<uint32_t>(),
-                                     b_prev.as<int32_t>(), b_chr.as<ChainResult>());
+                                     b_prev.as<int32_t>(), b_pm.as<uint32_t>(), b_chr.as<ChainResult>());
     region_kernel<<<(unsigned)div_up64(n, 256), 256, 0, st>>>(b_chf.as<ChainResult>(), b_chr.as<ChainResult>(), nr, k,
                                                               mp->d_off.as<uint64_t>(), ix->ref_len, b_reg.as<Region>());
     c->kernel_launches += 3;
@@ -1473,9 +1549,11 @@ extern "C" int b200_map_batch(b200_ctx* c, const b200_index* ix, size_t n, const
     for (size_t i = 0; i < n; ++i) if (reg[i].mapped) mapped.push_back((uint32_t)i);
     const size_t nm = mapped.size();
     if (nm == 0) return B200_OK;
-    b200_align_plan* plan = new (std::nothrow) b200_align_plan();
-    if (!plan) return fail(B200_E_NOMEM, "out of host memory");
-    struct PG { b200_align_plan* p; ~PG() { b200_align_plan_destroy(p); } } pg{plan};
+    if (!c->map_plan) {
+        c->map_plan = new (std::nothrow) b200_align_plan();
+        if (!c->map_plan) return fail(B200_E_NOMEM, "out of host memory");
+    }
+    b200_align_plan* plan = c->map_plan;
     plan->reset();
     plan->ctx = c; plan->n = nm; plan->type = type; plan->sc = Scores{match, mismatch, gap}; plan->want_cigar = want_cigar != 0;
     plan->h_pairs.resize(nm);

@@ -143,9 +143,16 @@ struct ChainResult {
     uint32_t len, first_f, first_s, last_f, last_s, pad;
 };
 
+// Matches are taken 32 at a time (one per lane). For a block [i0, i0+32) every lane first scans the
+// finished prefix j < i0 on its own: the prefix is fetched 32 entries at a time (coalesced) and handed
+// round by shuffle, so there is no reduction per match; then the 32 in-block predecessors are handed
+// round in index order. The distance test f[i]-f[j] < 5000 makes most of a long read's prefix
+// irrelevant: with pm[j] = max f[0..j] (one scan up front), every j with pm[j] <= min_block(f[i]) - 5000
+// fails the test for the whole block and is skipped -- exact whatever the order of f, and f is in fact
+// ascending except for the last w-1 minimizers of a read.
 __global__ void __launch_bounds__(128)
 chain_kernel(const uint32_t* __restrict__ mf, const uint32_t* __restrict__ ms, const uint32_t* __restrict__ roff,
-             uint32_t n_reads, uint32_t* lis, int32_t* prev, ChainResult* __restrict__ out) {
+             uint32_t n_reads, uint32_t* lis, int32_t* prev, uint32_t* pmax, ChainResult* __restrict__ out) {
     const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (r >= n_reads) return;
@@ -153,31 +160,72 @@ chain_kernel(const uint32_t* __restrict__ mf, const uint32_t* __restrict__ ms, c
     if (n == 0) { if (lane == 0) out[r] = ChainResult{0, 0, 0, 0, 0, 0}; return; }
     const uint32_t* f = mf + a;
     const uint32_t* s = ms + a;
-    volatile uint32_t* L = lis + a;
+    uint32_t* L = lis + a;
     int32_t* P = prev + a;
-    if (lane == 0) { L[0] = 1; P[0] = -1; }
-    __syncwarp();
-    for (uint32_t i = 1; i < n; ++i) {
-        const uint32_t fi = f[i], si = s[i];
-        uint32_t best = 0, bj = 0xffffffffu;
-        for (uint32_t j = lane; j < i; j += kWarp) {
-            const uint32_t fj = f[j], sj = s[j];
-            if (si > sj && fi != fj && (fi - fj) < 5000u && (si - sj) < 5000u) {
-                const uint32_t cand = L[j] + 1;
-                if (cand > best) { best = cand; bj = j; }
-            }
-        }
+    uint32_t* PM = pmax + a;
+    {   // prefix maxima of f
+        uint32_t carry = 0;
+        for (uint32_t c = 0; c < n; c += kWarp) {
+            uint32_t v = c + lane < n ? __ldg(f + c + lane) : 0u;
 #pragma unroll
-        for (int o = 16; o; o >>= 1) {
-            const uint32_t ob = __shfl_xor_sync(kFull, best, o), oj = __shfl_xor_sync(kFull, bj, o);
-            if (ob > best || (ob == best && oj < bj)) { best = ob; bj = oj; }
+            for (int o = 1; o < kWarp; o <<= 1) { const uint32_t u = __shfl_up_sync(kFull, v, o); if (lane >= o) v = max(v, u); }
+            v = max(v, carry);
+            if (c + lane < n) __stcg(PM + c + lane, v);
+            carry = __shfl_sync(kFull, v, kWarp - 1);
         }
-        if (lane == 0) { L[i] = best ? best : 1u; P[i] = best ? (int32_t)bj : -1; }
         __syncwarp();
     }
-    // first index of the maximum (std::max_element)
-    uint32_t mx = 0, mi = 0xffffffffu;
-    for (uint32_t i = lane; i < n; i += kWarp) { const uint32_t v = L[i]; if (v > mx) { mx = v; mi = i; } }
+    uint32_t mx = 0, mi = 0xffffffffu;   // running first maximum (std::max_element)
+    uint32_t jstart = 0, last_min = 0;
+    for (uint32_t i0 = 0; i0 < n; i0 += kWarp) {
+        const uint32_t i = i0 + lane;
+        const bool valid = i < n;
+        const uint32_t fi = valid ? __ldg(f + i) : 0u, si = valid ? __ldg(s + i) : 0u;
+        uint32_t fmin = valid ? fi : 0xffffffffu;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) fmin = min(fmin, __shfl_xor_sync(kFull, fmin, o));
+        if (fmin < last_min) jstart = 0;
+        last_min = fmin;
+        if (fmin >= 5000u) {   // skip the prefix that is out of reach of every match of this block
+            const uint32_t thr = fmin - 5000u;
+            for (;;) {
+                const uint32_t idx = jstart + lane;
+                const bool skip = idx < i0 && __ldcg(PM + idx) <= thr;
+                const uint32_t b = __ballot_sync(kFull, skip);
+                if (b == kFull) { jstart += kWarp; continue; }
+                jstart += __ffs(~b) - 1;
+                break;
+            }
+        }
+        uint32_t best = 0, bj = 0xffffffffu;
+        for (uint32_t c = jstart; c < i0; c += kWarp) {
+            const uint32_t idx = c + lane;
+            const uint32_t cf = idx < i0 ? __ldg(f + idx) : 0u, cs = idx < i0 ? __ldg(s + idx) : 0u;
+            const uint32_t cl = idx < i0 ? __ldcg(L + idx) : 0u;
+            const uint32_t cnt = min((uint32_t)kWarp, i0 - c);
+            for (uint32_t t = 0; t < cnt; ++t) {
+                const uint32_t fj = __shfl_sync(kFull, cf, (int)t), sj = __shfl_sync(kFull, cs, (int)t);
+                const uint32_t lj = __shfl_sync(kFull, cl, (int)t);
+                if (si > sj && fi != fj && (fi - fj) < 5000u && (si - sj) < 5000u && lj + 1 > best) { best = lj + 1; bj = c + t; }
+            }
+        }
+        const uint32_t in_block = min((uint32_t)kWarp, n - i0);
+        for (uint32_t jj = 0; jj + 1 < in_block; ++jj) {
+            // lane jj has seen every j < i0 + jj: its value is final
+            const uint32_t fj = __shfl_sync(kFull, fi, (int)jj), sj = __shfl_sync(kFull, si, (int)jj);
+            const uint32_t lj = __shfl_sync(kFull, best ? best : 1u, (int)jj);
+            if ((uint32_t)lane > jj && si > sj && fi != fj && (fi - fj) < 5000u && (si - sj) < 5000u && lj + 1 > best) {
+                best = lj + 1; bj = i0 + jj;
+            }
+        }
+        const uint32_t li = best ? best : 1u;
+        if (valid) {
+            __stcg(L + i, li);
+            P[i] = best ? (int32_t)bj : -1;
+            if (li > mx) { mx = li; mi = i; }   // per lane: indices ascend, so the first maximum is kept
+        }
+        __syncwarp();
+    }
 #pragma unroll
     for (int o = 16; o; o >>= 1) {
         const uint32_t ob = __shfl_xor_sync(kFull, mx, o), oi = __shfl_xor_sync(kFull, mi, o);
