@@ -1145,15 +1145,19 @@ static int min_plan_build(b200_min_plan* p, b200_ctx* ctx, size_t n, const uint6
         if (off[i + 1] < off[i] || off[i + 1] - off[i] > 0xfffffff0ull) return fail(B200_E_ARG, "bad offsets");
         const uint64_t cnt = b200_minimize_count((uint32_t)(off[i + 1] - off[i]), k, w);
         p->out_off[i + 1] = p->out_off[i] + cnt;
-        for (uint64_t f = 0; f < cnt; f += kMinTile) tiles.push_back(MinTile{(uint32_t)i, (uint32_t)f});
+        // tiles end at multiples of kMinTile in the GLOBAL output index space (vector stores need the alignment)
+        for (uint64_t f = 0; f < cnt;) {
+            tiles.push_back(MinTile{(uint32_t)i, (uint32_t)f});
+            f += kMinTile - ((p->out_off[i] + f) & (uint64_t)(kMinTile - 1));
+        }
         if (is_fwd) fwd[i] = is_fwd[i] ? 1 : 0;
     }
     p->tuples = p->out_off[n];
     p->n_tiles = tiles.size();
-    // shared memory: packed codes + one hash per k-mer the tile can touch
+    // shared memory: the packed 2-bit codes of every base the tile can touch (+ spare words, see the kernel)
     const uint64_t nx = (uint64_t)kMinTile + 2ull * w + 1;
-    const uint64_t nwords = (nx + k - 1 + 15) / 16 + 1;
-    p->smem_bytes = (size_t)((nwords + nx) * 4);
+    const uint64_t nwords = (nx + k - 1 + 15) / 16 + 3;
+    p->smem_bytes = (size_t)(nwords * 4);
     if (p->smem_bytes > 200 * 1024) return fail(B200_E_ARG, "window/k-mer length too large for the shared-memory tile");
     TRY(p->d_off.ensure((n + 1) * 8));
     TRY(p->d_out_off.ensure((n + 1) * 8));
@@ -1188,11 +1192,20 @@ extern "C" int b200_min_plan_run(b200_min_plan* p, const char* d_buf, uint32_t* 
     b200_ctx* c = p->ctx;
     TRY(set_device(c));
     cudaStream_t st = (cudaStream_t)stream;   // used as given: 0 is the CUDA default stream
-    if (p->smem_bytes > 48 * 1024)
-        CU(cudaFuncSetAttribute(minimize_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes));
-    minimize_kernel<0><<<(unsigned)p->n_tiles, kMinThreads, p->smem_bytes, st>>>(
-        reinterpret_cast<const uint8_t*>(d_buf), p->d_off.as<uint64_t>(), p->d_out_off.as<uint64_t>(),
-        p->d_fwd.as<uint8_t>(), p->d_tiles.as<MinTile>(), p->k, p->w, d_hash, d_pos, d_flag);
+    // register fast path for the common window lengths; it stores 16-byte vectors, so the output arrays must be aligned
+    const bool aligned = ((reinterpret_cast<uintptr_t>(d_hash) | reinterpret_cast<uintptr_t>(d_pos)) & 15u) == 0 &&
+                         (reinterpret_cast<uintptr_t>(d_flag) & 7u) == 0;
+    const uint32_t W = (aligned && p->w >= 1 && p->w <= (uint32_t)kMinMaxW) ? p->w : 0;
+#define MINK(WW)                                                                                                         \
+    case WW:                                                                                                             \
+        if (p->smem_bytes > 48 * 1024)                                                                                   \
+            CU(cudaFuncSetAttribute(minimize_kernel<WW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes)); \
+        minimize_kernel<WW><<<(unsigned)p->n_tiles, kMinThreads, p->smem_bytes, st>>>(                                   \
+            reinterpret_cast<const uint8_t*>(d_buf), p->d_off.as<uint64_t>(), p->d_out_off.as<uint64_t>(),               \
+            p->d_fwd.as<uint8_t>(), p->d_tiles.as<MinTile>(), p->k, p->w, d_hash, d_pos, d_flag);                        \
+        break;
+    switch (W) { MINK(1) MINK(2) MINK(3) MINK(4) MINK(5) MINK(6) MINK(7) MINK(8) default: MINK(0) }
+#undef MINK
     c->kernel_launches++;
     CU(cudaGetLastError());
     return B200_OK;

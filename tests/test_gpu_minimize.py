@@ -74,3 +74,24 @@ def test_empty_batch_and_capacity_error(ctx):
     rc = capi.lib().b200_minimize_batch_packed(ctx.h, 1, buf.ctypes.data, off.ctypes.data, 15, 5, None, h.ctypes.data,
                                                p.ctypes.data, f.ctypes.data, ooff.ctypes.data, 2)
     assert rc == capi.E_CAP
+
+
+def test_every_fast_path_window_length_ragged_batches(ctx):
+    """The register fast path (w = 1..8) stores 8 tuples at a time on 32-byte boundaries of the global output
+    arrays: sequences of odd lengths put every alignment of a sequence start inside a store chunk, long ones
+    cross the 2048-tuple tiles, all-G runs produce the zero tuple inside vector stores."""
+    rng = np.random.default_rng(17)
+    pyr = random.Random(17)
+    for w in range(1, 10):
+        for k in (1, 7, 15, 16, 21):
+            seqs = []
+            for _ in range(24):
+                n = int(rng.integers(k + w, 700))
+                seqs.append(seqgen.random_dna(rng, n).tobytes())
+            seqs.append(seqgen.random_dna(rng, 5000 + w).tobytes())
+            seqs.append(b"G" * 300 + seqgen.random_dna(rng, 77).tobytes() + b"G" * 90)
+            seqs.append(bytes(pyr.choice(b"ACGTNacgt-") for _ in range(333)))
+            fw = [pyr.randint(0, 1) for _ in seqs]
+            got = ctx.minimize(seqs, k, w, fw)
+            for s, f, g in zip(seqs, fw, got):
+                assert _same(g, ORACLE.minimize(s, k, w, bool(f))), (k, w, len(s))
