@@ -326,6 +326,16 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # one rank per GPU: run on (and first-touch the pinned staging buffers from) the CPUs next to this GPU, so
+        # that eight concurrent uploads do not all cross the socket interconnect
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
+            config["cpu_affinity"] = "GPU-local (nvmlDeviceSetCpuAffinity)"
+        except Exception as e:   # affinity is an optimisation, never a requirement
+            config["cpu_affinity"] = "unchanged (%s)" % type(e).__name__
+    if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
 

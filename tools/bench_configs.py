@@ -1,0 +1,217 @@
+#!/usr/bin/env python3
+"""BASELINE.json configs 3, 4 and 5 at their stated sizes (not the judged bench -- that is bench.py).
+
+  c3  Minimize k=15 w=5: index build over a 4.6 Mbp reference + MinimizeBatch over 100 k ONT-like reads
+  c4  end-to-end mapping of 100 k ONT-like reads (minimizers -> seeds -> chains -> semiGlobal Align + CIGAR)
+  c5  10 k local 10 kb x 10 kb pairs with full traceback
+
+Strong scaling: under torchrun the reads / pairs are split evenly over the ranks (no collective on the data
+path; the index is rebuilt on every GPU), every number is work of all ranks / max-over-ranks time. The read
+set is 2048 distinct ONT-like reads (seeded) repeated to the stated count: the kernels' cost does not depend
+on read identity, generating 100 k distinct reads in numpy would take minutes.
+
+  python tools/bench_configs.py [--configs c3,c4,c5] [--reads 100000] [--pairs 10000]
+  python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 tools/bench_configs.py ...
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--configs", default="c3,c4,c5")
+    ap.add_argument("--reads", type=int, default=100_000)
+    ap.add_argument("--pairs", type=int, default=10_000)
+    ap.add_argument("--batch", type=int, default=16384, help="reads per b200_map_batch / MinimizeBatch call")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    import torch
+    import torch.distributed as dist
+    import seqgen
+    from bioinfo1_b200 import capi
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = capi.lib()
+    ctx = capi.Context(local_rank)
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0}
+
+    def sync_max(seconds):
+        t = torch.tensor([seconds], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def emit(obj):
+        if rank == 0:
+            obj["n_gpus"] = world
+            print(json.dumps(obj), flush=True)
+
+    cfgs = args.configs.split(",")
+    rng = np.random.default_rng(1)
+    ref = seqgen.random_dna(rng, 4_600_000)
+    comp = bytes.maketrans(b"ACGT", b"TGCA")
+
+    def read_set(total):
+        """`total` reads as one packed buffer: 2048 distinct reads from both strands, tiled."""
+        base = []
+        for i in range(2048):
+            Lr = int(np.clip(rng.lognormal(np.log(8000) - 0.125, 0.5), 1000, 40000))
+            s0 = int(rng.integers(0, len(ref) - Lr))
+            q = seqgen.mutate(rng, ref[s0:s0 + Lr], sub=0.024, ins=0.048, dele=0.048).tobytes()
+            base.append(q.translate(comp)[::-1] if i % 2 else q)
+        lens = np.array([len(b) for b in base], dtype=np.uint64)
+        buf1 = np.frombuffer(b"".join(base), dtype=np.uint8)
+        reps = (total + 2047) // 2048
+        return buf1, lens, reps
+
+    if "c3" in cfgs or "c4" in cfgs:
+        buf1, lens1, reps = read_set(args.reads)
+        lo, hi = args.reads * rank // world, args.reads * (rank + 1) // world      # this rank's reads
+        t0 = time.perf_counter()
+        index = capi.Index(ctx, ref.tobytes(), 15, 5, 0.001)
+        torch.cuda.synchronize()
+        t_index = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        index2 = capi.Index(ctx, ref.tobytes(), 15, 5, 0.001)   # second build: allocations and modules warm
+        torch.cuda.synchronize()
+        t_index2 = time.perf_counter() - t0
+        index2.close()
+
+        def batches():
+            """(packed buffer, offsets) per batch of this rank's reads; read g is base read g % 2048"""
+            for a in range(lo, hi, args.batch):
+                b = min(hi, a + args.batch)
+                ids = np.arange(a, b) % 2048
+                ll = lens1[ids]
+                off = np.zeros(len(ids) + 1, dtype=np.uint64)
+                off[1:] = np.cumsum(ll)
+                starts = np.concatenate([[0], np.cumsum(lens1)]).astype(np.int64)
+                out = np.empty(int(off[-1]) + 1, dtype=np.uint8)
+                for k, i in enumerate(ids):
+                    out[int(off[k]):int(off[k + 1])] = buf1[starts[i]:starts[i] + int(lens1[i])]
+                yield out, off
+
+        if "c3" in cfgs:
+            # MinimizeBatch over the rank's reads, device-resident (inputs uploaded before the timed region)
+            tot_bases = tot_tuples = 0
+            t_dev = 0.0
+            for bufb, off in batches():
+                n = len(off) - 1
+                d_buf = torch.from_numpy(bufb).to(dev)
+                plan = C.c_void_p()
+                capi.check(L.b200_min_plan_create(ctx.h, n, off.ctypes.data, 15, 5, None, C.byref(plan)))
+                tot = int(L.b200_min_plan_tuples(plan))
+                d_h = torch.empty(tot, dtype=torch.int32, device=dev); d_p = torch.empty(tot, dtype=torch.int32, device=dev)
+                d_f = torch.empty(tot, dtype=torch.uint8, device=dev)
+                st = torch.cuda.current_stream()
+                for _ in range(2):
+                    capi.check(L.b200_min_plan_run(plan, d_buf.data_ptr(), d_h.data_ptr(), d_p.data_ptr(), d_f.data_ptr(), st.cuda_stream))
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(st)
+                for _ in range(5):
+                    capi.check(L.b200_min_plan_run(plan, d_buf.data_ptr(), d_h.data_ptr(), d_p.data_ptr(), d_f.data_ptr(), st.cuda_stream))
+                e1.record(st)
+                torch.cuda.synchronize()
+                t_dev += e0.elapsed_time(e1) / 5 * 1e-3
+                tot_bases += int(off[-1]); tot_tuples += tot
+                L.b200_min_plan_destroy(plan)
+                del d_buf, d_h, d_p, d_f
+            t = sync_max(t_dev)
+            sums = torch.tensor([tot_bases, tot_tuples], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(sums)
+            bases, tuples = float(sums[0]), float(sums[1])
+            alg = bases + 9 * tuples
+            emit({"config": "c3", "reads": args.reads, "bases": bases, "tuples": tuples, "minimize_s": t,
+                  "gbases_per_s": bases / t / 1e9, "hbm_gbs_algorithmic": alg / t / 1e9,
+                  "roofline_frac_hbm_per_gpu": alg / t / 1e9 / world / peaks["hbm_gbs"],
+                  "index_build_s_cold": t_index, "index_build_s_warm": t_index2,
+                  "index_stats": [int(x) for x in index.stats()]})
+
+        if "c4" in cfgs:
+            all_batches = list(batches())      # assembled before the timed region (test-harness work, not the product's)
+            max_n = max(len(off) - 1 for _, off in all_batches)
+            max_cap = max(int(4 * int(off[-1]) + 64 * (len(off) - 1) + 64) for _, off in all_batches)
+            out = np.zeros(max_n, dtype=capi.MAPPING_DTYPE)
+            cig = np.empty(max_cap, dtype=np.uint8); coff = np.zeros(max_n + 1, dtype=np.uint64)
+
+            def run_all(which):
+                mapped = 0
+                for bufb, off in which:
+                    n = len(off) - 1
+                    capi.check(L.b200_map_batch(ctx.h, index.h, n, bufb.ctypes.data, off.ctypes.data, 1, 2, 1, -1, -1, 1,
+                                                out.ctypes.data, cig.ctypes.data, coff.ctypes.data, max_cap))
+                    mapped += int(out["mapped"][:n].sum())
+                return mapped
+            run_all(all_batches[:1])   # warm-up on one batch so the context's scratch buffers have their size
+            barrier()
+            t0 = time.perf_counter()
+            mapped = run_all(all_batches)
+            torch.cuda.synchronize()
+            t = sync_max(time.perf_counter() - t0)
+            m = torch.tensor([mapped], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(m)
+            emit({"config": "c4", "reads": args.reads, "mapped": float(m[0]), "map_s": t, "mapped_reads_per_s": float(m[0]) / t,
+                  "batch_reads": args.batch,
+                  "note": "host buffers in, PAF fields + CIGAR out (b200_map_batch), semiGlobal 1/-1/-1, k=15 w=5 f=0.001"})
+        index.close()
+
+    if "c5" in cfgs:
+        fq, ft = seqgen.ont_like_pairs(4343, 64, fixed=10000)
+        lo, hi = args.pairs * rank // world, args.pairs * (rank + 1) // world
+        n = hi - lo
+        ids = np.arange(lo, hi) % 64
+        qb, qo = seqgen.pack_arrays([fq[i] for i in ids])
+        tb, to = seqgen.pack_arrays([ft[i] for i in ids])
+        d_q, d_t = torch.from_numpy(qb).to(dev), torch.from_numpy(tb).to(dev)
+        plan = C.c_void_p()
+        capi.check(L.b200_align_plan_create(ctx.h, n, qo.ctypes.data, to.ctypes.data, 1, 1, -1, -1, 1, C.byref(plan)))
+        cells = int(L.b200_align_plan_cells(plan))
+        cap = int(L.b200_align_plan_cigar_bound(plan))
+        d_s = torch.empty(n, dtype=torch.int32, device=dev); d_b = torch.empty(n, dtype=torch.int32, device=dev)
+        d_c = torch.empty(cap, dtype=torch.uint8, device=dev); d_o = torch.empty(n + 1, dtype=torch.int64, device=dev)
+        st = torch.cuda.current_stream()
+
+        def step():
+            capi.check(L.b200_align_plan_run(plan, d_q.data_ptr(), d_t.data_ptr(), d_s.data_ptr(), d_b.data_ptr(),
+                                             d_c.data_ptr(), d_o.data_ptr(), cap, st.cuda_stream))
+        step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        for _ in range(2):
+            step()
+        e1.record(st)
+        torch.cuda.synchronize()
+        t = sync_max(e0.elapsed_time(e1) / 2 * 1e-3)
+        c = torch.tensor([cells], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(c)
+        emit({"config": "c5", "pairs": args.pairs, "cells": float(c[0]), "s_per_pass": t, "gcups": float(c[0]) / t / 1e9,
+              "dir_bytes": float(c[0]) / 4, "note": "local 10 kb x 10 kb, score + CIGAR + target_begin, device-resident"})
+        L.b200_align_plan_destroy(plan)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
