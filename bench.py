@@ -238,8 +238,8 @@ def extra_workloads(ctx, capi, torch, dev, peaks):
 
     # MinimizeBatch, k=15 w=5: the reference (both strands) and ONT-like reads
     reads, _ = seqgen.ont_like_pairs(2, 256, mean_len=8000)
-    reads = reads * 16
-    for tag, seqs in (("minimize_ref_4.6Mbp_x2", [ref, ref[::-1].copy()]), ("minimize_4096_ont_reads", reads)):
+    reads = reads * 64
+    for tag, seqs in (("minimize_ref_4.6Mbp_x2", [ref, ref[::-1].copy()]), ("minimize_16384_ont_reads", reads)):
         buf, off = seqgen.pack_arrays(seqs)
         d_buf = torch.from_numpy(buf).to(dev)
         plan = C.c_void_p()
@@ -404,9 +404,17 @@ def main():
     ctx.set_option("profile", 0)
     peaks = load_peaks()
     fill_s = fill_ns * 1e-9 / prof_steps   # all fill launches of one step (a step is cut into waves)
+    # DRAM bytes of one fill launch from the committed `ncu --set full` capture of this kernel on this workload
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")))
+        if args.pairs == tr["fill_short_kernel"]["pairs"] and args.length == 150 and args.type == 0:
+            traffic = tr["fill_short_kernel"]["dram_bytes_per_launch"]
+    except Exception:
+        pass
     achieved_tops = cells * OPS_PER_CELL / fill_s / 1e12
     roofline = {"bound": "int-alu", "kernel": "DP fill", "achieved": achieved_tops, "peak": peaks["int_tops"],
-                "unit": "Tint-op/s", "frac": achieved_tops / peaks["int_tops"], "traffic": None,
+                "unit": "Tint-op/s", "frac": achieved_tops / peaks["int_tops"], "traffic": traffic,
                 "ops_per_cell": OPS_PER_CELL, "fill_gcups": cells / fill_s / 1e9, "fill_ms_per_step": fill_s * 1e3,
                 "fill_launches_per_step": fill_l / prof_steps,
                 "peak_source": peaks["int_source"],

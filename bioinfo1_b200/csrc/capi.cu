@@ -16,6 +16,7 @@
 #include <vector>
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_run_length_encode.cuh>
 #include <cub/device/device_scan.cuh>
 #include <cub/device/device_select.cuh>
 #include <cub/iterator/transform_input_iterator.cuh>
@@ -1396,42 +1397,46 @@ extern "C" int b200_index_build(b200_ctx* c, const char* ref, uint64_t ref_len, 
         c->kernel_launches++;
     }
     // frequency filter: the top int(f * |distinct reverse tuples|) forward hashes by window count, applied to both
-    // strands (team_mapper.cpp:433-434, :447-450, :467-470). Host side: it runs once per reference.
-    std::vector<uint32_t> banned;
+    // strands (team_mapper.cpp:433-434, :447-450, :467-470)
     TRY(sort_unique_keys(c, d_keys.as<uint64_t>(), n1, d_tmp, ix->keys_fwd, &ix->n_fwd, st));
     TRY(sort_unique_keys(c, d_keys.as<uint64_t>() + n1, tot - n1, d_tmp, ix->keys_rev, &ix->n_rev, st));
     ix->stats[2] = ix->n_fwd; ix->stats[3] = ix->n_rev;
-    if (f > 0 && n1) {
-        const long n_ban = (long)(f * (double)ix->n_rev);
-        if (n_ban > 0) {
-            std::vector<uint32_t> h(n1);
-            CU(cudaMemcpyAsync(h.data(), d_hash.p, n1 * 4, cudaMemcpyDeviceToHost, st));
-            CU(cudaStreamSynchronize(st));
-            std::sort(h.begin(), h.end());
-            std::vector<std::pair<uint32_t, uint32_t>> freq;   // (count, hash)
-            for (size_t i = 0; i < h.size();) {
-                size_t j = i;
-                while (j < h.size() && h[j] == h[i]) ++j;
-                freq.emplace_back((uint32_t)(j - i), h[i]);
-                i = j;
-            }
-            std::sort(freq.begin(), freq.end(), [](const auto& a, const auto& b) { return a.first != b.first ? a.first > b.first : a.second < b.second; });
-            for (long i = 0; i < std::min<long>(n_ban, (long)freq.size()); ++i) banned.push_back(freq[i].second);
-            std::sort(banned.begin(), banned.end());
-        }
-    }
-    if (!banned.empty()) {
-        DevBuf d_ban, d_keep, d_slot;
-        struct BG2 { std::vector<DevBuf*> v; ~BG2() { for (auto* b : v) b->release(); } } bg2{{&d_ban, &d_keep, &d_slot}};
-        TRY(d_ban.ensure(banned.size() * 4));
-        CU(cudaMemcpyAsync(d_ban.p, banned.data(), banned.size() * 4, cudaMemcpyHostToDevice, st));
+    const long n_ban_want = (f > 0 && n1) ? (long)(f * (double)ix->n_rev) : 0;
+    if (n_ban_want > 0) {
+        // on the device: sort the forward hashes, run-length encode them into (hash, window count), order by
+        // (count desc, hash asc) through one more radix sort on (~count << 32 | hash), keep the first n_ban
+        DevBuf d_hs, d_uh, d_uc, d_fk, d_fk2, d_ban, d_keep;
+        struct BG2 { std::vector<DevBuf*> v; ~BG2() { for (auto* b : v) b->release(); } } bg2{{&d_hs, &d_uh, &d_uc, &d_fk, &d_fk2, &d_ban, &d_keep}};
+        TRY(d_hs.ensure(n1 * 4)); TRY(d_uh.ensure(n1 * 4)); TRY(d_uc.ensure(n1 * 4));
+        TRY(c->total.ensure(16));
+        size_t tb = 0;
+        CU(cub::DeviceRadixSort::SortKeys(nullptr, tb, d_hash.as<uint32_t>(), d_hs.as<uint32_t>(), (int)n1, 0, 32, st));
+        TRY(c->scan_tmp.ensure(tb));
+        CU(cub::DeviceRadixSort::SortKeys(c->scan_tmp.p, tb, d_hash.as<uint32_t>(), d_hs.as<uint32_t>(), (int)n1, 0, 32, st));
+        CU(cub::DeviceRunLengthEncode::Encode(nullptr, tb, d_hs.as<uint32_t>(), d_uh.as<uint32_t>(), d_uc.as<uint32_t>(), c->total.as<uint32_t>(), (int)n1, st));
+        TRY(c->scan_tmp.ensure(tb));
+        CU(cub::DeviceRunLengthEncode::Encode(c->scan_tmp.p, tb, d_hs.as<uint32_t>(), d_uh.as<uint32_t>(), d_uc.as<uint32_t>(), c->total.as<uint32_t>(), (int)n1, st));
+        uint32_t n_distinct = 0;
+        CU(cudaMemcpyAsync(&n_distinct, c->total.p, 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        const uint32_t n_ban = (uint32_t)std::min<long>(n_ban_want, (long)n_distinct);
+        TRY(d_fk.ensure((size_t)n_distinct * 8)); TRY(d_fk2.ensure((size_t)n_distinct * 8)); TRY(d_ban.ensure((size_t)n_ban * 4 + 4));
+        freq_keys_kernel<<<(unsigned)div_up64(n_distinct, 256), 256, 0, st>>>(d_uh.as<uint32_t>(), d_uc.as<uint32_t>(), n_distinct, d_fk.as<uint64_t>());
+        CU(cub::DeviceRadixSort::SortKeys(nullptr, tb, d_fk.as<uint64_t>(), d_fk2.as<uint64_t>(), (int)n_distinct, 0, 64, st));
+        TRY(c->scan_tmp.ensure(tb));
+        CU(cub::DeviceRadixSort::SortKeys(c->scan_tmp.p, tb, d_fk.as<uint64_t>(), d_fk2.as<uint64_t>(), (int)n_distinct, 0, 64, st));
+        low_words_kernel<<<(unsigned)div_up64(n_ban, 256), 256, 0, st>>>(d_fk2.as<uint64_t>(), n_ban, d_uh.as<uint32_t>());
+        CU(cub::DeviceRadixSort::SortKeys(nullptr, tb, d_uh.as<uint32_t>(), d_ban.as<uint32_t>(), (int)n_ban, 0, 32, st));
+        TRY(c->scan_tmp.ensure(tb));
+        CU(cub::DeviceRadixSort::SortKeys(c->scan_tmp.p, tb, d_uh.as<uint32_t>(), d_ban.as<uint32_t>(), (int)n_ban, 0, 32, st));
+        c->kernel_launches += 10;
         for (int strand = 0; strand < 2; ++strand) {
             DevBuf& keys = strand ? ix->keys_rev : ix->keys_fwd;
             uint64_t& cnt = strand ? ix->n_rev : ix->n_fwd;
             if (!cnt) continue;
             TRY(d_keep.ensure(cnt));
             TRY(d_tmp.ensure(cnt * 8));
-            ban_flag_kernel<<<(unsigned)div_up64(cnt, 256), 256, 0, st>>>(keys.as<uint64_t>(), cnt, d_ban.as<uint32_t>(), (uint32_t)banned.size(), d_keep.as<uint8_t>());
+            ban_flag_kernel<<<(unsigned)div_up64(cnt, 256), 256, 0, st>>>(keys.as<uint64_t>(), cnt, d_ban.as<uint32_t>(), n_ban, d_keep.as<uint8_t>());
             size_t fb = 0;
             CU(cub::DeviceSelect::Flagged(nullptr, fb, keys.as<uint64_t>(), d_keep.as<uint8_t>(), d_tmp.as<uint64_t>(), c->total.as<uint64_t>(), (int)cnt, st));
             TRY(c->scan_tmp.ensure(fb));

@@ -23,6 +23,17 @@ __global__ void make_keys_kernel(const uint32_t* __restrict__ hash, const uint32
     if (i < n) keys[i] = ((uint64_t)hash[i] << 32) | pos[i];
 }
 
+// frequency ranking of the forward hashes: ascending order of (~count << 32 | hash) = count descending, hash ascending
+__global__ void freq_keys_kernel(const uint32_t* __restrict__ hash, const uint32_t* __restrict__ count, uint32_t n,
+                                 uint64_t* __restrict__ keys) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) keys[i] = ((uint64_t)(0xffffffffu - count[i]) << 32) | hash[i];
+}
+__global__ void low_words_kernel(const uint64_t* __restrict__ keys, uint32_t n, uint32_t* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (uint32_t)keys[i];
+}
+
 // drop keys whose hash is in the (sorted) ban list; flags feed a stream compaction
 __global__ void ban_flag_kernel(const uint64_t* __restrict__ keys, uint64_t n, const uint32_t* __restrict__ banned,
                                 uint32_t n_banned, uint8_t* __restrict__ keep) {
