@@ -43,8 +43,6 @@ constexpr int kL16LaneRows = 64;                     // query rows per lane (two
 constexpr int kL16Stripe = kL16LaneRows * kWarp;     // 2048 rows per stripe
 constexpr int kL16Chunk = 64;                        // steps between progress publications / polls / re-centring
 
-__device__ __forceinline__ uint32_t pack16(int lo, int hi) { return ((uint32_t)hi << 16) | ((uint32_t)lo & 0xffffu); }
-
 // Y[r] for a warp-uniform r without 31 selects: a jump on r.
 #define B200_PICK4(k) case k: v = Y[k]; break; case k + 1: v = Y[k + 1]; break; case k + 2: v = Y[k + 2]; break; case k + 3: v = Y[k + 3]; break;
 __device__ __forceinline__ uint32_t pick_uniform(const uint32_t (&Y)[32], uint32_t r) {
@@ -56,25 +54,6 @@ __device__ __forceinline__ uint32_t pick_uniform(const uint32_t (&Y)[32], uint32
     return v;
 }
 #undef B200_PICK4
-
-__device__ __forceinline__ uint32_t pick_any(const uint32_t (&Y)[32], uint32_t r) {   // lane-varying r (rare paths)
-    uint32_t v = Y[0];
-#pragma unroll
-    for (int k = 1; k < 32; ++k) if (r == (uint32_t)k) v = Y[k];
-    return v;
-}
-
-// packed maximum of the 32 registers (16 VIMNMX3.S16x2)
-__device__ __forceinline__ uint32_t max_tree16(const uint32_t (&Y)[32]) {
-    uint32_t m[12];
-#pragma unroll
-    for (int k = 0; k < 10; ++k) m[k] = __vimax3_s16x2(Y[3 * k], Y[3 * k + 1], Y[3 * k + 2]);
-    m[10] = Y[30]; m[11] = Y[31];
-    uint32_t n[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) n[k] = __vimax3_s16x2(m[3 * k], m[3 * k + 1], m[3 * k + 2]);
-    return __vmaxs2(__vimax3_s16x2(n[0], n[1], n[2]), n[3]);
-}
 
 // One stripe sweep. LOCATE = false: the fill (directions, boundary row, progress, end-cell candidates).
 // LOCATE = true: local alignments' second pass over the first stripe that attains the maximum M; no

@@ -16,6 +16,12 @@
 //     accZ = accZ*4 + Z ; accY = accY*4 + Y       IMAD chains; accZ - accY + 0x5555.. = 8 tags / half
 // = 3 alu-pipe + 2 fma-pipe + 1 PRMT issue slots for TWO cells (see the moving-frame note below).
 //
+// All three alignment types: global captures cell (Q,T); semiGlobal tracks the best of the last column
+// (per block, at the pair's last column) and of row Q (every column of the pair's last block), with the
+// reference's tie rules (team_alignment.cpp:265-278); local clamps at 0 (tag 3 = stop) and keeps the first
+// maximum in row-major order (:186-192): a packed max tree per column gives the column maximum, and only
+// when it beats -- or, inside the same block, ties -- the running best are the rows scanned for the cell.
+//
 // Eligibility (decided on the host, capi.cu): both sequences pure ACGT, |s - gap| <= 31 for
 // s in {match, mismatch}, and 4 * ((Q+T+2) * max|score| + |gap| * T + 4) <= 32767 so nothing leaves int16.
 #pragma once
@@ -131,6 +137,27 @@ __device__ __forceinline__ uint32_t lop3_and_or(uint32_t a, uint32_t b, uint32_t
 
 __device__ __forceinline__ int half_lo(uint32_t v) { return (int)(int16_t)(v & 0xffffu); }
 __device__ __forceinline__ int half_hi(uint32_t v) { return (int)(int16_t)(v >> 16); }
+template <int HI> __device__ __forceinline__ int half_of(uint32_t v) { return HI ? half_hi(v) : half_lo(v); }
+__device__ __forceinline__ uint32_t pack16(int lo, int hi) { return ((uint32_t)hi << 16) | ((uint32_t)lo & 0xffffu); }
+
+__device__ __forceinline__ uint32_t pick_any(const uint32_t (&Y)[32], uint32_t r) {   // Y[r] for a lane-varying r
+    uint32_t v = Y[0];
+#pragma unroll
+    for (int k = 1; k < 32; ++k) if (r == (uint32_t)k) v = Y[k];
+    return v;
+}
+
+// packed maximum of the 32 registers (16 VIMNMX3.S16x2)
+__device__ __forceinline__ uint32_t max_tree16(const uint32_t (&Y)[32]) {
+    uint32_t m[12];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) m[k] = __vimax3_s16x2(Y[3 * k], Y[3 * k + 1], Y[3 * k + 2]);
+    m[10] = Y[30]; m[11] = Y[31];
+    uint32_t n[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) n[k] = __vimax3_s16x2(m[3 * k], m[3 * k + 1], m[3 * k + 2]);
+    return __vmaxs2(__vimax3_s16x2(n[0], n[1], n[2]), n[3]);
+}
 
 // Direction word layout written by this kernel (read back by walk_kernel, klass kClassShort):
 //   uint4 at dirs[dir_off + ((block * Tg + (j-1)) * 32 + lane) * 4 .. +3]; word k covers rows
@@ -188,6 +215,12 @@ fill_short_kernel(const uint32_t* __restrict__ qpk, const uint32_t* __restrict__
         const uint32_t Qm = max(liveA ? QA : 0u, liveB ? QB : 0u), Tm = max(liveA ? TA : 0u, liveB ? TB : 0u);
         const uint32_t n_blocks = (Qm + R - 1) / R;
         int resA = 0, resB = 0;
+        // semiGlobal candidates: last column (smallest i first, H(0,T) = 0 leads), last row (smallest j, H(Q,0) = 0 leads)
+        int colbestA = 0, colbestB = 0, rowbestA = 0, rowbestB = 0;
+        uint32_t coliA = 0, coliB = 0, rowjA = 0, rowjB = 0;
+        // local: running first maximum in row-major order
+        int bvA = INT_MIN, bvB = INT_MIN;
+        uint32_t biA = 0, bjA = 0, biB = 0, bjB = 0;
 
         for (uint32_t b = 0; b < n_blocks; ++b) {
             const uint32_t i0 = b * R;   // rows i0+1 .. i0+R
@@ -216,6 +249,13 @@ fill_short_kernel(const uint32_t* __restrict__ qpk, const uint32_t* __restrict__
             // hoisted end-cell test: the column at which this block holds cell (Q,T) of either pair
             const uint32_t jhitA = (TYPE == 0 && liveA && (QA - 1) / R == b) ? TA : 0u;
             const uint32_t jhitB = (TYPE == 0 && liveB && (QB - 1) / R == b) ? TB : 0u;
+            // rows of each pair inside this block, and whether the block holds the pair's row Q
+            const uint32_t nvA = (liveA && QA > i0) ? min((uint32_t)R, QA - i0) : 0u;
+            const uint32_t nvB = (liveB && QB > i0) ? min((uint32_t)R, QB - i0) : 0u;
+            const bool lastA = nvA && QA <= i0 + R, lastB = nvB && QB <= i0 + R;
+            const uint32_t rqA = lastA ? QA - 1 - i0 : 0u, rqB = lastB ? QB - 1 - i0 : 0u;
+            const bool full_rows = nvA == (uint32_t)R && nvB == (uint32_t)R;
+            const uint32_t Tmin = min(TA, TB);
 #pragma unroll 2
             for (uint32_t j = 1; j <= Tm; ++j) {
                 if (((j - 1) & 15u) == 0) {
@@ -234,11 +274,13 @@ fill_short_kernel(const uint32_t* __restrict__ qpk, const uint32_t* __restrict__
                 uint32_t dg = top_prev;   // Y(i0, j-1), previous column's frame
                 top_prev = top;
                 uint32_t accZ = 0, accY = 0, w[4];
+                const uint32_t clampv = dup16(3 - 4 * K.gap * (int)j);   // local: H = 0 with the stop tag, this column's frame
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
                     const uint32_t S = prmt(tabA, tabB, sel[r]);
                     const uint32_t m1 = __viaddmax_s16x2(dg, S, Y[r]);
                     uint32_t Z = __viaddmax_s16x2(up, K.cu, m1);
+                    if (TYPE == 1) Z = __vmaxs2(Z, clampv);   // clamp at 0 (team_alignment.cpp:185), tag 3 = stop
                     dg = Y[r];
                     Y[r] = lop3_and_or(Z, MASK, ONE);
                     up = Y[r];
@@ -262,6 +304,51 @@ fill_short_kernel(const uint32_t* __restrict__ qpk, const uint32_t* __restrict__
                         if (hitB) resB = (half_hi(vB) - 1 + 4 * K.gap * (int)j) >> 2;
                     }
                 }
+                const int back = 4 * K.gap * (int)j - 1;   // H = (Y + back) >> 2 in this column's frame
+                if (TYPE == 2) {
+                    if ((j == TA && nvA) || (j == TB && nvB)) {   // a pair's last column: rows ascend, strict '>' keeps the smallest i
+#pragma unroll
+                        for (int r = 0; r < R; ++r) {
+                            const int hA = (half_lo(Y[r]) + back) >> 2, hB = (half_hi(Y[r]) + back) >> 2;
+                            if (j == TA && (uint32_t)r < nvA && hA > colbestA) { colbestA = hA; coliA = i0 + 1 + r; }
+                            if (j == TB && (uint32_t)r < nvB && hB > colbestB) { colbestB = hB; coliB = i0 + 1 + r; }
+                        }
+                    }
+                    if (lastA || lastB) {   // row Q of a pair, every column: strict '>' keeps the smallest j
+                        const int hA = (half_lo(pick_any(Y, rqA)) + back) >> 2, hB = (half_hi(pick_any(Y, rqB)) + back) >> 2;
+                        if (lastA && j <= TA && hA > rowbestA) { rowbestA = hA; rowjA = j; }
+                        if (lastB && j <= TB && hB > rowbestB) { rowbestB = hB; rowjB = j; }
+                    }
+                }
+                if (TYPE == 1) {
+                    int mA, mB;   // column maxima over the valid rows, as register halves
+                    if (full_rows && j <= Tmin) {
+                        const uint32_t cm = max_tree16(Y);
+                        mA = half_lo(cm); mB = half_hi(cm);
+                    } else {
+                        mA = INT_MIN; mB = INT_MIN;
+#pragma unroll
+                        for (int r = 0; r < R; ++r) {
+                            if ((uint32_t)r < nvA) mA = max(mA, half_lo(Y[r]));
+                            if ((uint32_t)r < nvB) mB = max(mB, half_hi(Y[r]));
+                        }
+                    }
+                    const int hA = (nvA && j <= TA) ? (mA + back) >> 2 : INT_MIN;
+                    const int hB = (nvB && j <= TB) ? (mB + back) >> 2 : INT_MIN;
+                    // a new maximum, or a tie that may sit on a smaller row of this block than the current holder
+                    if (hA > bvA || (hA == bvA && biA > i0 + 1)) {
+                        uint32_t rr = R;
+#pragma unroll
+                        for (int r = R - 1; r >= 0; --r) if ((uint32_t)r < nvA && half_lo(Y[r]) == mA) rr = r;
+                        if (hA > bvA || i0 + 1 + rr < biA) { bvA = hA; biA = i0 + 1 + rr; bjA = j; }
+                    }
+                    if (hB > bvB || (hB == bvB && biB > i0 + 1)) {
+                        uint32_t rr = R;
+#pragma unroll
+                        for (int r = R - 1; r >= 0; --r) if ((uint32_t)r < nvB && half_hi(Y[r]) == mB) rr = r;
+                        if (hB > bvB || i0 + 1 + rr < biB) { bvB = hB; biB = i0 + 1 + rr; bjB = j; }
+                    }
+                }
             }
         }
         if (TYPE == 0) {
@@ -273,6 +360,22 @@ fill_short_kernel(const uint32_t* __restrict__ qpk, const uint32_t* __restrict__
                 score[pB] = liveB ? resB : (int)((QB + TB) * (uint32_t)K.init);
                 end_i[pB] = QB; end_j[pB] = TB;
             }
+        }
+        if (TYPE == 2) {   // last column wins ties, the last row only if strictly greater (team_alignment.cpp:265-278)
+            if (pA != 0xffffffffu) {
+                if (!liveA) { score[pA] = 0; end_i[pA] = 0; end_j[pA] = TA; }
+                else if (rowbestA > colbestA) { score[pA] = rowbestA; end_i[pA] = QA; end_j[pA] = rowjA; }
+                else { score[pA] = colbestA; end_i[pA] = coliA; end_j[pA] = TA; }
+            }
+            if (pB != 0xffffffffu) {
+                if (!liveB) { score[pB] = 0; end_i[pB] = 0; end_j[pB] = TB; }
+                else if (rowbestB > colbestB) { score[pB] = rowbestB; end_i[pB] = QB; end_j[pB] = rowjB; }
+                else { score[pB] = colbestB; end_i[pB] = coliB; end_j[pB] = TB; }
+            }
+        }
+        if (TYPE == 1) {
+            if (pA != 0xffffffffu) { score[pA] = liveA ? bvA : 0; end_i[pA] = liveA ? biA : 0u; end_j[pA] = liveA ? bjA : 0u; }
+            if (pB != 0xffffffffu) { score[pB] = liveB ? bvB : 0; end_i[pB] = liveB ? biB : 0u; end_j[pB] = liveB ? bjB : 0u; }
         }
     }
 }

@@ -378,7 +378,7 @@ static inline uint64_t generic_dir_words(uint32_t Q, uint32_t T) {
 
 // Can the int16 tagged kernel (align_fill_short.cuh) represent every value of this pair?
 static bool short_scores_ok(const Scores& sc, int type) {
-    if (type != 0) return false;   // K1 finalises global alignments only (semi/local go through the warp kernels)
+    (void)type;
     auto fits8 = [](int v) { return v >= -128 && v <= 127; };
     const long sm = 4l * ((long)sc.match - sc.gap) + 1, sx = 4l * ((long)sc.mismatch - sc.gap) + 1;
     return fits8((int)sm) && fits8((int)sx) && std::abs((long)sc.gap) < 4000 && std::abs((long)sc.match) < 4000 &&
@@ -702,7 +702,9 @@ static int launch_fill_short(b200_align_plan* p, const Wave& wv, const RunBufs& 
     b200_ctx* c = p->ctx;
     const uint32_t n_groups = (wv.count + 63) / 64;
     int per_sm = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fill_short_kernel<0>, kShortThreads, 0));
+    if (p->type == 0) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fill_short_kernel<0>, kShortThreads, 0));
+    else if (p->type == 1) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fill_short_kernel<1>, kShortThreads, 0));
+    else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fill_short_kernel<2>, kShortThreads, 0));
     per_sm = std::max(per_sm, 1);
     const int n_blocks = (int)std::min<uint64_t>((uint64_t)c->sm_count * per_sm, div_up64(n_groups, kShortThreads / 32));
     const uint32_t bnd_cols = p->max_T_short + 4;
@@ -710,10 +712,12 @@ static int launch_fill_short(b200_align_plan* p, const Wave& wv, const RunBufs& 
     CU(cudaMemsetAsync(rb.ws->counter.p, 0, 64, rb.st));
     const ShortConsts K = make_short_consts(p->sc, p->type);
     prof_begin(c, rb.st, 0);
-    fill_short_kernel<0><<<n_blocks, kShortThreads, 0, rb.st>>>(
-        c->qpk.as<uint32_t>(), c->tpk.as<uint32_t>(), p->d_pairs.as<PairDesc>(), p->d_work.as<uint32_t>() + wv.first,
-        wv.count, p->d_groups.as<ShortGroup>() + wv.first_group, rb.ws->counter.as<uint32_t>(), c->flags.as<uint8_t>(), K,
-        rb.dirs, rb.ws->bnd_short.as<uint32_t>(), bnd_cols, rb.score, c->end_i.as<uint32_t>(), c->end_j.as<uint32_t>());
+#define SHORTK(TY) fill_short_kernel<TY><<<n_blocks, kShortThreads, 0, rb.st>>>(                                            \
+        c->qpk.as<uint32_t>(), c->tpk.as<uint32_t>(), p->d_pairs.as<PairDesc>(), p->d_work.as<uint32_t>() + wv.first,     \
+        wv.count, p->d_groups.as<ShortGroup>() + wv.first_group, rb.ws->counter.as<uint32_t>(), c->flags.as<uint8_t>(), K, \
+        rb.dirs, rb.ws->bnd_short.as<uint32_t>(), bnd_cols, rb.score, c->end_i.as<uint32_t>(), c->end_j.as<uint32_t>())
+    switch (p->type) { case 0: SHORTK(0); break; case 1: SHORTK(1); break; default: SHORTK(2); break; }
+#undef SHORTK
     prof_end(c, rb.st);
     c->kernel_launches++;
     return B200_OK;

@@ -267,3 +267,32 @@ def test_long32_kernel_kept_covered(ctx, typ):
         ctx.set_option("long16", 1)
     # 4(s-gap)+1 fits the byte tables, but one vertical step moves Y by 803: the 16-bit bound rejects it
     _check_batch(ctx, qs, ts, typ, -170, -200, -200)
+
+
+@pytest.mark.parametrize("typ", [1, 2])
+def test_short_kernel_semi_global_and_local(ctx, typ):
+    """K1 on the other two alignment types: end-cell rules (last column before last row, first maximum in
+    row-major order) inside the thread-per-pair kernel, uniform and ragged batches, with fallbacks."""
+    qb, qo, tb, to = seqgen.short_pairs(23 + typ, 16384)
+    _check_packed_vs_oracle(ctx, qb, qo, tb, to, typ, 1, -1, -1, 5)
+    _check_packed_vs_oracle(ctx, qb, qo, tb, to, typ, 2, -3, -2, 37)
+    _check_packed_vs_oracle(ctx, qb, qo, tb, to, typ, 0, -1, -1, 37)      # zero match score: ties everywhere
+    rng = np.random.default_rng(80 + typ)
+    qs, ts = [], []
+    for k in range(12000):
+        T = int(rng.integers(0, 260))
+        t = seqgen.random_dna(rng, T)
+        if k % 3 == 0:
+            q = seqgen.random_dna(rng, int(rng.integers(0, 260)))
+        elif k % 3 == 1:
+            q = seqgen.mutate(rng, t, sub=0.05, ins=0.04, dele=0.04)
+        else:   # overhangs on either side: what semi-global and local are for
+            a, b = sorted(int(x) for x in rng.integers(0, T + 1, size=2))
+            q = np.concatenate([seqgen.random_dna(rng, int(rng.integers(0, 40))), t[a:b], seqgen.random_dna(rng, int(rng.integers(0, 40)))])
+        if k % 97 == 0 and len(q) > 3:
+            q = q.copy(); q[len(q) // 2] = ord("N")
+        qs.append(q); ts.append(t)
+    qb, qo = seqgen.pack_arrays(qs)
+    tb, to = seqgen.pack_arrays(ts)
+    _check_packed_vs_oracle(ctx, qb, qo, tb, to, typ, 1, -1, -1, 7)
+    _check_packed_vs_oracle(ctx, qb, qo, tb, to, typ, 3, -2, -4, 13)
