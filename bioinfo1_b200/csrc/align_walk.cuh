@@ -259,6 +259,7 @@ __global__ void target_begin_kernel(uint32_t n, int type, const uint32_t* __rest
     if (p < n) target_begin[p] = (type == 1) ? end_j[p] + 1 : 0;
 }
 
+// One thread per pair (short pairs: a few runs each).
 __global__ void __launch_bounds__(128)
 emit_kernel(const PairDesc* __restrict__ pairs, uint32_t n, const uint32_t* __restrict__ runs,
             const uint32_t* __restrict__ n_runs, const uint64_t* __restrict__ cigar_off,
@@ -277,6 +278,37 @@ emit_kernel(const PairDesc* __restrict__ pairs, uint32_t n, const uint32_t* __re
         for (uint32_t d = nd; d-- > 0;) { dst[d] = (char)('0' + cnt % 10); cnt /= 10; }
         dst[nd] = (op == 0) ? 'M' : (op == 1 ? 'I' : 'D');
         dst += nd + 1;
+    }
+}
+
+// One warp per pair (long pairs: thousands of runs each): 32 runs at a time, back to front; a warp scan of
+// the runs' text lengths gives every lane its place.
+__global__ void __launch_bounds__(128)
+emit_warp_kernel(const PairDesc* __restrict__ pairs, uint32_t n, const uint32_t* __restrict__ runs,
+                 const uint32_t* __restrict__ n_runs, const uint64_t* __restrict__ cigar_off,
+                 char* __restrict__ cigar) {
+    const uint32_t p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (p >= n) return;
+    const uint32_t nr = n_runs[p];
+    char* dst = cigar + cigar_off[p];
+    if (nr == 0) { if (lane == 0) { dst[0] = '1'; dst[1] = '\0'; } return; }
+    const uint32_t* src = runs + pairs[p].run_off;
+    uint32_t at = 0;   // bytes already placed (warp-uniform)
+    for (uint32_t base = 0; base < nr; base += kWarp) {
+        const uint32_t t = base + lane;              // t-th run of the text = run nr-1-t of the walk
+        uint32_t cnt = 0, op = 0, len = 0;
+        if (t < nr) { const uint32_t rw = src[nr - 1 - t]; cnt = rw >> 2; op = rw & 3u; len = dec_digits(cnt) + 1; }
+        uint32_t incl = len;
+#pragma unroll
+        for (int o = 1; o < kWarp; o <<= 1) { const uint32_t u = __shfl_up_sync(kFull, incl, o); if (lane >= o) incl += u; }
+        if (t < nr) {
+            char* d = dst + at + incl - len;
+            const uint32_t nd = len - 1;
+            for (uint32_t k = nd; k-- > 0;) { d[k] = (char)('0' + cnt % 10); cnt /= 10; }
+            d[nd] = (op == 0) ? 'M' : (op == 1 ? 'I' : 'D');
+        }
+        at += __shfl_sync(kFull, incl, kWarp - 1);
     }
 }
 

@@ -964,7 +964,11 @@ extern "C" int b200_align_plan_run(b200_align_plan* p, const char* d_q_buf, cons
         if (total > cigar_cap)
             return fail(B200_E_CAP, "CIGAR buffer too small: need " + std::to_string(total) + " bytes, have " + std::to_string(cigar_cap));
         prof_begin(c, st, 2);
-        emit_kernel<<<(unsigned)div_up64(n, 128), 128, 0, st>>>(p->d_pairs.as<PairDesc>(), (uint32_t)n, c->runs.as<uint32_t>(), c->n_runs.as<uint32_t>(), d_cigar_off, d_cigar);
+        // many short pairs: a thread each; fewer, longer pairs (thousands of runs): a warp each
+        if (p->n_short * 2 >= n)
+            emit_kernel<<<(unsigned)div_up64(n, 128), 128, 0, st>>>(p->d_pairs.as<PairDesc>(), (uint32_t)n, c->runs.as<uint32_t>(), c->n_runs.as<uint32_t>(), d_cigar_off, d_cigar);
+        else
+            emit_warp_kernel<<<(unsigned)div_up64(n * 32, 128), 128, 0, st>>>(p->d_pairs.as<PairDesc>(), (uint32_t)n, c->runs.as<uint32_t>(), c->n_runs.as<uint32_t>(), d_cigar_off, d_cigar);
         prof_end(c, st);
         c->kernel_launches++;
     }
@@ -1017,7 +1021,7 @@ extern "C" int b200_align_batch_packed(b200_ctx* c, size_t n, const char* q_buf,
     TRY(c->d_q.ensure(q1 - q0 + 64));
     TRY(c->d_t.ensure(t1 - t0 + 64));
     cudaStream_t st = c->stream;
-    constexpr int kPipe = 8;
+    constexpr int kPipe = 16;
     if (!c->copy_stream) CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     while (c->copy_events.size() < (size_t)kPipe) {
         cudaEvent_t e; CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -1038,8 +1042,19 @@ extern "C" int b200_align_batch_packed(b200_ctx* c, size_t n, const char* q_buf,
         c->host_plan->ctx = c;
     }
     b200_align_plan* plan = c->host_plan;   // recycled: its device and host buffers keep their capacity
-    // four chunks: smaller ones start earlier but under-fill the GPU (fill and walk kernels lose efficiency)
-    const size_t chunk_pairs = c->chunk_pairs > 0 ? (size_t)c->chunk_pairs : std::max<size_t>(8192, (n / 4 + 63) & ~(size_t)63);
+    // Uniform short batches are cut into chunks of whole ROUNDS of the thread-per-pair kernel (every resident warp
+    // takes one 64-pair group per round): any other size leaves a partly empty last round in every chunk, and the
+    // smaller the last chunk, the less work is left when the last byte of the upload lands.
+    size_t chunk_pairs = (size_t)c->chunk_pairs;
+    if (chunk_pairs == 0) {
+        int per_sm = 0;
+        if (type == 0) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fill_short_kernel<0>, kShortThreads, 0));
+        else if (type == 1) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fill_short_kernel<1>, kShortThreads, 0));
+        else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fill_short_kernel<2>, kShortThreads, 0));
+        const size_t round_pairs = (size_t)c->sm_count * std::max(per_sm, 1) * (kShortThreads / 32) * 64;
+        const size_t rounds_per_chunk = std::max<size_t>(1, div_up64(div_up64(n, round_pairs), 16));   // at most 16 chunks
+        chunk_pairs = round_pairs * rounds_per_chunk;
+    }
     TRY(plan_build(plan, c, n, q_off, t_off, true, false, type, match, mismatch, gap, want_cigar ? 1 : 0, chunk_pairs));
     // which upload slice does each wave have to wait for
     plan->wave_events.assign(plan->waves.size(), c->copy_events[kPipe - 1]);
