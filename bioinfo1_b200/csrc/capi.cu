@@ -1140,6 +1140,7 @@ struct b200_min_plan {
     uint64_t tuples = 0;
     size_t n_tiles = 0;
     size_t smem_bytes = 0;
+    uint64_t buf_bytes = 0;   // bytes of the packed sequence buffer the plan was made for (= off[n])
     std::vector<uint64_t> out_off;
     DevBuf d_off, d_out_off, d_fwd, d_tiles;
 };
@@ -1166,18 +1167,19 @@ static int min_plan_build(b200_min_plan* p, b200_ctx* ctx, size_t n, const uint6
         const uint64_t cnt = b200_minimize_count((uint32_t)(off[i + 1] - off[i]), k, w);
         p->out_off[i + 1] = p->out_off[i] + cnt;
         // tiles end at multiples of kMinTile in the GLOBAL output index space (vector stores need the alignment)
+        if (is_fwd) fwd[i] = is_fwd[i] ? 1 : 0;
         for (uint64_t f = 0; f < cnt;) {
-            tiles.push_back(MinTile{(uint32_t)i, (uint32_t)f});
+            tiles.push_back(MinTile{off[i], p->out_off[i] + f, (uint32_t)(off[i + 1] - off[i]), (uint32_t)f, fwd[i], 0u});
             f += kMinTile - ((p->out_off[i] + f) & (uint64_t)(kMinTile - 1));
         }
-        if (is_fwd) fwd[i] = is_fwd[i] ? 1 : 0;
     }
     p->tuples = p->out_off[n];
     p->n_tiles = tiles.size();
     // shared memory: the packed 2-bit codes of every base the tile can touch (+ spare words, see the kernel)
     const uint64_t nx = (uint64_t)kMinTile + 2ull * w + 1;
-    const uint64_t nwords = (nx + k - 1 + 15) / 16 + 3;
+    const uint64_t nwords = (15 + nx + k - 1 + 15) / 16 + 3;
     p->smem_bytes = (size_t)(nwords * 4);
+    p->buf_bytes = n ? off[n] : 0;
     if (p->smem_bytes > 200 * 1024) return fail(B200_E_ARG, "window/k-mer length too large for the shared-memory tile");
     TRY(p->d_off.ensure((n + 1) * 8));
     TRY(p->d_out_off.ensure((n + 1) * 8));
@@ -1221,8 +1223,8 @@ extern "C" int b200_min_plan_run(b200_min_plan* p, const char* d_buf, uint32_t* 
         if (p->smem_bytes > 48 * 1024)                                                                                   \
             CU(cudaFuncSetAttribute(minimize_kernel<WW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes)); \
         minimize_kernel<WW><<<(unsigned)p->n_tiles, kMinThreads, p->smem_bytes, st>>>(                                   \
-            reinterpret_cast<const uint8_t*>(d_buf), p->d_off.as<uint64_t>(), p->d_out_off.as<uint64_t>(),               \
-            p->d_fwd.as<uint8_t>(), p->d_tiles.as<MinTile>(), p->k, p->w, d_hash, d_pos, d_flag);                        \
+            reinterpret_cast<const uint8_t*>(d_buf), p->d_tiles.as<MinTile>(), p->k, p->w, p->buf_bytes, d_hash,         \
+            d_pos, d_flag);                                                                                              \
         break;
     switch (W) { MINK(1) MINK(2) MINK(3) MINK(4) MINK(5) MINK(6) MINK(7) MINK(8) default: MINK(0) }
 #undef MINK

@@ -12,7 +12,7 @@
 //     every thread's chunk of 8 consecutive tuples is 32-byte aligned in the hash/pos arrays and 8-byte
 //     aligned in the flag array: five vector stores per 8 tuples;
 //   * the bases the slice needs are staged once into shared memory as 2-bit codes (16 per word, first
-//     base most significant), four bases at a time in SWAR form;
+//     base most significant): one aligned 128-bit load per word, four bases at a time in SWAR form;
 //   * a thread pulls three packed words, lines them up with two funnel shifts and gets each of the
 //     8+w-1 k-mer hashes its windows touch with one more funnel shift and a shift;
 //   * the leftmost minima of the 8 overlapping windows share partial minima (pairs, then quads, for w = 5).
@@ -23,14 +23,21 @@
 namespace b200 {
 
 constexpr int kMinThreads = 256;
-constexpr int kMinTile = 2048;   // output tuples per CTA (8 per thread)
+constexpr int kMinTile = 4096;   // output tuples per CTA (two chunks of 8 per thread)
 constexpr int kMinMaxW = 8;      // largest window length with a register fast path
 
+// One CTA's work, precomputed by the host so that the kernel starts with ONE broadcast load instead of a
+// chain of dependent ones (tile -> sequence offsets -> bases). The tile covers tuples [o0, o1) of a sequence;
+// it ends at the next multiple of kMinTile in the global output index space, or at the end of the sequence.
 struct MinTile {
-    uint32_t seq;    // sequence index
-    uint32_t first;  // first output slot (within the sequence) of this tile; it ends at the next multiple of
-                     // kMinTile in the global output index space, or at the end of the sequence
+    uint64_t src;    // byte offset of the sequence in the packed buffer
+    uint64_t gout;   // global output index of tuple o0 (= out_off[seq] + o0)
+    uint32_t L;      // sequence length
+    uint32_t o0;     // first tuple of the tile, within the sequence
+    uint32_t fwd;    // strand flag stamped on the tuples
+    uint32_t pad;
 };
+static_assert(sizeof(MinTile) == 32, "MinTile layout");
 
 __device__ __forceinline__ uint32_t base_code(uint32_t c) {
     // C=0 A=1 T=2 G=3, everything else 0 (reference :73-78, operator[] default)
@@ -68,102 +75,97 @@ __device__ __forceinline__ void lmin(uint32_t& v, uint32_t& at, uint32_t bv, uin
 // per-tuple path (any w; also used when the output pointers are not 16-byte aligned).
 template <int W>
 __global__ void __launch_bounds__(kMinThreads)
-minimize_kernel(const uint8_t* __restrict__ buf, const uint64_t* __restrict__ off,
-                const uint64_t* __restrict__ out_off, const uint8_t* __restrict__ is_fwd,
-                const MinTile* __restrict__ tiles, uint32_t k, uint32_t w,
-                uint32_t* __restrict__ hash, uint32_t* __restrict__ pos, uint8_t* __restrict__ flag) {
+minimize_kernel(const uint8_t* __restrict__ buf, const MinTile* __restrict__ tiles, uint32_t k, uint32_t w,
+                uint64_t buf_bytes, uint32_t* __restrict__ hash, uint32_t* __restrict__ pos, uint8_t* __restrict__ flag) {
     extern __shared__ uint32_t codes[];
     const MinTile tl = tiles[blockIdx.x];
-    const uint64_t s_off = off[tl.seq];
-    const uint32_t L = (uint32_t)(off[tl.seq + 1] - s_off);
-    const uint8_t* seq = buf + s_off;
-    const uint64_t n = (uint64_t)L - k + 1;                 // k-mers inside the sequence (L >= k here)
-    const uint64_t full = n >= w ? n - w + 1 : 0;
-    const uint64_t tail = n < (uint64_t)w - 1 ? n : (uint64_t)w - 1;
-    const uint64_t total = (uint64_t)(w - 1) + full + tail;
-    const uint64_t obase = out_off[tl.seq];
-    const uint64_t o0 = tl.first;
-    const uint64_t g0 = obase + o0;                          // global index of the tile's first tuple
-    const uint64_t o1 = min(total, o0 + ((uint64_t)kMinTile - (g0 & (uint64_t)(kMinTile - 1))));
+    const uint32_t L = tl.L;
+    const uint32_t n = L - k + 1;                            // k-mers inside the sequence (L >= k here)
+    const uint32_t full = n >= w ? n - w + 1 : 0;
+    const uint32_t tail = n < w - 1 ? n : w - 1;
+    const uint32_t total = (w - 1) + full + tail;            // (sequences are shorter than 2^32 - 16: no wrap)
+    const uint32_t o0 = tl.o0;
+    const uint32_t g_in = (uint32_t)(tl.gout & (uint64_t)(kMinTile - 1));   // where the tile starts inside its aligned slice
+    const uint32_t o1 = min(total - o0, (uint32_t)kMinTile - g_in) + o0;
+    hash += tl.gout - g_in; pos += tl.gout - g_in; flag += tl.gout - g_in;  // slice-relative outputs: index g_in + (o - o0)
 
     // k-mer index range this tile can touch: [x0, x1)
-    const uint64_t x0 = o0 > 2ull * w ? o0 - 2ull * w : 0;
-    const uint64_t x1 = o1 + 1;                              // sections 1/2 use k-mers <= slot index
-    const uint32_t nx = (uint32_t)(x1 - x0);                 // <= kMinTile + 2w + 1
+    const uint32_t x0 = o0 > 2 * w ? o0 - 2 * w : 0;
+    const uint32_t nx = o1 + 1 - x0;                         // sections 1/2 use k-mers <= slot index; <= kMinTile + 2w + 1
     const uint32_t kk = k < 16 ? k : 16;                     // bases that survive in the 32-bit hash
     const uint32_t hshift = 32 - 2 * kk;                     // (k = 0 never reaches the shifts below)
-    const uint32_t nwords = (nx + k - 1 + 15) / 16 + 2;      // two spare words: hashes read one and two words ahead
-
-    // 16 bases -> one packed word, from aligned 32-bit words realigned by funnel shifts; bytes past the
-    // end of the sequence read as code 0
+    // Staging works on ALIGNED 16-byte chunks of the input (one 128-bit load and four SWAR conversions per
+    // packed word, no realignment): packed word wi holds the 16 bytes at chunk origin + 16 wi, so base x0 sits
+    // `mis` bases into word 0 and every base index below is shifted by that much.
+    const uintptr_t addr0 = reinterpret_cast<uintptr_t>(buf) + tl.src + x0;
+    const uint32_t mis = (uint32_t)(addr0 & 15u);
+    const uint8_t* origin = reinterpret_cast<const uint8_t*>(addr0 - mis);
+    const int32_t cb0 = (int32_t)x0 - (int32_t)mis;              // sequence index of the first byte of word 0 (>= -15)
+    const uint32_t nwords = (mis + nx + k - 1 + 15) / 16 + 2;    // two spare words: hashes read one and two words ahead
+    const uint64_t room = buf_bytes - tl.src;                    // bytes from the sequence start to the end of the buffer
     for (uint32_t wi = threadIdx.x; wi < nwords; wi += blockDim.x) {
-        const uint64_t b0 = x0 + (uint64_t)wi * 16;
+        const int64_t cb = (int64_t)cb0 + 16ll * wi;             // sequence index of this chunk's first byte
         uint32_t word = 0;
-        if (b0 < L) {
-            const uint32_t nb = (uint32_t)min((uint64_t)16, L - b0);
-            const uintptr_t addr = reinterpret_cast<uintptr_t>(seq + b0);
-            const uint32_t* aw = reinterpret_cast<const uint32_t*>(addr & ~(uintptr_t)3);
-            const uint32_t shb = (uint32_t)(addr & 3u) * 8u;
-            uint32_t raw[5];
-#pragma unroll
-            for (int q = 0; q < 5; ++q) raw[q] = ((uint32_t)q * 4u < (uint32_t)(addr & 3u) + nb) ? __ldg(aw + q) : 0u;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                uint32_t v = __funnelshift_r(raw[q], raw[q + 1], shb);   // bases 4q..4q+3, first base in the low byte
-                if (nb < 4u * q + 4u) {                                  // ragged end of the sequence
-                    const uint32_t valid = nb > 4u * q ? nb - 4u * q : 0u;
-                    v = valid ? (v & (0xffffffffu >> (8u * (4u - valid)))) : 0u;
+        if (cb < (int64_t)L) {
+            const uint8_t* src = origin + 16ull * wi;
+            if (cb + 16 <= (int64_t)L && (uint64_t)(cb + 16) <= room) {
+                const uint4 v = __ldg(reinterpret_cast<const uint4*>(src));
+                word = (code4(v.x) << 24) | (code4(v.y) << 16) | (code4(v.z) << 8) | code4(v.w);
+            } else {                                             // last chunk of the sequence: bytes past its end are code 0
+#pragma unroll 1
+                for (int bb = 0; bb < 16; ++bb) {
+                    const int64_t at = cb + bb;
+                    const uint32_t c = (at >= 0 && at < (int64_t)L) ? (uint32_t)src[bb] : 0u;
+                    word = (word << 2) | base_code(c);
                 }
-                word |= code4(v) << (8 * (3 - q));
             }
         }
         codes[wi] = word;
     }
     __syncthreads();
 
-    const uint32_t fl = is_fwd[tl.seq] ? 1u : 0u;
-    // hash of k-mer x (absolute index): its last kk bases, first of them at base x + k - kk
-    auto hash_at = [&](uint64_t x) -> uint32_t {
+    const uint32_t fl = tl.fwd;
+    const uint32_t bshift = (k - kk) + mis - x0;             // base index in the staged words of k-mer x's first surviving base: x + bshift
+    // hash of k-mer x (index within the sequence): its last kk bases
+    auto hash_at = [&](uint32_t x) -> uint32_t {
         if (kk == 0) return 0u;
-        const uint32_t b = (uint32_t)(x - x0) + (k - kk);
+        const uint32_t b = x + bshift;
         const uint32_t top = __funnelshift_l(codes[(b >> 4) + 1], codes[b >> 4], (b & 15u) * 2);
         return top >> hshift;
     };
-    auto slow_one = [&](uint64_t o) {
-        uint64_t a, b;  // window of k-mer indices [a, b]
-        if (o < (uint64_t)w - 1) { a = 0; b = o; }
-        else if (o < (uint64_t)w - 1 + full) { a = o - (w - 1); b = o; }
-        else { const uint64_t s = o - ((uint64_t)w - 1 + full) + 1; a = n - s; b = n - 1; }
+    auto slow_one = [&](uint32_t o) {
+        uint32_t a, b;  // window of k-mer indices [a, b]
+        if (o < w - 1) { a = 0; b = o; }
+        else if (o < w - 1 + full) { a = o - (w - 1); b = o; }
+        else { const uint32_t s = o - (w - 1 + full) + 1; a = n - s; b = n - 1; }
         uint32_t mn = 0xffffffffu, mpos = 0;
-        for (uint64_t x = a; x <= b; ++x) {
+        for (uint32_t x = a; x <= b; ++x) {
             const uint32_t h = hash_at(x);
-            if (h < mn) { mn = h; mpos = (uint32_t)x + 1; }
+            if (h < mn) { mn = h; mpos = x + 1; }
         }
         const bool none = (mpos == 0);                       // every hash was 0xFFFFFFFF
-        hash[obase + o] = none ? 0u : mn;
-        pos[obase + o] = mpos;
-        flag[obase + o] = none ? 0 : (uint8_t)fl;
+        const uint32_t at = g_in + (o - o0);
+        hash[at] = none ? 0u : mn;
+        pos[at] = mpos;
+        flag[at] = none ? 0 : (uint8_t)fl;
     };
 
-    const uint64_t gbase = g0 & ~(uint64_t)(kMinTile - 1);
-    for (uint32_t chunk = threadIdx.x; chunk < kMinTile / 8; chunk += blockDim.x) {
-        const uint64_t gc = gbase + 8ull * chunk;
-        const uint64_t lo = max(gc, g0), hi = min(gc + 8, obase + o1);
-        if (lo >= hi) continue;
+    // chunk c of the slice = slice positions [8c, 8c+8) = tuples o0 - g_in + 8c ... of the sequence
+    const uint32_t c_first = g_in >> 3, c_last = (g_in + (o1 - o0) + 7) >> 3;   // chunks that intersect the tile
+    for (uint32_t chunk = c_first + threadIdx.x; chunk < c_last; chunk += blockDim.x) {
+        const uint32_t sp = 8 * chunk;                        // slice position of the chunk
+        const uint32_t lo = max(sp, g_in), hi = min(sp + 8, g_in + (o1 - o0));
+        const uint32_t oc = sp - g_in + o0;                   // tuple index of the chunk's first slot (wraps if sp < g_in: then lo != sp)
         bool fast = false;
-        uint64_t oc = 0;
-        if (W > 0) {
-            oc = gc - obase;   // valid when gc >= obase, which lo == gc implies
-            fast = lo == gc && hi == gc + 8 && kk != 0 && oc >= (uint64_t)(W - 1) && oc + 8 <= (uint64_t)(W - 1) + full;
-        }
+        if (W > 0) fast = lo == sp && hi == sp + 8 && kk != 0 && oc >= (uint32_t)(W - 1) && oc + 8 <= (uint32_t)(W - 1) + full;
         if (!fast) {
-            for (uint64_t g = lo; g < hi; ++g) slow_one(g - obase);
+            for (uint32_t q = lo; q < hi; ++q) slow_one(q - g_in + o0);
             continue;
         }
         if (W > 0) {
             constexpr int NH = 8 + (W > 0 ? W : 1) - 1;       // hashes the 8 windows touch
-            const uint64_t xa = oc - (W - 1);                 // first k-mer of the first window
-            const uint32_t b = (uint32_t)(xa - x0) + (k - kk);
+            const uint32_t xa = oc - (W - 1);                 // first k-mer of the first window
+            const uint32_t b = xa + bshift;
             const uint32_t w0 = codes[b >> 4], w1 = codes[(b >> 4) + 1], w2 = codes[(b >> 4) + 2];
             const uint32_t sh0 = (b & 15u) * 2;
             const uint32_t A0 = __funnelshift_l(w1, w0, sh0), A1 = __funnelshift_l(w2, w1, sh0);   // 32 bases from b on
@@ -189,7 +191,7 @@ minimize_kernel(const uint8_t* __restrict__ buf, const uint64_t* __restrict__ of
                     for (int u = 1; u < (W > 0 ? W : 1); ++u) lmin(mv[t], ma[t], h[t + u], t + u);
                 }
             }
-            const uint32_t p0 = (uint32_t)xa + 1;             // reported positions are 1-based k-mer indices
+            const uint32_t p0 = xa + 1;                       // reported positions are 1-based k-mer indices
             uint32_t ho[8], po[8];
             uint32_t f0 = 0, f1 = 0;
 #pragma unroll
@@ -200,13 +202,13 @@ minimize_kernel(const uint8_t* __restrict__ buf, const uint64_t* __restrict__ of
                 const uint32_t fb = none ? 0u : fl;
                 if (t < 4) f0 |= fb << (8 * t); else f1 |= fb << (8 * (t - 4));
             }
-            uint4* hp = reinterpret_cast<uint4*>(hash + gc);
-            uint4* pp = reinterpret_cast<uint4*>(pos + gc);
+            uint4* hp = reinterpret_cast<uint4*>(hash + sp);
+            uint4* pp = reinterpret_cast<uint4*>(pos + sp);
             __stcs(hp, make_uint4(ho[0], ho[1], ho[2], ho[3]));
             __stcs(hp + 1, make_uint4(ho[4], ho[5], ho[6], ho[7]));
             __stcs(pp, make_uint4(po[0], po[1], po[2], po[3]));
             __stcs(pp + 1, make_uint4(po[4], po[5], po[6], po[7]));
-            __stcs(reinterpret_cast<uint2*>(flag + gc), make_uint2(f0, f1));
+            __stcs(reinterpret_cast<uint2*>(flag + sp), make_uint2(f0, f1));
         }
     }
 }
