@@ -23,7 +23,7 @@
 namespace b200 {
 
 constexpr int kMinThreads = 256;
-constexpr int kMinTile = 4096;   // output tuples per CTA (two chunks of 8 per thread)
+constexpr int kMinTile = 8192;   // output tuples per CTA (four chunks of 8 per thread)
 constexpr int kMinMaxW = 8;      // largest window length with a register fast path
 
 // One CTA's work, precomputed by the host so that the kernel starts with ONE broadcast load instead of a
