@@ -271,6 +271,14 @@ def extra_workloads(ctx, capi, torch, dev, peaks):
     return res
 
 
+_OUT = sys.stdout
+
+
+def emit(obj):
+    _OUT.write(json.dumps(obj) + "\n")
+    _OUT.flush()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -289,6 +297,11 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly one JSON line: anything a library prints there (NCCL's version banner does) goes to stderr
+    global _OUT
+    sys.stdout.flush()
+    _OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     workload = (f"{args.pairs} pairs x {args.length}x{args.length} bp, {TYPE_NAMES[args.type]} NW, match 1 "
                 f"mismatch -1 gap -1, score+CIGAR+target_begin (BASELINE.json configs[1])")
     config = {"workload": workload, "pairs_per_gpu": args.pairs, "query_len": args.length, "target_len": args.length,
@@ -308,7 +321,7 @@ def main():
             one_step()
         t = sum(one_step() for _ in range(args.steps))
         v = cells * args.steps / t / 1e9
-        print(json.dumps({
+        emit(({
             "impl": "reference", "metric": "alignment GCUPS (score+CIGAR)", "value": v, "unit": "GCUPS",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
@@ -424,7 +437,7 @@ def main():
                         "dir_store_gbs": cells / 4 / fill_s / 1e9, "hbm_source": peaks["source"]}}
 
     if args.device_only:
-        print(json.dumps({"value": value, "ms_per_step": ms_max / args.steps, "roofline": roofline, "clocks": clocks}))
+        emit({"value": value, "ms_per_step": ms_max / args.steps, "roofline": roofline, "clocks": clocks})
         return 0
 
     # ---- end-to-end arm: host buffers through the public host C-ABI ---------------------
@@ -483,7 +496,7 @@ def main():
         except Exception as e:  # the headline line must survive a failure of the side measurements
             out["extra"] = {"error": repr(e)}
     if rank == 0:
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -296,3 +296,47 @@ def test_short_kernel_semi_global_and_local(ctx, typ):
     tb, to = seqgen.pack_arrays(ts)
     _check_packed_vs_oracle(ctx, qb, qo, tb, to, typ, 1, -1, -1, 7)
     _check_packed_vs_oracle(ctx, qb, qo, tb, to, typ, 3, -2, -4, 13)
+
+
+# ---- full-size properties (BASELINE.json sizes; the oracle only sees a sample) ---------------------
+
+def test_config2_full_size_two_implementations_agree(ctx):
+    """1 048 576 pairs of 150 x 150 (BASELINE config 2): the int16x2 thread-per-pair kernel and the int32
+    byte-compare warp kernel are independent implementations; every score, target_begin and CIGAR byte of the
+    full batch must agree, and a sample is checked against the oracle."""
+    n = 1 << 20
+    qb, qo, tb, to = seqgen.short_pairs(1000, n)
+    fast = ctx.align_packed(qb, qo, tb, to, 0)
+    ctx.set_option("force_generic", 1)
+    try:
+        slow = ctx.align_packed(qb, qo, tb, to, 0)
+    finally:
+        ctx.set_option("force_generic", 0)
+    assert np.array_equal(fast[0], slow[0]) and np.array_equal(fast[1], slow[1])
+    assert np.array_equal(fast[3], slow[3])
+    total = int(fast[3][-1])
+    assert np.array_equal(fast[2][:total], slow[2][:total])
+    for k in range(0, n, 9973):
+        q = qb[int(qo[k]):int(qo[k + 1])].tobytes(); t = tb[int(to[k]):int(to[k + 1])].tobytes()
+        assert (int(fast[0][k]), int(fast[1][k]), fast[2][int(fast[3][k]):int(fast[3][k + 1])].tobytes()) == ORACLE.align(q, t, 0)
+
+
+@pytest.mark.parametrize("typ", [1, 2])
+def test_ont_like_long_pairs_two_implementations_agree(ctx, typ):
+    """ONT-like pairs of BASELINE configs 4/5 shape (8 kb mean, 12 % indel-heavy error; 10 kb local): the packed
+    int16x2 stripe kernel against the int32 stripe kernel on every pair, the oracle on two of them."""
+    qs, ts = seqgen.ont_like_pairs(900 + typ, 48, mean_len=8000) if typ == 2 else seqgen.ont_like_pairs(900 + typ, 24, fixed=10000)
+    qb, qo = seqgen.pack_arrays(qs)
+    tb, to = seqgen.pack_arrays(ts)
+    a = ctx.align_packed(qb, qo, tb, to, typ)
+    ctx.set_option("long16", 0)
+    try:
+        b = ctx.align_packed(qb, qo, tb, to, typ)
+    finally:
+        ctx.set_option("long16", 1)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[3], b[3])
+    total = int(a[3][-1])
+    assert np.array_equal(a[2][:total], b[2][:total])
+    for k in (0, len(qs) - 1):
+        exp = ORACLE.align(qs[k].tobytes(), ts[k].tobytes(), typ)
+        assert (int(a[0][k]), int(a[1][k]), a[2][int(a[3][k]):int(a[3][k + 1])].tobytes()) == exp
