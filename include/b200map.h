@@ -57,11 +57,14 @@ int b200_version(void); /* ABI version, currently 1 */
 
 int b200_ctx_create(int device, b200_ctx** out);
 void b200_ctx_destroy(b200_ctx* ctx);
-/* Tunables (all optional): "dir_budget_bytes" (HBM given to 2-bit direction storage per wave),
- * "force_generic" (1 = route every pair through the int32 byte-compare kernel),
- * "chunk_pairs" (host-API pipeline chunk). Returns B200_E_ARG for an unknown key. */
+/* Tunables (all optional): "dir_budget_bytes" (HBM given to 2-bit direction storage; a batch that needs more
+ * is cut into waves of half of it, two in flight), "force_generic" (1 = route every pair through the int32
+ * byte-compare kernel), "long16" (0 = long pairs stay on the int32 stripe kernel), "overlap_waves" (0 = waves
+ * run one after the other on the caller's stream), "chunk_pairs" (host-API pipeline chunk), "profile" (1 =
+ * bracket kernels with events: the "*_ns" counters), "reset_counters". Returns B200_E_ARG for an unknown key. */
 int b200_ctx_set_option(b200_ctx* ctx, const char* key, int64_t value);
-/* Counters since the context was created: "kernel_launches", "h2d_bytes", "d2h_bytes". */
+/* Counters since the context was created (or the last "reset_counters"): "kernel_launches", "h2d_bytes",
+ * "d2h_bytes"; with "profile" on also "fill_ns", "walk_ns", "emit_ns", "other_ns" and "*_launches". */
 int64_t b200_ctx_get_counter(b200_ctx* ctx, const char* key);
 
 /* ------------------------------------------------------------------ alignment ---- */
