@@ -224,7 +224,12 @@ def extra_workloads(ctx, capi, torch, dev, peaks):
     t0 = time.perf_counter()
     index = capi.Index(ctx, ref.tobytes(), 15, 5, 0.001)
     torch.cuda.synchronize()
-    t_index = time.perf_counter() - t0
+    t_index = time.perf_counter() - t0          # first build of the process: module loading and first allocations included
+    index.close()
+    t0 = time.perf_counter()
+    index = capi.Index(ctx, ref.tobytes(), 15, 5, 0.001)
+    torch.cuda.synchronize()
+    t_index_warm = time.perf_counter() - t0
     index.map_batch(mreads, True, 2, 1, -1, -1, True)   # warm-up at full size: the context's scratch buffers grow once
     t0 = time.perf_counter()
     mres, _ = index.map_batch(mreads, True, 2, 1, -1, -1, True)
@@ -232,7 +237,7 @@ def extra_workloads(ctx, capi, torch, dev, peaks):
     t_map = time.perf_counter() - t0
     res["map_2048_ont_reads_4.6Mbp_ref"] = {
         "reads": len(mreads), "bases": int(sum(len(r) for r in mreads)), "mapped": int(mres["mapped"].sum()),
-        "index_build_s": t_index, "map_s": t_map, "mapped_reads_per_s": float(mres["mapped"].sum()) / t_map,
+        "index_build_s": t_index_warm, "index_build_first_call_s": t_index, "map_s": t_map, "mapped_reads_per_s": float(mres["mapped"].sum()) / t_map,
         "note": "host buffers in, PAF fields + CIGAR out (b200_map_batch), semiGlobal, k=15 w=5 f=0.001"}
     index.close()
 
