@@ -400,9 +400,12 @@ static bool long_scores_ok(const Scores& sc, int type) {
 // its drift over one chunk. With g = gap, U = max(g, s_max - g, 0): neighbouring cells obey g <= dH <= U in
 // both directions (induction over team_alignment.cpp:104-114; the local clamp only tightens it), hence in the
 // moving frame Y = 4H - 4gj + 1 a vertical step changes Y by at most Dv = 4 max(|g|,|U|) + 3 and a horizontal
-// step by 0 .. Dh = 4 (U - g) + 3.
+// step by 0 .. Dh = 4 (U - g) + 3. The induction starts at the borders, whose own step is `init`: it needs
+// g <= init <= U, which holds for global (init = g) and, for semiGlobal/local (init = 0), only while g <= 0 --
+// with a positive gap score the cells next to a zero border grow by g per row and the bound is gone.
 static bool long16_scores_ok(const Scores& sc, int type) {
     if (!long_scores_ok(sc, type)) return false;
+    if (type != 0 && sc.gap > 0) return false;
     const long g = sc.gap, smax = std::max(sc.match, sc.mismatch);
     const long U = std::max({g, smax - g, 0l});
     const long Dv = 4 * std::max(std::labs(g), std::labs(U)) + 3, Dh = 4 * (U - g) + 3;

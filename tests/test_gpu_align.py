@@ -255,6 +255,21 @@ def test_long16_large_scores_leave_int16(ctx, typ):
 
 
 @pytest.mark.parametrize("typ", [0, 1, 2])
+def test_long_pairs_positive_gap_scores(ctx, typ):
+    """A positive gap score makes cells next to a zero border grow by `gap` per row: the 16-bit kernel's spread
+    bound only holds for global alignments there, the other two types must be planned on the int32 kernel
+    (found by tools/fuzz_gpu.py)."""
+    rng = np.random.default_rng(700 + typ)
+    qs, ts = [], []
+    for n in (2402, 5088):
+        t = seqgen.random_dna(rng, n)
+        qs.append(seqgen.mutate(rng, t, sub=0.05, ins=0.06, dele=0.06).tobytes()); ts.append(t.tobytes())
+    qs.append(seqgen.random_dna(rng, 2402).tobytes()); ts.append(seqgen.random_dna(rng, 4839).tobytes())
+    for m, x, g in ((12, -6, 2), (-3, 1, 2), (1, -1, 1)):
+        _check_batch(ctx, qs, ts, typ, m, x, g)
+
+
+@pytest.mark.parametrize("typ", [0, 1, 2])
 def test_long32_kernel_kept_covered(ctx, typ):
     """The int32 stripe kernel serves score sets the 16-bit bound rejects: keep it covered on the same inputs."""
     qs, ts = seqgen.ont_like_pairs(40 + typ, 3, mean_len=2500, min_len=1800, max_len=3200)
