@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(ROOT, "include")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "--use_fast_math", "-Xcompiler", "-fPIC,-O2,-Wall", "-shared", "-Xptxas", "-v",
+              "--use_fast_math", "-Xcompiler", "-fPIC,-O2,-Wall,-pthread", "-shared", "-Xptxas", "-v",
               "--expt-relaxed-constexpr"]
 
 

@@ -253,18 +253,23 @@ walk_tile_kernel(const PairDesc* __restrict__ pairs, const uint32_t* __restrict_
 }
 
 // Score-only batches still owe the caller target_begin (reference :119-121, :197-199, :283-285).
-__global__ void target_begin_kernel(uint32_t n, int type, const uint32_t* __restrict__ end_j,
+__global__ void target_begin_kernel(uint32_t first, uint32_t n, int type, const uint32_t* __restrict__ end_j,
                                     uint32_t* __restrict__ target_begin) {
-    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t p = first + blockIdx.x * blockDim.x + threadIdx.x;   // pairs [first, n)
     if (p < n) target_begin[p] = (type == 1) ? end_j[p] + 1 : 0;
+}
+
+__global__ void add_offset_kernel(uint64_t* __restrict__ v, uint32_t n, const uint64_t* __restrict__ base) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] += *base;
 }
 
 // One thread per pair (short pairs: a few runs each).
 __global__ void __launch_bounds__(128)
-emit_kernel(const PairDesc* __restrict__ pairs, uint32_t n, const uint32_t* __restrict__ runs,
+emit_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint32_t n, const uint32_t* __restrict__ runs,
             const uint32_t* __restrict__ n_runs, const uint64_t* __restrict__ cigar_off,
             char* __restrict__ cigar) {
-    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t p = first + blockIdx.x * blockDim.x + threadIdx.x;   // pairs [first, n)
     if (p >= n) return;
     const uint32_t nr = n_runs[p];
     char* dst = cigar + cigar_off[p];
@@ -284,10 +289,10 @@ emit_kernel(const PairDesc* __restrict__ pairs, uint32_t n, const uint32_t* __re
 // One warp per pair (long pairs: thousands of runs each): 32 runs at a time, back to front; a warp scan of
 // the runs' text lengths gives every lane its place.
 __global__ void __launch_bounds__(128)
-emit_warp_kernel(const PairDesc* __restrict__ pairs, uint32_t n, const uint32_t* __restrict__ runs,
+emit_warp_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint32_t n, const uint32_t* __restrict__ runs,
                  const uint32_t* __restrict__ n_runs, const uint64_t* __restrict__ cigar_off,
                  char* __restrict__ cigar) {
-    const uint32_t p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t p = first + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);   // pairs [first, n)
     const int lane = threadIdx.x & 31;
     if (p >= n) return;
     const uint32_t nr = n_runs[p];

@@ -13,6 +13,7 @@
 #include <new>
 #include <numeric>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <cub/device/device_radix_sort.cuh>
@@ -121,6 +122,11 @@ struct b200_ctx {
     // workspaces shared by every plan run on this context (one run at a time per context)
     WaveSlot slot[2];
     cudaStream_t aux_stream = nullptr;      // second wave stream of a run
+    cudaStream_t emit_stream = nullptr;     // host path: scan / emit / download of finished waves while later ones run
+    std::vector<cudaEvent_t> wave_done;     // one event per wave of the current run
+    // B200_TRACE=2: device timeline of a run (events with timing, printed relative to the first)
+    struct TlMark { std::string what; cudaEvent_t e; };
+    std::vector<TlMark> timeline;
     cudaEvent_t fork_event = nullptr;
     int64_t overlap_waves = 1;              // 0 = all waves on the caller's stream, one after the other
     DevBuf qpk, tpk, end_i, end_j, runs, n_runs, cigar_len, scan_tmp, flags, total;
@@ -175,6 +181,28 @@ static void prof_collect(b200_ctx* c, cudaStream_t st) {
     c->spans.clear();
 }
 
+static void tl_mark(b200_ctx* c, cudaStream_t st, const std::string& what) {
+    static const bool on = std::getenv("B200_TRACE") && std::atoi(std::getenv("B200_TRACE")) >= 2;
+    if (!on) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, st);
+    c->timeline.push_back({what, e});
+}
+static void tl_dump(b200_ctx* c) {
+    if (c->timeline.empty()) return;
+    cudaDeviceSynchronize();
+    std::string line = "[b200 timeline ms]";
+    for (auto& m : c->timeline) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, c->timeline[0].e, m.e);
+        line += " " + m.what + "=" + std::to_string(ms).substr(0, 5);
+    }
+    std::fprintf(stderr, "%s\n", line.c_str());
+    for (auto& m : c->timeline) cudaEventDestroy(m.e);
+    c->timeline.clear();
+}
+
 static int set_device(const b200_ctx* c) {
     CU(cudaSetDevice(c->device));
     return B200_OK;
@@ -219,6 +247,8 @@ extern "C" void b200_ctx_destroy(b200_ctx* c) {
     for (auto& sp : c->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     for (auto e : c->event_pool) cudaEventDestroy(e);
     if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
+    if (c->emit_stream) cudaStreamDestroy(c->emit_stream);
+    for (auto e : c->wave_done) cudaEventDestroy(e);
     if (c->fork_event) cudaEventDestroy(c->fork_event);
     for (WaveSlot& w : c->slot) {
         for (DevBuf* b : {&w.dirs, &w.bnd, &w.bnd_short, &w.progress, &w.stripe_res, &w.counter, &w.fix_work}) b->release();
@@ -452,8 +482,27 @@ static int plan_build(b200_align_plan* p, b200_ctx* ctx, size_t n, const uint64_
         const uint64_t Q0 = q_off[1] - q_off[0], T0 = t_off[1] - t_off[0];
         bool uni = q_off[1] >= q_off[0] && t_off[1] >= t_off[0] && Q0 <= 4096 && T0 <= 4096 &&
                    short_pair_ok(p->sc, (uint32_t)Q0, (uint32_t)T0);
-        for (size_t i = 1; uni && i < n; ++i)
-            uni = (q_off[i + 1] - q_off[i] == Q0) & (t_off[i + 1] - t_off[i] == T0);
+        // The scan reads 16 bytes per pair from host memory and sits between the start of the upload and the first
+        // wave (1 M pairs: 1.2 ms on one core): no early exit inside a block so the compiler can vectorise it, and
+        // large batches are split over a few threads.
+        auto scan = [&](size_t a, size_t b) -> bool {   // pairs [a, b), a >= 1
+            uint64_t bad = 0;
+            for (size_t i = a; i < b; ++i)
+                bad |= ((q_off[i + 1] - q_off[i]) ^ Q0) | ((t_off[i + 1] - t_off[i]) ^ T0);
+            return bad == 0;
+        };
+        if (uni && n > (1u << 18)) {
+            constexpr int kThreads = 4;
+            bool ok[kThreads] = {true, true, true, true};
+            std::thread th[kThreads - 1];
+            for (int t = 1; t < kThreads; ++t)
+                th[t - 1] = std::thread([&, t] { ok[t] = scan(std::max<size_t>(1, n * t / kThreads), n * (t + 1) / kThreads); });
+            ok[0] = scan(1, n / kThreads);
+            for (auto& x : th) x.join();
+            uni = ok[0] && ok[1] && ok[2] && ok[3];
+        } else if (uni) {
+            for (size_t i0 = 1; uni && i0 < n; i0 += 65536) uni = scan(i0, std::min(n, i0 + 65536));
+        }
         const uint64_t n_groups = div_up64(n, 64);
         const uint64_t wpg = p->want_cigar ? (uint64_t)div_up((uint32_t)Q0, kShortRows) * T0 * 128 : 0;
         // uniform batches may be cut into equal chunks (whole 64-pair groups) so that the host entry point can
@@ -816,9 +865,27 @@ static int launch_walk(b200_align_plan* p, uint32_t wave_klass, const uint32_t* 
     return B200_OK;
 }
 
+// Host destinations of a run made through the host-buffer entry point. When given (and the batch is a uniform
+// one cut into several waves), results are downloaded while later waves still run: scores and target_begin
+// wave by wave, CIGAR offsets and text in two groups (all waves but the last, then the last).
+struct HostOut {
+    int32_t* score; uint32_t* target_begin; char* cigar; uint64_t* cigar_off; uint64_t cigar_cap;
+    bool done = false;   // set by the run when it has issued (and completed) every download itself
+};
+
+static int plan_run_impl(b200_align_plan* p, const char* d_q_buf, const char* d_t_buf, int32_t* d_score,
+                         uint32_t* d_target_begin, char* d_cigar, uint64_t* d_cigar_off, uint64_t cigar_cap,
+                         void* stream, HostOut* ho);
+
 extern "C" int b200_align_plan_run(b200_align_plan* p, const char* d_q_buf, const char* d_t_buf,
                                    int32_t* d_score, uint32_t* d_target_begin, char* d_cigar,
                                    uint64_t* d_cigar_off, uint64_t cigar_cap, void* stream) {
+    return plan_run_impl(p, d_q_buf, d_t_buf, d_score, d_target_begin, d_cigar, d_cigar_off, cigar_cap, stream, nullptr);
+}
+
+static int plan_run_impl(b200_align_plan* p, const char* d_q_buf, const char* d_t_buf, int32_t* d_score,
+                         uint32_t* d_target_begin, char* d_cigar, uint64_t* d_cigar_off, uint64_t cigar_cap,
+                         void* stream, HostOut* ho) {
     if (!p) return fail(B200_E_ARG, "null plan");
     b200_ctx* c = p->ctx;
     const size_t n = p->n;
@@ -870,6 +937,15 @@ extern "C" int b200_align_plan_run(b200_align_plan* p, const char* d_q_buf, cons
     if (overlap) {   // the second stream starts after everything already queued on the caller's stream
         CU(cudaEventRecord(c->fork_event, st));
         CU(cudaStreamWaitEvent(c->aux_stream, c->fork_event, 0));
+    }
+    // pipelined download (see HostOut): pair index == work position in a uniform plan, so a wave is a contiguous slice
+    const bool piped = ho && overlap && p->uniform && p->waves.size() >= 3 && d_target_begin && ho->target_begin;
+    if (piped) {
+        if (!c->emit_stream) CU(cudaStreamCreateWithFlags(&c->emit_stream, cudaStreamNonBlocking));
+        while (c->wave_done.size() < p->waves.size()) {
+            cudaEvent_t e; CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            c->wave_done.push_back(e);
+        }
     }
 
     // A wave = classify (+ 2-bit pack) -> fill -> traceback walk, in order on its stream; when the host entry
@@ -929,6 +1005,7 @@ extern "C" int b200_align_plan_run(b200_align_plan* p, const char* d_q_buf, cons
             }
         }
         rb.dirs = p->want_cigar ? ws.dirs.as<uint32_t>() : nullptr;
+        tl_mark(c, wst, "pack" + std::to_string(k));
         if (wv.klass != kClassGeneric) {
             if (wv.klass == kClassShort) TRY(launch_fill_short(p, wv, rb));
             else TRY(launch_fill_long(p, wv, rb));
@@ -941,39 +1018,86 @@ extern "C" int b200_align_plan_run(b200_align_plan* p, const char* d_q_buf, cons
         } else {
             TRY(launch_fill_generic(p, work, wv.count, rb));
         }
+        tl_mark(c, wst, "fill" + std::to_string(k));
         if (p->want_cigar) TRY(launch_walk(p, wv.klass, work, wv.count, rb));
+        tl_mark(c, wst, "walk" + std::to_string(k));
+        if (piped) {
+            const uint32_t a = wv.first, b = wv.first + wv.count;
+            target_begin_kernel<<<(unsigned)div_up64(wv.count, 256), 256, 0, wst>>>(a, b, p->type, c->end_j.as<uint32_t>(), d_target_begin);
+            c->kernel_launches++;
+            CU(cudaMemcpyAsync(ho->score + a, d_score + a, (size_t)wv.count * 4, cudaMemcpyDeviceToHost, wst));
+            CU(cudaMemcpyAsync(ho->target_begin + a, d_target_begin + a, (size_t)wv.count * 4, cudaMemcpyDeviceToHost, wst));
+            c->d2h_bytes += (uint64_t)wv.count * 8;
+            CU(cudaEventRecord(c->wave_done[k], wst));
+        }
         if (overlap) CU(cudaEventRecord(ws.done, wst));
     }
     CU(cudaGetLastError());
     if (overlap) CU(cudaStreamWaitEvent(st, c->slot[1].done, 0));   // join: the rest runs on the caller's stream
 
-    if (d_target_begin) {
-        target_begin_kernel<<<(unsigned)div_up64(n, 256), 256, 0, st>>>((uint32_t)n, p->type, c->end_j.as<uint32_t>(), d_target_begin);
+    if (d_target_begin && !piped) {
+        target_begin_kernel<<<(unsigned)div_up64(n, 256), 256, 0, st>>>(0u, (uint32_t)n, p->type, c->end_j.as<uint32_t>(), d_target_begin);
         c->kernel_launches++;
     }
     if (p->want_cigar) {
-        cub::TransformInputIterator<uint64_t, U32ToU64, const uint32_t*> in(c->cigar_len.as<uint32_t>(), U32ToU64());
-        size_t tmp_bytes = 0;
-        CU(cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, in, d_cigar_off + 1, (int)n, st));
-        TRY(c->scan_tmp.ensure(tmp_bytes));
-        CU(cudaMemsetAsync(d_cigar_off, 0, sizeof(uint64_t), st));
-        prof_begin(c, st, 3);
-        CU(cub::DeviceScan::InclusiveSum(c->scan_tmp.p, tmp_bytes, in, d_cigar_off + 1, (int)n, st));
-        prof_end(c, st);
-        c->kernel_launches += 2;
-        uint64_t total = 0;
-        CU(cudaMemcpyAsync(&total, d_cigar_off + n, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
-        if (total > cigar_cap)
-            return fail(B200_E_CAP, "CIGAR buffer too small: need " + std::to_string(total) + " bytes, have " + std::to_string(cigar_cap));
-        prof_begin(c, st, 2);
-        // many short pairs: a thread each; fewer, longer pairs (thousands of runs): a warp each
-        if (p->n_short * 2 >= n)
-            emit_kernel<<<(unsigned)div_up64(n, 128), 128, 0, st>>>(p->d_pairs.as<PairDesc>(), (uint32_t)n, c->runs.as<uint32_t>(), c->n_runs.as<uint32_t>(), d_cigar_off, d_cigar);
-        else
-            emit_warp_kernel<<<(unsigned)div_up64(n * 32, 128), 128, 0, st>>>(p->d_pairs.as<PairDesc>(), (uint32_t)n, c->runs.as<uint32_t>(), c->n_runs.as<uint32_t>(), d_cigar_off, d_cigar);
-        prof_end(c, st);
-        c->kernel_launches++;
+        // CIGAR offsets (scan of the text lengths) and text, for pairs [a, b) on stream es; `base` = bytes before pair a
+        // (device scalar d_cigar_off[a] is final by then). Returns the byte count up to pair b through *total_out.
+        auto scan_emit = [&](uint32_t a, uint32_t b, cudaStream_t es, uint64_t* total_out) -> int {
+            cub::TransformInputIterator<uint64_t, U32ToU64, const uint32_t*> in(c->cigar_len.as<uint32_t>() + a, U32ToU64());
+            size_t tmp_bytes = 0;
+            CU(cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, in, d_cigar_off + a + 1, (int)(b - a), es));
+            TRY(c->scan_tmp.ensure(tmp_bytes));
+            if (a == 0) CU(cudaMemsetAsync(d_cigar_off, 0, sizeof(uint64_t), es));
+            prof_begin(c, es, 3);
+            CU(cub::DeviceScan::InclusiveSum(c->scan_tmp.p, tmp_bytes, in, d_cigar_off + a + 1, (int)(b - a), es));
+            if (a) add_offset_kernel<<<(unsigned)div_up64(b - a, 256), 256, 0, es>>>(d_cigar_off + a + 1, b - a, d_cigar_off + a);
+            prof_end(c, es);
+            c->kernel_launches += 2 + (a ? 1 : 0);
+            uint64_t total = 0;
+            CU(cudaMemcpyAsync(&total, d_cigar_off + b, sizeof(uint64_t), cudaMemcpyDeviceToHost, es));
+            CU(cudaStreamSynchronize(es));
+            *total_out = total;
+            if (total > cigar_cap)
+                return fail(B200_E_CAP, "CIGAR buffer too small: need " + std::to_string(total) + " bytes, have " + std::to_string(cigar_cap));
+            prof_begin(c, es, 2);
+            // many short pairs: a thread each; fewer, longer pairs (thousands of runs): a warp each
+            if (p->n_short * 2 >= n)
+                emit_kernel<<<(unsigned)div_up64(b - a, 128), 128, 0, es>>>(p->d_pairs.as<PairDesc>(), a, b, c->runs.as<uint32_t>(), c->n_runs.as<uint32_t>(), d_cigar_off, d_cigar);
+            else
+                emit_warp_kernel<<<(unsigned)div_up64((uint64_t)(b - a) * 32, 128), 128, 0, es>>>(p->d_pairs.as<PairDesc>(), a, b, c->runs.as<uint32_t>(), c->n_runs.as<uint32_t>(), d_cigar_off, d_cigar);
+            prof_end(c, es);
+            c->kernel_launches++;
+            return B200_OK;
+        };
+        if (piped) {
+            // group A = every wave but the last: scanned, emitted and downloaded on the emit stream while the last wave runs
+            const size_t nw = p->waves.size();
+            const uint32_t nA = p->waves[nw - 1].first;
+            cudaStream_t es = c->emit_stream;
+            CU(cudaStreamWaitEvent(es, c->wave_done[nw - 2], 0));
+            CU(cudaStreamWaitEvent(es, c->wave_done[nw - 3], 0));
+            uint64_t totalA = 0, total = 0;
+            tl_mark(c, es, "A-ready");
+            TRY(scan_emit(0, nA, es, &totalA));
+            if (ho->cigar_cap < totalA) return fail(B200_E_CAP, "CIGAR buffer too small: need " + std::to_string(totalA));
+            CU(cudaMemcpyAsync(ho->cigar_off, d_cigar_off, ((size_t)nA + 1) * 8, cudaMemcpyDeviceToHost, es));
+            if (totalA) CU(cudaMemcpyAsync(ho->cigar, d_cigar, totalA, cudaMemcpyDeviceToHost, es));
+            // group B = the last wave, after everything else (st has joined the other wave stream above)
+            tl_mark(c, es, "A-down");
+            CU(cudaStreamWaitEvent(es, c->wave_done[nw - 1], 0));
+            tl_mark(c, es, "B-ready");
+            TRY(scan_emit(nA, (uint32_t)n, es, &total));
+            if (ho->cigar_cap < total) return fail(B200_E_CAP, "CIGAR buffer too small: need " + std::to_string(total));
+            CU(cudaMemcpyAsync(ho->cigar_off + nA + 1, d_cigar_off + nA + 1, ((size_t)n - nA) * 8, cudaMemcpyDeviceToHost, es));
+            if (total > totalA) CU(cudaMemcpyAsync(ho->cigar + totalA, d_cigar + totalA, total - totalA, cudaMemcpyDeviceToHost, es));
+            tl_mark(c, es, "B-down");
+            CU(cudaStreamSynchronize(es));
+            c->d2h_bytes += ((uint64_t)n + 1) * 8 + total;
+            ho->done = true;
+        } else {
+            uint64_t total = 0;
+            TRY(scan_emit(0, (uint32_t)n, st, &total));
+        }
     }
     CU(cudaGetLastError());
     if (p->n_long) {
@@ -1031,11 +1155,13 @@ extern "C" int b200_align_batch_packed(b200_ctx* c, size_t n, const char* q_buf,
         c->copy_events.push_back(e);
     }
     const uint64_t qn = q1 - q0, tn = t1 - t0;
+    tl_mark(c, c->copy_stream, "start");
     for (int s = 0; s < kPipe; ++s) {
         const uint64_t qa = qn * s / kPipe, qb = qn * (s + 1) / kPipe, ta = tn * s / kPipe, tb = tn * (s + 1) / kPipe;
         if (qb > qa) CU(cudaMemcpyAsync(c->d_q.as<char>() + qa, q_buf + q0 + qa, qb - qa, cudaMemcpyHostToDevice, c->copy_stream));
         if (tb > ta) CU(cudaMemcpyAsync(c->d_t.as<char>() + ta, t_buf + t0 + ta, tb - ta, cudaMemcpyHostToDevice, c->copy_stream));
         CU(cudaEventRecord(c->copy_events[s], c->copy_stream));
+        if (s == 0 || s == kPipe / 2 - 1 || s == kPipe - 1) tl_mark(c, c->copy_stream, "h2d" + std::to_string(s));
     }
     c->h2d_bytes += qn + tn;
     tr.mark("enqueue-h2d");
@@ -1077,10 +1203,17 @@ extern "C" int b200_align_batch_packed(b200_ctx* c, size_t n, const char* q_buf,
     TRY(c->d_tb.ensure(n * 4));
     if (want_cigar) { TRY(c->d_cigar.ensure(dev_cigar_cap + 16)); TRY(c->d_cigar_off.ensure((n + 1) * 8)); }
     if (tr.on) { cudaStreamSynchronize(st); tr.mark("alloc+h2d"); }
-    TRY(b200_align_plan_run(plan, c->d_q.as<char>(), c->d_t.as<char>(), c->d_score.as<int32_t>(),
-                            c->d_tb.as<uint32_t>(), want_cigar ? c->d_cigar.as<char>() : nullptr,
-                            want_cigar ? c->d_cigar_off.as<uint64_t>() : nullptr, dev_cigar_cap, st));
+    HostOut ho{score, target_begin, cigar_buf, cigar_off, cigar_cap};
+    TRY(plan_run_impl(plan, c->d_q.as<char>(), c->d_t.as<char>(), c->d_score.as<int32_t>(),
+                      c->d_tb.as<uint32_t>(), want_cigar ? c->d_cigar.as<char>() : nullptr,
+                      want_cigar ? c->d_cigar_off.as<uint64_t>() : nullptr, dev_cigar_cap, st, want_cigar ? &ho : nullptr));
     if (tr.on) { cudaStreamSynchronize(st); tr.mark("run"); }
+    if (ho.done) {   // everything was downloaded while the last wave ran
+        CU(cudaStreamSynchronize(st));
+        tr.mark("d2h");
+        tl_dump(c);
+        return B200_OK;
+    }
     CU(cudaMemcpyAsync(score, c->d_score.p, n * 4, cudaMemcpyDeviceToHost, st));
     c->d2h_bytes += n * 4;
     if (target_begin) { CU(cudaMemcpyAsync(target_begin, c->d_tb.p, n * 4, cudaMemcpyDeviceToHost, st)); c->d2h_bytes += n * 4; }
