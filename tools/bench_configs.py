@@ -33,6 +33,9 @@ def main():
     ap.add_argument("--reads", type=int, default=100_000)
     ap.add_argument("--pairs", type=int, default=10_000)
     ap.add_argument("--batch", type=int, default=16384, help="reads per b200_map_batch / MinimizeBatch call")
+    ap.add_argument("--cpu", action="store_true",
+                    help="rank 0 also times the UNMODIFIED reference (oracle/_ref, one thread) on samples of each config "
+                         "and checks the GPU results of those samples against it (BASELINE.md section 4)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -140,7 +143,23 @@ def main():
                 dist.all_reduce(sums)
             bases, tuples = float(sums[0]), float(sums[1])
             alg = bases + 9 * tuples
-            emit({"config": "c3", "reads": args.reads, "bases": bases, "tuples": tuples, "minimize_s": t,
+            cpu = None
+            if args.cpu and rank == 0:
+                from cpu_checkers import load_ref
+                R = load_ref()
+                if R is not None:
+                    starts = np.concatenate([[0], np.cumsum(lens1)]).astype(np.int64)
+                    ids = list(range(0, 2048, 16))            # 128 sampled reads
+                    seqs = [buf1[starts[i]:starts[i] + int(lens1[i])].tobytes() for i in ids]
+                    t0 = time.perf_counter()
+                    exp = [R.minimize(sq, 15, 5, True) for sq in seqs]
+                    t_cpu = time.perf_counter() - t0
+                    got = ctx.minimize(seqs, 15, 5)
+                    ok = all(all(np.array_equal(a, b) for a, b in zip(g, e)) for g, e in zip(got, exp))
+                    nb = sum(len(sq) for sq in seqs)
+                    cpu = {"kind": "reference", "cores": 1, "sample": f"{len(seqs)} reads, {nb} bases", "mbases_per_s": nb / t_cpu / 1e6,
+                           "extrapolated_full_config_s": bases / (nb / t_cpu), "parity_on_sample": bool(ok)}
+            emit({"config": "c3", "reads": args.reads, "bases": bases, "tuples": tuples, "minimize_s": t, "cpu_baseline": cpu,
                   "gbases_per_s": bases / t / 1e9, "hbm_gbs_algorithmic": alg / t / 1e9,
                   "roofline_frac_hbm_per_gpu": alg / t / 1e9 / world / peaks["hbm_gbs"],
                   "index_build_s_cold": t_index, "index_build_s_warm": t_index2,
@@ -170,8 +189,50 @@ def main():
             m = torch.tensor([mapped], dtype=torch.float64, device=dev)
             if world > 1:
                 dist.all_reduce(m)
+            cpu = None
+            ref_bin = os.path.join(ROOT, "oracle", "_ref", "ref_mapper")
+            if args.cpu and rank == 0 and os.path.exists(ref_bin):
+                import subprocess, tempfile
+                sys.path.insert(0, os.path.join(ROOT, "oracle"))
+                import mapper_oracle
+                starts = np.concatenate([[0], np.cumsum(lens1)]).astype(np.int64)
+                ids = list(range(0, 2048, 64))                # 32 sampled reads, both strands
+                seqs = [buf1[starts[i]:starts[i] + int(lens1[i])].tobytes() for i in ids]
+                with tempfile.TemporaryDirectory() as td:
+                    with open(os.path.join(td, "ref.fa"), "wb") as fh:
+                        fh.write(b">ref\n" + ref.tobytes() + b"\n")
+                    with open(os.path.join(td, "reads.fq"), "wb") as fh:
+                        for i, sq in zip(ids, seqs):
+                            fh.write(b"@r%d\n" % i + sq + b"\n+\n" + b"I" * len(sq) + b"\n")
+                    with open(os.path.join(td, "one.fq"), "wb") as fh:
+                        fh.write(b"@r0\n" + seqs[0][:200] + b"\n+\n" + b"I" * 200 + b"\n")
+                    argv = ["-a", "semiGlobal", "-c", "-f", "0"]
+                    t0 = time.perf_counter()
+                    subprocess.run([ref_bin] + argv + ["ref.fa", "one.fq"], cwd=td, capture_output=True)
+                    t_index = time.perf_counter() - t0        # index build + one 200-base read
+                    t0 = time.perf_counter()
+                    r = subprocess.run([ref_bin] + argv + ["ref.fa", "reads.fq"], cwd=td, capture_output=True)
+                    t_all = time.perf_counter() - t0
+                exp_lines = r.stdout.decode().splitlines()
+                # the same reads through the GPU pipeline with f = 0 (strict parity; the default f's tie order is unstable in the reference)
+                idx0 = capi.Index(ctx, ref.tobytes(), 15, 5, 0.0)
+                res, cigs = idx0.map_batch(seqs, True, 2, 1, -1, -1, True)
+                idx0.close()
+                got_lines = []
+                for k, sq in enumerate(seqs):
+                    if not res[k]["mapped"]:
+                        continue
+                    d = dict(q_begin=int(res[k]["q_begin"]), q_end=int(res[k]["q_end"]), fwd=bool(res[k]["strand_fwd"]),
+                             t_begin=int(res[k]["t_begin"]), t_end=int(res[k]["t_end"]), score=int(res[k]["score"]), cigar=cigs[k])
+                    got_lines.append(mapper_oracle.paf_line("r%d" % ids[k], len(sq), "ref", len(ref), d, True))
+                norm = lambda L: [x.decode() if isinstance(x, bytes) else x for x in L]
+                per_read = max(t_all - t_index, 1e-9) / len(seqs)
+                cpu = {"kind": "reference", "cores": 1, "sample": f"{len(seqs)} reads (+ index build over the 4.6 Mbp reference)",
+                       "index_build_s": t_index, "reads_per_s_without_index": 1.0 / per_read,
+                       "extrapolated_full_config_s": per_read * args.reads + t_index,
+                       "paf_lines": len(exp_lines), "parity_on_sample": norm(got_lines) == norm(exp_lines)}
             emit({"config": "c4", "reads": args.reads, "mapped": float(m[0]), "map_s": t, "mapped_reads_per_s": float(m[0]) / t,
-                  "batch_reads": args.batch,
+                  "batch_reads": args.batch, "cpu_baseline": cpu,
                   "note": "host buffers in, PAF fields + CIGAR out (b200_map_batch), semiGlobal 1/-1/-1, k=15 w=5 f=0.001"})
         index.close()
 
@@ -206,7 +267,23 @@ def main():
         c = torch.tensor([cells], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(c)
-        emit({"config": "c5", "pairs": args.pairs, "cells": float(c[0]), "s_per_pass": t, "gcups": float(c[0]) / t / 1e9,
+        cpu = None
+        if args.cpu and rank == 0:
+            from cpu_checkers import load_ref
+            R = load_ref()
+            if R is not None:
+                sc = d_s.cpu().numpy(); tbg = d_b.cpu().numpy(); cg = d_c.cpu().numpy(); co = d_o.cpu().numpy()
+                ok = True; t_cpu = 0.0; ccells = 0
+                for kk in range(4):                           # 4 sampled pairs (800 MB and ~1.5 s each on the CPU)
+                    q = fq[int(ids[kk])].tobytes(); tt = ft[int(ids[kk])].tobytes()
+                    t0 = time.perf_counter()
+                    exp = R.align(q, tt, 1, 1, -1, -1, True)
+                    t_cpu += time.perf_counter() - t0
+                    ccells += len(q) * len(tt)
+                    ok &= (int(sc[kk]), int(tbg[kk]) & 0xffffffff, cg[int(co[kk]):int(co[kk + 1])].tobytes()) == exp
+                cpu = {"kind": "reference", "cores": 1, "sample": "4 pairs", "gcups": ccells / t_cpu / 1e9,
+                       "extrapolated_full_config_s": float(c[0]) / (ccells / t_cpu), "parity_on_sample": bool(ok)}
+        emit({"config": "c5", "pairs": args.pairs, "cells": float(c[0]), "s_per_pass": t, "gcups": float(c[0]) / t / 1e9, "cpu_baseline": cpu,
               "dir_bytes": float(c[0]) / 4, "note": "local 10 kb x 10 kb, score + CIGAR + target_begin, device-resident"})
         L.b200_align_plan_destroy(plan)
     if world > 1:
