@@ -14,6 +14,7 @@
 // All arithmetic of the path (minimizers, index, seeds, chaining, alignment) runs on the GPU through
 // include/b200map.h; this file is argument parsing, FASTA/FASTQ text, statistics and PAF printing.
 #include <algorithm>
+#include <chrono>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -34,6 +35,8 @@ constexpr const char* kProgram = "toolForGenomeAllignment";   // the reference's
 constexpr const char* kVersion = "3.1.0";
 
 struct Record { std::string name, seq; };
+
+double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 void usage(std::ostream& os) {
     os << "\nUsage: " << kProgram << " [options] <file1> <file2>\n"
@@ -137,10 +140,14 @@ struct MappedRead { b200_mapping m; std::string cigar; };
 // one device: replicated index, a contiguous slice of the reads, chunked to bound device memory
 int map_slice(int device, const Options& o, const std::string& ref, const std::vector<Record>& reads, size_t lo, size_t hi,
               bool fastq, std::vector<MappedRead>& out, std::string& err) {
+    const bool trace = std::getenv("B200_TRACE") != nullptr;
+    const double t0 = now_s();
     b200_ctx* ctx = nullptr;
     if (b200_ctx_create(device, &ctx) != B200_OK) { err = b200_last_error(); return 1; }
+    const double t1 = now_s();
     b200_index* ix = nullptr;
     if (b200_index_build(ctx, ref.data(), ref.size(), o.k, o.w, o.f, &ix) != B200_OK) { err = b200_last_error(); b200_ctx_destroy(ctx); return 1; }
+    if (trace) std::fprintf(stderr, "[b200_mapper trace] gpu %d: context %.3f s, index %.3f s\n", device, t1 - t0, now_s() - t1);
     int rc = 0;
     size_t i = lo;
     while (i < hi && rc == 0) {
@@ -153,8 +160,10 @@ int map_slice(int device, const Options& o, const std::string& ref, const std::v
         const uint64_t cap = o.cigar ? 4 * bases + 64 * (j - i) + 64 : 0;
         std::vector<char> cig(cap ? cap : 1);
         std::vector<uint64_t> coff(j - i + 1, 0);
+        const double tb0 = now_s();
         const int e = b200_map_batch(ctx, ix, j - i, buf.data(), off.data(), fastq ? 1 : 0, o.type, o.match, o.mismatch, o.gap,
                                      o.cigar ? 1 : 0, m.data(), o.cigar ? cig.data() : nullptr, o.cigar ? coff.data() : nullptr, cap);
+        if (trace) std::fprintf(stderr, "[b200_mapper trace] gpu %d: batch of %zu reads mapped in %.3f s\n", device, j - i, now_s() - tb0);
         if (e != B200_OK) {
             // the reference logs and skips a read whose Align throws (:680-683); a batch failure is fatal here
             err = std::string("ERROR: Exception during Align: ") + b200_last_error();
@@ -167,14 +176,17 @@ int map_slice(int device, const Options& o, const std::string& ref, const std::v
         }
         i = j;
     }
-    b200_index_destroy(ix);
-    b200_ctx_destroy(ctx);
+    // The index and the context (tens of GB of device workspace) are deliberately not destroyed: the process is
+    // about to exit, and returning that memory piece by piece costs about a second.
+    (void)ix;
     return rc;
 }
 
 }  // namespace
 
 int main(int argc, char** argv) {
+    const bool trace = std::getenv("B200_TRACE") != nullptr;   // phase wall clocks on stderr
+    const double t_start = now_s();
     Options o;
     if (argc < 2) { std::cerr << "Error: Not enough arguments\n"; usage(std::cout); return 1; }
     const std::string a1 = argv[1];
@@ -212,6 +224,7 @@ int main(int argc, char** argv) {
     bool fastq = read_fastq(o.file2, reads);   // FASTQ first, FASTA on failure (:533-556)
     if (!fastq) { reads.clear(); if (!read_fasta(o.file2, reads)) { std::cerr << "Given file is not in FASTA or FASTQ format! \n"; return 1; } }
 
+    const double t_parsed = now_s();
     if (b200_device_count() <= 0) { std::cerr << "Error: no CUDA device visible (this mapper has no CPU fallback)\n"; return 1; }
     o.gpus = std::min(o.gpus, b200_device_count());
 
@@ -233,6 +246,7 @@ int main(int argc, char** argv) {
     }
     for (auto& t : th) t.join();
     for (int g = 0; g < o.gpus; ++g) if (rcs[g]) { std::cerr << errs[g] << std::endl; return 1; }
+    const double t_mapped = now_s();
 
     const uint64_t RL = ref.seq.size();
     std::string outbuf;
@@ -250,5 +264,10 @@ int main(int argc, char** argv) {
         if (outbuf.size() > (1u << 20)) { std::fwrite(outbuf.data(), 1, outbuf.size(), stdout); outbuf.clear(); }
     }
     std::fwrite(outbuf.data(), 1, outbuf.size(), stdout);
-    return 0;
+    if (trace)
+        std::fprintf(stderr, "[b200_mapper trace] read files %.3f s, index + map %.3f s, write PAF %.3f s\n", t_parsed - t_start,
+                     t_mapped - t_parsed, now_s() - t_mapped);
+    std::fflush(stdout);
+    std::fflush(stderr);
+    std::_Exit(0);   // skip the CUDA runtime's teardown of the (large) device allocations
 }

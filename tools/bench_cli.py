@@ -37,8 +37,8 @@ with tempfile.TemporaryDirectory() as td:
     exe = os.path.join(ROOT, "bioinfo1_b200", "b200_mapper")
     for argv in (["-a", "semiGlobal", "-c"], ["-a", "semiGlobal"]):
         t0 = time.perf_counter()
-        r = subprocess.run([exe] + argv + ["--gpus", str(gpus), "ref.fa", "reads.fq"], cwd=td, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+        r = subprocess.run([exe] + argv + ["--gpus", str(gpus), "ref.fa", "reads.fq"], cwd=td, stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=dict(os.environ, B200_TRACE="1"))
         t = time.perf_counter() - t0
         print(json.dumps({"argv": argv, "gpus": gpus, "reads": n_reads, "bases": nb, "rc": r.returncode, "wall_s": t,
                           "reads_per_s": n_reads / t, "paf_lines": r.stdout.count(b"\n"), "paf_bytes": len(r.stdout),
-                          "stderr": r.stderr.decode(errors="replace")[-200:]}))
+                          "trace": [l for l in r.stderr.decode(errors="replace").splitlines() if "b200_mapper trace" in l]}))
