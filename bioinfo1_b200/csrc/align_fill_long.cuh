@@ -270,14 +270,40 @@ fill_long_kernel(const uint32_t* __restrict__ qpk, const uint32_t* __restrict__ 
     }
 }
 
-// One thread per pair of the long class: combine the per-stripe candidates with the reference's
-// tie rules (team_alignment.cpp:117-118, :265-278) and handle pairs without inner cells.
+// Combine the per-stripe candidates of one pair (wave position k, pair p) with the reference's tie rules
+// (team_alignment.cpp:117-118, :265-278). `results` is read through L2 (__ldcg): the caller may be the last
+// stripe's warp of a still running fill kernel, and the entries were written by other SMs.
+template <int TYPE>
+__device__ __forceinline__ void finalize_pair(uint32_t p, uint32_t Q, uint32_t T, uint32_t t0, uint32_t t1,
+                                              const StripeResult* results, int32_t* score, uint32_t* end_i, uint32_t* end_j) {
+    const int2* r2 = reinterpret_cast<const int2*>(results);   // an entry = three int2: {colbest, coli}, {rowbest, rowj}, {final_h, pad}
+    if (TYPE == 1) {
+        int M = INT_MIN; uint32_t sfirst = 0;
+        for (uint32_t t = t0; t < t1; ++t) { const int cb = __ldcg(r2 + 3 * t).x; if (cb > M) { M = cb; sfirst = t - t0; } }
+        score[p] = M;
+        // M == 0: the reference's strict '>' scan keeps the very first cell (team_alignment.cpp:186-192)
+        if (M <= 0) { end_i[p] = 1; end_j[p] = 1; }
+        else { end_i[p] = 0x80000000u | sfirst; end_j[p] = 0; }   // to be resolved by the locate kernel
+        return;
+    }
+    if (TYPE == 0) { score[p] = __ldcg(r2 + 3 * (t1 - 1) + 2).x; end_i[p] = Q; end_j[p] = T; return; }
+    int colbest = INT_MIN; uint32_t coli = 0;
+    for (uint32_t t = t0; t < t1; ++t) {   // stripes in row order, strict '>' keeps the smallest i
+        const int2 c = __ldcg(r2 + 3 * t);
+        if (c.x > colbest) { colbest = c.x; coli = (uint32_t)c.y; }
+    }
+    const int2 last = __ldcg(r2 + 3 * (t1 - 1) + 1);   // {rowbest, rowj} of the last stripe
+    if (last.x > colbest) { score[p] = last.x; end_i[p] = Q; end_j[p] = (uint32_t)last.y; }
+    else { score[p] = colbest; end_i[p] = coli; end_j[p] = T; }
+}
+
+// One thread per pair of the long class: finalize_pair, plus the pairs without inner cells.
 template <int TYPE>
 __global__ void finalize_long_kernel(const PairDesc* __restrict__ pairs, const uint32_t* __restrict__ work,
                                      uint32_t n_work, const uint32_t* __restrict__ task_off,
-                                     const uint8_t* __restrict__ flags, const StripeResult* __restrict__ results,
+                                     const uint8_t* __restrict__ flags, const StripeResult* results,
                                      int init, int32_t* __restrict__ score, uint32_t* __restrict__ end_i,
-                                     uint32_t* __restrict__ end_j) {
+                                     uint32_t* __restrict__ end_j, int only_empty, uint32_t* __restrict__ ready) {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n_work) return;
     const uint32_t p = work[k];
@@ -287,25 +313,11 @@ __global__ void finalize_long_kernel(const PairDesc* __restrict__ pairs, const u
         if (TYPE == 0) { score[p] = (int)((Q + T) * (uint32_t)init); end_i[p] = Q; end_j[p] = T; }
         else if (TYPE == 1) { score[p] = 0; end_i[p] = 0; end_j[p] = 0; }
         else { score[p] = 0; end_i[p] = 0; end_j[p] = T; }
+        if (ready) ready[k] = 1u;   // nothing to fill: a concurrent walker may take the pair at once
         return;
     }
-    const uint32_t t0 = task_off[k], t1 = task_off[k + 1];
-    if (TYPE == 1) {
-        int M = INT_MIN; uint32_t sfirst = 0;
-        for (uint32_t t = t0; t < t1; ++t) if (results[t].colbest > M) { M = results[t].colbest; sfirst = t - t0; }
-        score[p] = M;
-        // M == 0: the reference's strict '>' scan keeps the very first cell (team_alignment.cpp:186-192)
-        if (M <= 0) { end_i[p] = 1; end_j[p] = 1; }
-        else { end_i[p] = 0x80000000u | sfirst; end_j[p] = 0; }   // to be resolved by locate_long_kernel
-        return;
-    }
-    if (TYPE == 0) { score[p] = results[t1 - 1].final_h; end_i[p] = Q; end_j[p] = T; return; }
-    int colbest = INT_MIN; uint32_t coli = 0;
-    for (uint32_t t = t0; t < t1; ++t)   // stripes in row order, strict '>' keeps the smallest i
-        if (results[t].colbest > colbest) { colbest = results[t].colbest; coli = results[t].coli; }
-    const StripeResult last = results[t1 - 1];
-    if (last.rowbest > colbest) { score[p] = last.rowbest; end_i[p] = Q; end_j[p] = last.rowj; }
-    else { score[p] = colbest; end_i[p] = coli; end_j[p] = T; }
+    if (only_empty) return;
+    finalize_pair<TYPE>(p, Q, T, task_off[k], task_off[k + 1], results, score, end_i, end_j);
 }
 
 // Local alignments, second pass: fill_long_kernel<1> only tracks the VALUE of the maximum; this

@@ -278,7 +278,10 @@ fill_long16_kernel(const uint32_t* __restrict__ qpk, const uint32_t* __restrict_
                    const uint32_t* __restrict__ task_off, const uint64_t* __restrict__ bnd_off,
                    uint32_t* __restrict__ work_counter, const uint8_t* __restrict__ flags, ShortConsts K,
                    uint32_t* __restrict__ dirs, int32_t* bnd, uint32_t* progress,
-                   StripeResult* __restrict__ results, uint32_t* __restrict__ stall_flag) {
+                   StripeResult* results, uint32_t* __restrict__ stall_flag,
+                   // concurrent walk (all null otherwise): the warp that finishes a pair's last outstanding stripe
+                   // finalises the pair and raises its ready flag, so a walker can start while the fill goes on
+                   uint32_t* pair_done, uint32_t* ready, int32_t* score, uint32_t* end_i, uint32_t* end_j) {
     const int lane = threadIdx.x & 31;
     const uint32_t n_tasks = task_off[n_work];
     for (;;) {
@@ -331,6 +334,18 @@ fill_long16_kernel(const uint32_t* __restrict__ qpk, const uint32_t* __restrict_
         const int rowbest = __shfl_sync(kFull, sw.rowbest, (int)lq);
         const uint32_t rowj = __shfl_sync(kFull, sw.rowj, (int)lq);
         if (lane == 0) results[task] = StripeResult{colbest, coli, rowbest, rowj, final_h, first_block};
+        if (TYPE != 1 && ready != nullptr) {
+            if (lane == 0) {
+                __threadfence();                                           // this stripe's result before the count
+                if (atomicAdd(pair_done + k, 1u) + 1 == n_stripes) {       // every stripe of the pair has reported
+                    __threadfence();
+                    finalize_pair<TYPE>(p, pd.Q, pd.T, task_off[k], task_off[k] + n_stripes, results, score, end_i, end_j);
+                    __threadfence();
+                    st_release(ready + k, 1u);
+                }
+            }
+            __syncwarp();
+        }
     }
 }
 

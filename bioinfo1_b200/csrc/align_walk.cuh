@@ -25,6 +25,12 @@
 
 namespace b200 {
 
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
 __device__ __forceinline__ uint32_t dec_digits(uint32_t v) {
     uint32_t d = 1;
     while (v >= 10) { v /= 10; ++d; }
@@ -140,7 +146,9 @@ constexpr int kWalkTileWords = kTileBlocks * kTileSlots * 4;   // shared-memory 
 // Inside the tile the warp advances by whole RUNS: lane l looks at the cell l steps further along the
 // current direction (diagonal first), a ballot counts how far the run goes, and the run is pushed at once --
 // a CIGAR is run-length encoded anyway, and ONT-like paths average ~10 cells per run.
-template <int TYPE, uint32_t KLASS>
+// COHERENT: tile loads go through L2 (ld.cg) instead of the read-only path -- for the walker that runs while the
+// fill kernel is still writing other pairs' matrices.
+template <int TYPE, uint32_t KLASS, bool COHERENT>
 __device__ __forceinline__ void walk_tiles(const PairDesc& pd, const uint32_t* __restrict__ base, uint32_t& i, uint32_t& j,
                                            uint32_t* tile, RunWriter& rw, int lane) {
     constexpr uint32_t RL = TileShape<KLASS>::RL, WPC = TileShape<KLASS>::WPC;
@@ -178,9 +186,15 @@ __device__ __forceinline__ void walk_tiles(const PairDesc& pd, const uint32_t* _
                     if (rb_base + b < n_rb && sl < pitch) {
                         const uint32_t* src = base + ((uint64_t)(rb_base + b) * pitch + sl) * WPC;
                         uint32_t* dst = tile + (b * kTileSlots + srel) * WPC;
-                        if (WPC == 1) dst[0] = __ldg(src);
-                        else if (WPC == 2) *reinterpret_cast<uint2*>(dst) = __ldg(reinterpret_cast<const uint2*>(src));
-                        else *reinterpret_cast<uint4*>(dst) = __ldg(reinterpret_cast<const uint4*>(src));
+                        if (COHERENT) {
+                            if (WPC == 1) dst[0] = __ldcg(src);
+                            else if (WPC == 2) *reinterpret_cast<uint2*>(dst) = __ldcg(reinterpret_cast<const uint2*>(src));
+                            else *reinterpret_cast<uint4*>(dst) = __ldcg(reinterpret_cast<const uint4*>(src));
+                        } else {
+                            if (WPC == 1) dst[0] = __ldg(src);
+                            else if (WPC == 2) *reinterpret_cast<uint2*>(dst) = __ldg(reinterpret_cast<const uint2*>(src));
+                            else *reinterpret_cast<uint4*>(dst) = __ldg(reinterpret_cast<const uint4*>(src));
+                        }
                     }
                 }
             }
@@ -215,6 +229,33 @@ __device__ __forceinline__ void walk_tiles(const PairDesc& pd, const uint32_t* _
     }
 }
 
+// The walk of one pair by one warp (tile by tile), from its end cell to a border / stop cell.
+template <int TYPE, bool COHERENT>
+__device__ __forceinline__ void walk_pair_tiles(const PairDesc& pd, uint32_t p, const uint32_t* __restrict__ dirs,
+                                                uint32_t i, uint32_t j, uint32_t* tile, uint32_t* __restrict__ runs,
+                                                uint32_t* __restrict__ n_runs, uint32_t* __restrict__ cigar_len, int lane) {
+    const uint32_t klass = pd.klass & 0xffu;
+    const uint32_t Q = pd.Q, T = pd.T;
+    RunWriter rw{runs + pd.run_off, 0, 0, 3, 0, lane == 0};
+    if (TYPE == 2) {  // the pad is the tail of the text, so it is the first thing a backward walk meets
+        if (i == Q && j < T) rw.push(1, T - j);
+        else if (j == T && i < Q) rw.push(2, Q - i);
+    }
+    const uint32_t* base = dirs + pd.dir_off;
+    if (klass == kClassLong16) walk_tiles<TYPE, kClassLong16, COHERENT>(pd, base, i, j, tile, rw, lane);
+    else if (klass == kClassLong) walk_tiles<TYPE, kClassLong, COHERENT>(pd, base, i, j, tile, rw, lane);
+    else walk_tiles<TYPE, kClassGeneric, COHERENT>(pd, base, i, j, tile, rw, lane);
+    if (TYPE != 1) {   // the borders: row 0 points left ('I'), column 0 points up ('D') (reference :83-92)
+        if (i == 0 && j) rw.push(1, j);
+        else if (j == 0 && i) rw.push(2, i);
+    }
+    rw.flush();
+    if (lane == 0) {
+        n_runs[p] = rw.nr;
+        cigar_len[p] = rw.nr == 0 ? 2u : rw.bytes;  // empty path: "1\0"
+    }
+}
+
 template <int TYPE>
 __global__ void __launch_bounds__(128)
 walk_tile_kernel(const PairDesc* __restrict__ pairs, const uint32_t* __restrict__ work, uint32_t n_work,
@@ -227,28 +268,43 @@ walk_tile_kernel(const PairDesc* __restrict__ pairs, const uint32_t* __restrict_
     if (w >= n_work) return;
     const uint32_t p = work[w];
     const PairDesc pd = pairs[p];
-    const uint32_t klass = pd.klass & 0xffu;
-    if (klass == kClassShort) return;   // walk_kernel's
-    const uint32_t Q = pd.Q, T = pd.T;
-    uint32_t i = end_i[p], j = end_j[p];
-    RunWriter rw{runs + pd.run_off, 0, 0, 3, 0, lane == 0};
-    if (TYPE == 2) {  // the pad is the tail of the text, so it is the first thing a backward walk meets
-        if (i == Q && j < T) rw.push(1, T - j);
-        else if (j == T && i < Q) rw.push(2, Q - i);
-    }
-    uint32_t* tile = tiles[threadIdx.x >> 5];
-    const uint32_t* base = dirs + pd.dir_off;
-    if (klass == kClassLong16) walk_tiles<TYPE, kClassLong16>(pd, base, i, j, tile, rw, lane);
-    else if (klass == kClassLong) walk_tiles<TYPE, kClassLong>(pd, base, i, j, tile, rw, lane);
-    else walk_tiles<TYPE, kClassGeneric>(pd, base, i, j, tile, rw, lane);
-    if (TYPE != 1) {   // the borders: row 0 points left ('I'), column 0 points up ('D') (reference :83-92)
-        if (i == 0 && j) rw.push(1, j);
-        else if (j == 0 && i) rw.push(2, i);
-    }
-    rw.flush();
-    if (lane == 0) {
-        n_runs[p] = rw.nr;
-        cigar_len[p] = rw.nr == 0 ? 2u : rw.bytes;  // empty path: "1\0"
+    if ((pd.klass & 0xffu) == kClassShort) return;   // walk_kernel's
+    walk_pair_tiles<TYPE, false>(pd, p, dirs, end_i[p], end_j[p], tiles[threadIdx.x >> 5], runs, n_runs, cigar_len, lane);
+}
+
+// Persistent walkers for the wave that is still being filled: warps take pairs in work order (largest first, the
+// order the fill hands its stripes out in), wait for the pair's ready flag -- raised by the fill warp that finished
+// the pair's last stripe -- and walk it while the fill goes on with the other pairs. Pairs the 2-bit fill does not
+// own (flags != 0) are skipped; they are walked after their fallback fill.
+template <int TYPE>
+__global__ void __launch_bounds__(128)
+walk_tile_wait_kernel(const PairDesc* __restrict__ pairs, const uint32_t* __restrict__ work, uint32_t n_work,
+                      const uint8_t* __restrict__ flags, uint32_t* __restrict__ counter, const uint32_t* ready,
+                      uint32_t* __restrict__ stall_flag, const uint32_t* __restrict__ dirs, const uint32_t* end_i,
+                      const uint32_t* end_j, uint32_t* __restrict__ runs, uint32_t* __restrict__ n_runs,
+                      uint32_t* __restrict__ cigar_len) {
+    __shared__ __align__(16) uint32_t tiles[4][kWalkTileWords];
+    const int lane = threadIdx.x & 31;
+    for (;;) {
+        uint32_t w = 0;
+        if (lane == 0) w = atomicAdd(counter, 1u);
+        w = __shfl_sync(kFull, w, 0);
+        if (w >= n_work) break;
+        const uint32_t p = work[w];
+        if (flags[p]) continue;
+        const PairDesc pd = pairs[p];
+        uint32_t ok = 1;
+        if (lane == 0) {
+            uint32_t spins = 0;
+            while (ld_acquire_u32(ready + w) == 0u) {
+                __nanosleep(256);
+                if (++spins > (1u << 24)) { atomicExch(stall_flag, 1u); ok = 0; break; }   // never hang the device
+            }
+        }
+        ok = __shfl_sync(kFull, ok, 0);
+        if (!ok) break;
+        walk_pair_tiles<TYPE, true>(pd, p, dirs, __ldcg(end_i + p), __ldcg(end_j + p), tiles[threadIdx.x >> 5], runs, n_runs,
+                                    cigar_len, lane);
     }
 }
 

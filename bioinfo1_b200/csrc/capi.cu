@@ -111,8 +111,12 @@ struct HostBuf {  // pinned staging
 // Per-wave workspaces. Two slots: consecutive waves of a run alternate between them (and between two
 // streams), so the latency-bound traceback walk of wave k overlaps the ALU-bound fill of wave k+1.
 struct WaveSlot {
-    DevBuf dirs, bnd, bnd_short, progress, stripe_res, counter, fix_work;
+    DevBuf dirs, bnd, bnd_short, progress, stripe_res, counter, fix_work, pair_state;
     cudaEvent_t done = nullptr;
+    // concurrent walk of the wave that is being filled (long class): its own stream, fork / join events
+    cudaStream_t walk_stream = nullptr;
+    cudaEvent_t pre_event = nullptr, walk_event = nullptr;
+    bool walk_inflight = false;
 };
 
 struct b200_ctx {
@@ -129,6 +133,7 @@ struct b200_ctx {
     std::vector<TlMark> timeline;
     cudaEvent_t fork_event = nullptr;
     int64_t overlap_waves = 1;              // 0 = all waves on the caller's stream, one after the other
+    int64_t concurrent_walk = 1;            // 0 = a wave's pairs are walked after its fill kernel has finished
     DevBuf qpk, tpk, end_i, end_j, runs, n_runs, cigar_len, scan_tmp, flags, total;
     // staging for the host-buffer entry points
     DevBuf d_q, d_t, d_score, d_tb, d_cigar, d_cigar_off, d_seq, d_hash, d_pos, d_flag;
@@ -225,6 +230,26 @@ extern "C" int b200_ctx_create(int device, b200_ctx** out) {
     c->sm_count = prop.multiProcessorCount;
     CU(cudaSetDevice(device));
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    // Kernels only share an SM when they agree on its shared-memory carve-out: the long-pair fills use no shared
+    // memory, the tile walkers 16 KB, and with the default preferences a walker CTA did not become resident until
+    // the fill running on the SM was over (measured: the "concurrent" walkers finished 2.9 ms after the fill; launched
+    // first, they kept the fill out instead). Same explicit preference on all of them.
+    {
+        const int pct = 20;
+        cudaFuncSetAttribute(fill_long16_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        cudaFuncSetAttribute(fill_long16_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        cudaFuncSetAttribute(fill_long16_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        cudaFuncSetAttribute(locate_long16_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        cudaFuncSetAttribute(fill_long_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        cudaFuncSetAttribute(fill_long_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        cudaFuncSetAttribute(fill_long_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        cudaFuncSetAttribute(walk_tile_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        cudaFuncSetAttribute(walk_tile_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        cudaFuncSetAttribute(walk_tile_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        cudaFuncSetAttribute(walk_tile_wait_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        cudaFuncSetAttribute(walk_tile_wait_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        cudaGetLastError();
+    }
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess)
         c->dir_budget_bytes = std::max<int64_t>(1ll << 30, (int64_t)(free_b / 3));
@@ -251,8 +276,11 @@ extern "C" void b200_ctx_destroy(b200_ctx* c) {
     for (auto e : c->wave_done) cudaEventDestroy(e);
     if (c->fork_event) cudaEventDestroy(c->fork_event);
     for (WaveSlot& w : c->slot) {
-        for (DevBuf* b : {&w.dirs, &w.bnd, &w.bnd_short, &w.progress, &w.stripe_res, &w.counter, &w.fix_work}) b->release();
+        for (DevBuf* b : {&w.dirs, &w.bnd, &w.bnd_short, &w.progress, &w.stripe_res, &w.counter, &w.fix_work, &w.pair_state}) b->release();
         if (w.done) cudaEventDestroy(w.done);
+        if (w.walk_stream) cudaStreamDestroy(w.walk_stream);
+        if (w.pre_event) cudaEventDestroy(w.pre_event);
+        if (w.walk_event) cudaEventDestroy(w.walk_event);
     }
     for (DevBuf* b : {&c->qpk, &c->tpk, &c->end_i, &c->end_j, &c->runs, &c->n_runs,
                       &c->cigar_len, &c->scan_tmp, &c->flags, &c->total, &c->d_q, &c->d_t, &c->d_score, &c->d_tb,
@@ -269,6 +297,7 @@ extern "C" int b200_ctx_set_option(b200_ctx* c, const char* key, int64_t value) 
     else if (k == "force_generic") c->force_generic = value;
     else if (k == "long16") c->long16 = value;
     else if (k == "overlap_waves") c->overlap_waves = value;
+    else if (k == "concurrent_walk") c->concurrent_walk = value;
     else if (k == "chunk_pairs") c->chunk_pairs = value;
     else if (k == "profile") c->profile = value;
     else if (k == "reset_counters") {
@@ -794,15 +823,48 @@ static int launch_fill_long(b200_align_plan* p, const Wave& wv, const RunBufs& r
     const uint32_t* d_work = p->d_work.as<uint32_t>() + wv.first;
     if (p->long16) {
         const ShortConsts K16 = make_short_consts(p->sc, p->type);
+        // Global and semi-global waves with CIGARs: the walkers start with the fill and take each pair as soon as
+        // its last stripe is in (the traceback of the longest pairs no longer trails the whole wave).
+        WaveSlot& ws = *rb.ws;
+        const bool cw = c->concurrent_walk && !c->profile && p->want_cigar && p->type != 1 && rb.dirs != nullptr;
+        uint32_t *d_done = nullptr, *d_ready = nullptr;
+        if (cw) {
+            TRY(ws.pair_state.ensure(((size_t)wv.count + 8) * 8));
+            d_done = ws.pair_state.as<uint32_t>();
+            d_ready = d_done + wv.count + 4;
+            CU(cudaMemsetAsync(ws.pair_state.p, 0, ((size_t)wv.count + 8) * 8, rb.st));
+            CU(cudaMemsetAsync(ws.counter.as<uint32_t>() + 28, 0, 4, rb.st));
+            if (!ws.walk_stream) CU(cudaStreamCreateWithFlags(&ws.walk_stream, cudaStreamNonBlocking));
+            if (!ws.pre_event) CU(cudaEventCreateWithFlags(&ws.pre_event, cudaEventDisableTiming));
+            if (!ws.walk_event) CU(cudaEventCreateWithFlags(&ws.walk_event, cudaEventDisableTiming));
+        }
         prof_begin(c, rb.st, 0);
 #define LONG16K(TY)                                                                                                    \
+    if (cw) {   /* pairs without inner cells have nothing to wait for: result and ready flag now */                   \
+        finalize_long_kernel<TY><<<(unsigned)div_up64(wv.count, 128), 128, 0, rb.st>>>(p->d_pairs.as<PairDesc>(), d_work, \
+            wv.count, d_task_off, c->flags.as<uint8_t>(), ws.stripe_res.as<StripeResult>(), K16.init, rb.score,        \
+            c->end_i.as<uint32_t>(), c->end_j.as<uint32_t>(), 1, d_ready);                                             \
+        CU(cudaEventRecord(ws.pre_event, rb.st));                                                                      \
+        CU(cudaStreamWaitEvent(ws.walk_stream, ws.pre_event, 0));                                                      \
+    }                                                                                                                  \
     fill_long16_kernel<TY><<<n_blocks, 128, 0, rb.st>>>(c->qpk.as<uint32_t>(), c->tpk.as<uint32_t>(), p->d_pairs.as<PairDesc>(), \
-        d_work, wv.count, d_task_off, d_bnd_off, rb.ws->counter.as<uint32_t>(), c->flags.as<uint8_t>(), K16, rb.dirs,       \
-        rb.ws->bnd.as<int32_t>(), rb.ws->progress.as<uint32_t>(), rb.ws->stripe_res.as<StripeResult>(),                            \
-        rb.ws->counter.as<uint32_t>() + 24);                                                                               \
+        d_work, wv.count, d_task_off, d_bnd_off, rb.ws->counter.as<uint32_t>(), c->flags.as<uint8_t>(), K16, rb.dirs,  \
+        rb.ws->bnd.as<int32_t>(), rb.ws->progress.as<uint32_t>(), rb.ws->stripe_res.as<StripeResult>(),                \
+        rb.ws->counter.as<uint32_t>() + 24, d_done, d_ready, cw ? rb.score : nullptr,                                  \
+        cw ? c->end_i.as<uint32_t>() : nullptr, cw ? c->end_j.as<uint32_t>() : nullptr);                               \
+    if (cw) {                                                                                                          \
+        walk_tile_wait_kernel<TY><<<(unsigned)c->sm_count, 128, 0, ws.walk_stream>>>(p->d_pairs.as<PairDesc>(), d_work, \
+            wv.count, c->flags.as<uint8_t>(), ws.counter.as<uint32_t>() + 28, d_ready, ws.counter.as<uint32_t>() + 24, \
+            rb.dirs, c->end_i.as<uint32_t>(), c->end_j.as<uint32_t>(), c->runs.as<uint32_t>(), c->n_runs.as<uint32_t>(), \
+            c->cigar_len.as<uint32_t>());                                                                              \
+        CU(cudaEventRecord(ws.walk_event, ws.walk_stream));                                                            \
+        ws.walk_inflight = true;                                                                                       \
+        c->kernel_launches++;                                                                                          \
+    }                                                                                                                  \
+    if (!cw)                                                                                                           \
     finalize_long_kernel<TY><<<(unsigned)div_up64(wv.count, 128), 128, 0, rb.st>>>(p->d_pairs.as<PairDesc>(), d_work,  \
-        wv.count, d_task_off, c->flags.as<uint8_t>(), rb.ws->stripe_res.as<StripeResult>(), K16.init, rb.score,            \
-        c->end_i.as<uint32_t>(), c->end_j.as<uint32_t>())
+        wv.count, d_task_off, c->flags.as<uint8_t>(), rb.ws->stripe_res.as<StripeResult>(), K16.init, rb.score,        \
+        c->end_i.as<uint32_t>(), c->end_j.as<uint32_t>(), 0, nullptr)
         if (p->type == 0) { LONG16K(0); } else if (p->type == 2) { LONG16K(2); } else {
             LONG16K(1);
             locate_long16_kernel<<<(unsigned)div_up64((uint64_t)wv.count * 32, 128), 128, 0, rb.st>>>(
@@ -825,7 +887,7 @@ static int launch_fill_long(b200_align_plan* p, const Wave& wv, const RunBufs& r
         rb.ws->counter.as<uint32_t>() + 24);                                                                               \
     finalize_long_kernel<TY><<<(unsigned)div_up64(wv.count, 128), 128, 0, rb.st>>>(p->d_pairs.as<PairDesc>(), d_work,  \
         wv.count, d_task_off, c->flags.as<uint8_t>(), rb.ws->stripe_res.as<StripeResult>(), K.init, rb.score,              \
-        c->end_i.as<uint32_t>(), c->end_j.as<uint32_t>())
+        c->end_i.as<uint32_t>(), c->end_j.as<uint32_t>(), 0, nullptr)
     if (p->type == 0) { LONGK(0); } else if (p->type == 2) { LONGK(2); } else {
         LONGK(1);
         locate_long_kernel<<<(unsigned)div_up64((uint64_t)wv.count * 32, 128), 128, 0, rb.st>>>(
@@ -948,6 +1010,7 @@ static int plan_run_impl(b200_align_plan* p, const char* d_q_buf, const char* d_
         }
     }
 
+    if (!ho) tl_mark(c, st, "start");
     // A wave = classify (+ 2-bit pack) -> fill -> traceback walk, in order on its stream; when the host entry
     // point pipelines the upload, wave k first waits for the event that marks its bytes as resident.
     for (size_t k = 0; k < p->waves.size(); ++k) {
@@ -1019,7 +1082,14 @@ static int plan_run_impl(b200_align_plan* p, const char* d_q_buf, const char* d_
             TRY(launch_fill_generic(p, work, wv.count, rb));
         }
         tl_mark(c, wst, "fill" + std::to_string(k));
-        if (p->want_cigar) TRY(launch_walk(p, wv.klass, work, wv.count, rb));
+        if (ws.walk_inflight) {
+            // the wave's own pairs are being walked next to the fill; pairs that fell back to the generic kernel follow
+            // here, and the wave's stream waits for the walkers so that everything after it sees every pair walked
+            ws.walk_inflight = false;
+            if (!fix.empty()) TRY(launch_walk(p, kClassGeneric, ws.fix_work.as<uint32_t>(), (uint32_t)fix.size(), rb));
+            CU(cudaStreamWaitEvent(wst, ws.walk_event, 0));
+            tl_mark(c, wst, "cwalk" + std::to_string(k));
+        } else if (p->want_cigar) TRY(launch_walk(p, wv.klass, work, wv.count, rb));
         tl_mark(c, wst, "walk" + std::to_string(k));
         if (piped) {
             const uint32_t a = wv.first, b = wv.first + wv.count;
@@ -1108,6 +1178,7 @@ static int plan_run_impl(b200_align_plan* p, const char* d_q_buf, const char* d_
         if (stalled[0] | stalled[1]) return fail(B200_E_CUDA, "long-pair kernel: a stripe gave up waiting for its predecessor");
     }
     prof_collect(c, st);
+    if (!ho) tl_dump(c);
     return B200_OK;
 }
 
