@@ -140,10 +140,11 @@ __device__ __forceinline__ int half_hi(uint32_t v) { return (int)(int16_t)(v >> 
 template <int HI> __device__ __forceinline__ int half_of(uint32_t v) { return HI ? half_hi(v) : half_lo(v); }
 __device__ __forceinline__ uint32_t pack16(int lo, int hi) { return ((uint32_t)hi << 16) | ((uint32_t)lo & 0xffffu); }
 
-__device__ __forceinline__ uint32_t pick_any(const uint32_t (&Y)[32], uint32_t r) {   // Y[r] for a lane-varying r
+template <int N>
+__device__ __forceinline__ uint32_t pick_any(const uint32_t (&Y)[N], uint32_t r) {   // Y[r] for a lane-varying r
     uint32_t v = Y[0];
 #pragma unroll
-    for (int k = 1; k < 32; ++k) if (r == (uint32_t)k) v = Y[k];
+    for (int k = 1; k < N; ++k) if (r == (uint32_t)k) v = Y[k];
     return v;
 }
 
@@ -158,6 +159,21 @@ __device__ __forceinline__ uint32_t max_tree16(const uint32_t (&Y)[32]) {
     for (int k = 0; k < 4; ++k) n[k] = __vimax3_s16x2(m[3 * k], m[3 * k + 1], m[3 * k + 2]);
     return __vmaxs2(__vimax3_s16x2(n[0], n[1], n[2]), n[3]);
 }
+// the same for a shorter register block (N = 8, 16, 24): the trimmed last block of align_fill_short.cuh
+template <int N>
+__device__ __forceinline__ uint32_t max_tree16(const uint32_t (&Y)[N]) {
+    static_assert(N == 8 || N == 16 || N == 24, "register block heights are multiples of 8");
+    uint32_t m[N / 2];
+#pragma unroll
+    for (int k = 0; k < N / 4; ++k) {      // 4 registers -> 2 (one three-way, one passed on)
+        m[2 * k] = __vimax3_s16x2(Y[4 * k], Y[4 * k + 1], Y[4 * k + 2]);
+        m[2 * k + 1] = Y[4 * k + 3];
+    }
+    uint32_t v = m[0];
+#pragma unroll
+    for (int k = 1; k + 1 < N / 2; k += 2) v = __vimax3_s16x2(v, m[k], m[k + 1]);
+    return __vmaxs2(v, m[N / 2 - 1]);
+}
 
 // Direction word layout written by this kernel (read back by walk_kernel, klass kClassShort):
 //   uint4 at dirs[dir_off + ((block * Tg + (j-1)) * 32 + lane) * 4 .. +3]; word k covers rows
@@ -170,6 +186,180 @@ __device__ __forceinline__ uint32_t max_tree16(const uint32_t (&Y)[32]) {
 //     left      Y(i,  j-1)                    -> 4H' + 1
 //     up        Y(i-1,j)   + 4*gap - 1        -> 4H' + 0
 // (H' = H - gap*j) and one signed max gives maximum, tie order and direction tag at once.
+// The state one thread carries through the row blocks of its two pairs; block<RB>() sweeps one block of RB
+// (8, 16, 24 or 32) register rows over every column. Blocks are 32 rows apart whatever RB is: only the LAST
+// block of a group is trimmed (150-row pairs: 4 x 32 + 24 rows instead of 5 x 32), its unused direction words
+// are stored as zeros and never read (the walker only visits rows <= Q).
+template <int TYPE>
+struct ShortSweep {
+    // the thread's two pairs
+    uint32_t QA, TA, QB, TB;
+    const uint32_t *qwA, *twA, *qwB, *twB;
+    bool liveA, liveB;
+    uint32_t Tm, n_blocks;
+    // per group
+    uint32_t* dirs_g;      // dirs + dir_off + lane * 4, or nullptr
+    uint32_t Tg;
+    uint32_t* my_bnd;
+    // results
+    int resA, resB;
+    int colbestA, colbestB, rowbestA, rowbestB;      // semiGlobal candidates (last column / row Q)
+    uint32_t coliA, coliB, rowjA, rowjB;
+    int bvA, bvB;                                    // local: running first maximum in row-major order
+    uint32_t biA, bjA, biB, bjB;
+
+    __device__ __forceinline__ void reset() {
+        resA = 0; resB = 0;
+        // last column: smallest i first, H(0,T) = 0 leads; last row: smallest j, H(Q,0) = 0 leads
+        colbestA = 0; colbestB = 0; rowbestA = 0; rowbestB = 0;
+        coliA = 0; coliB = 0; rowjA = 0; rowjB = 0;
+        bvA = INT_MIN; bvB = INT_MIN;
+        biA = 0; bjA = 0; biB = 0; bjB = 0;
+    }
+
+    template <int RB>
+    __device__ __forceinline__ void block(const ShortConsts& K, const uint32_t b) {
+        constexpr int R = kShortRows;   // block stride in rows
+        const uint32_t MASK = K.mask, ONE = K.one, FOUR = K.four;
+        const int frame = 4 * (K.init - K.gap);   // top border row in the moving frame: Y(0,j) = frame*j + 1
+        const uint32_t i0 = b * R;   // rows i0+1 .. i0+RB
+        // per-row PRMT selectors: byte0 = tabA[qA], byte1 = its sign, byte2 = tabB[qB], byte3 = sign
+        uint32_t sel[RB], Y[RB];
+        {
+            const uint32_t qa0 = qwA[(i0 >> 4)], qa1 = RB > 16 ? qwA[(i0 >> 4) + 1] : 0u;
+            const uint32_t qb0 = qwB[(i0 >> 4)], qb1 = RB > 16 ? qwB[(i0 >> 4) + 1] : 0u;
+#pragma unroll
+            for (int r = 0; r < RB; ++r) {
+                const uint32_t ca = ((r < 16 ? qa0 : qa1) >> (2 * (r & 15))) & 3u;
+                const uint32_t cb = ((r < 16 ? qb0 : qb1) >> (2 * (r & 15))) & 3u;
+                sel[r] = ca | ((8u + ca) << 4) | ((4u + cb) << 8) | ((12u + cb) << 12);
+                Y[r] = dup16(4 * (int)((i0 + 1 + r) * (uint32_t)K.init) + 1);   // column 0, frame 0
+            }
+        }
+        uint32_t top_prev = dup16(4 * (int)(i0 * (uint32_t)K.init) + 1);       // Y(i0, 0)
+        // software prefetch: the boundary row and the packed target words are fetched one step early
+        // (two columns early: the compiler sinks the load to the end of the body, so a distance of one
+        // column would leave only a few instructions between issue and use)
+        uint32_t top_next = (b == 0) ? dup16(frame * 1 + 1) : my_bnd[(size_t)1 * kWarp];
+        uint32_t top_next2 = (b == 0) ? dup16(frame * 2 + 1) : my_bnd[(size_t)2 * kWarp];
+        uint32_t tA_next = twA[0], tB_next = twB[0], tA = 0, tB = 0;
+        uint32_t* dcol = dirs_g ? dirs_g + (uint64_t)b * Tg * 128 : nullptr;
+
+        // hoisted end-cell test: the column at which this block holds cell (Q,T) of either pair
+        const uint32_t jhitA = (TYPE == 0 && liveA && (QA - 1) / R == b) ? TA : 0u;
+        const uint32_t jhitB = (TYPE == 0 && liveB && (QB - 1) / R == b) ? TB : 0u;
+        // rows of each pair inside this block, and whether the block holds the pair's row Q
+        const uint32_t nvA = (liveA && QA > i0) ? min((uint32_t)RB, QA - i0) : 0u;
+        const uint32_t nvB = (liveB && QB > i0) ? min((uint32_t)RB, QB - i0) : 0u;
+        const bool lastA = nvA && QA <= i0 + R, lastB = nvB && QB <= i0 + R;
+        const uint32_t rqA = lastA ? QA - 1 - i0 : 0u, rqB = lastB ? QB - 1 - i0 : 0u;
+        const bool full_rows = nvA == (uint32_t)RB && nvB == (uint32_t)RB;
+        const uint32_t Tmin = min(TA, TB);
+#pragma unroll 2
+        for (uint32_t j = 1; j <= Tm; ++j) {
+            if (((j - 1) & 15u) == 0) {
+                tA = tA_next; tB = tB_next;
+                tA_next = twA[((j - 1) >> 4) + 1]; tB_next = twB[((j - 1) >> 4) + 1];
+            }
+            const uint32_t cA = tA & 3u, cB = tB & 3u;
+            tA >>= 2; tB >>= 2;
+            // per-column byte tables: entry c = S'(c, target) (match where c == target code)
+            const uint32_t tabA = K.tab_mis ^ (K.tab_diff << (8 * cA));
+            const uint32_t tabB = K.tab_mis ^ (K.tab_diff << (8 * cB));
+            const uint32_t top = top_next;
+            top_next = top_next2;
+            if (j + 2 <= Tm) top_next2 = (b == 0) ? dup16(frame * (int)(j + 2) + 1) : my_bnd[(size_t)(j + 2) * kWarp];
+            uint32_t up = top;        // Y of the row above, this column's frame
+            uint32_t dg = top_prev;   // Y(i0, j-1), previous column's frame
+            top_prev = top;
+            uint32_t accZ = 0, accY = 0, w[4] = {0u, 0u, 0u, 0u};
+            const uint32_t clampv = dup16(3 - 4 * K.gap * (int)j);   // local: H = 0 with the stop tag, this column's frame
+#pragma unroll
+            for (int r = 0; r < RB; ++r) {
+                const uint32_t S = prmt(tabA, tabB, sel[r]);
+                const uint32_t m1 = __viaddmax_s16x2(dg, S, Y[r]);
+                uint32_t Z = __viaddmax_s16x2(up, K.cu, m1);
+                if (TYPE == 1) Z = __vmaxs2(Z, clampv);   // clamp at 0 (team_alignment.cpp:185), tag 3 = stop
+                dg = Y[r];
+                Y[r] = lop3_and_or(Z, MASK, ONE);
+                up = Y[r];
+                // direction tags: two multiply-add chains on the fma pipe; (Z - Y) = tag - 1 per half
+                accZ = accZ * FOUR + Z;
+                accY = accY * FOUR + Y[r];
+                if ((r & 7) == 7) { w[r >> 3] = accZ - accY + 0x55555555u; accZ = 0; accY = 0; }
+            }
+            if (b + 1 < n_blocks) my_bnd[(size_t)j * kWarp] = up;   // (RB = 32 whenever a block follows)
+            // streaming store: the direction matrix is written once and must not evict the boundary rows from L2
+            if (dcol) __stcs(reinterpret_cast<uint4*>(dcol + (uint64_t)(j - 1) * 128), make_uint4(w[0], w[1], w[2], w[3]));
+            // end-cell capture (global): the cell (Q, T) of either pair
+            if (TYPE == 0) {
+                const bool hitA = j == jhitA, hitB = j == jhitB;
+                if (hitA || hitB) {
+                    const uint32_t rA = (QA - 1) % R, rB = (QB - 1) % R;
+                    const uint32_t vA = pick_any(Y, rA), vB = pick_any(Y, rB);
+                    if (hitA) resA = (half_lo(vA) - 1 + 4 * K.gap * (int)j) >> 2;
+                    if (hitB) resB = (half_hi(vB) - 1 + 4 * K.gap * (int)j) >> 2;
+                }
+            }
+            const int back = 4 * K.gap * (int)j - 1;   // H = (Y + back) >> 2 in this column's frame
+            if (TYPE == 2) {
+                if ((j == TA && nvA) || (j == TB && nvB)) {   // a pair's last column: rows ascend, strict '>' keeps the smallest i
+#pragma unroll
+                    for (int r = 0; r < RB; ++r) {
+                        const int hA = (half_lo(Y[r]) + back) >> 2, hB = (half_hi(Y[r]) + back) >> 2;
+                        if (j == TA && (uint32_t)r < nvA && hA > colbestA) { colbestA = hA; coliA = i0 + 1 + r; }
+                        if (j == TB && (uint32_t)r < nvB && hB > colbestB) { colbestB = hB; coliB = i0 + 1 + r; }
+                    }
+                }
+                if (lastA || lastB) {   // row Q of a pair, every column: strict '>' keeps the smallest j
+                    const int hA = (half_lo(pick_any(Y, rqA)) + back) >> 2, hB = (half_hi(pick_any(Y, rqB)) + back) >> 2;
+                    if (lastA && j <= TA && hA > rowbestA) { rowbestA = hA; rowjA = j; }
+                    if (lastB && j <= TB && hB > rowbestB) { rowbestB = hB; rowjB = j; }
+                }
+            }
+            if (TYPE == 1) {
+                int mA, mB;   // column maxima over the valid rows, as register halves
+                if (full_rows && j <= Tmin) {
+                    const uint32_t cm = max_tree16(Y);
+                    mA = half_lo(cm); mB = half_hi(cm);
+                } else {
+                    mA = INT_MIN; mB = INT_MIN;
+#pragma unroll
+                    for (int r = 0; r < RB; ++r) {
+                        if ((uint32_t)r < nvA) mA = max(mA, half_lo(Y[r]));
+                        if ((uint32_t)r < nvB) mB = max(mB, half_hi(Y[r]));
+                    }
+                }
+                const int hA = (nvA && j <= TA) ? (mA + back) >> 2 : INT_MIN;
+                const int hB = (nvB && j <= TB) ? (mB + back) >> 2 : INT_MIN;
+                // a new maximum, or a tie that may sit on a smaller row of this block than the current holder
+                if (hA > bvA || (hA == bvA && biA > i0 + 1)) {
+                    uint32_t rr = RB;
+#pragma unroll
+                    for (int r = RB - 1; r >= 0; --r) if ((uint32_t)r < nvA && half_lo(Y[r]) == mA) rr = r;
+                    if (hA > bvA || i0 + 1 + rr < biA) { bvA = hA; biA = i0 + 1 + rr; bjA = j; }
+                }
+                if (hB > bvB || (hB == bvB && biB > i0 + 1)) {
+                    uint32_t rr = RB;
+#pragma unroll
+                    for (int r = RB - 1; r >= 0; --r) if ((uint32_t)r < nvB && half_hi(Y[r]) == mB) rr = r;
+                    if (hB > bvB || i0 + 1 + rr < biB) { bvB = hB; biB = i0 + 1 + rr; bjB = j; }
+                }
+            }
+        }
+    }
+};
+
+// The trimmed variants are real calls: inlined next to the 32-row loop they cost that loop its register
+// allocation (measured: -8 % on every block); a call per group is free.
+template <int TYPE, int RB>
+__device__ __noinline__ void short_block_trimmed(ShortSweep<TYPE>* sw, const ShortConsts* K, uint32_t b) {
+    ShortSweep<TYPE> s = *sw;   // by value: nothing the loop reads may alias its stores
+    const ShortConsts k = *K;
+    s.template block<RB>(k, b);
+    *sw = s;
+}
+
 template <int TYPE>
 __global__ void __launch_bounds__(kShortThreads, 7)
 fill_short_kernel(const uint32_t* __restrict__ qpk, const uint32_t* __restrict__ tpk,
@@ -181,10 +371,9 @@ fill_short_kernel(const uint32_t* __restrict__ qpk, const uint32_t* __restrict__
     constexpr int R = kShortRows;
     const int lane = threadIdx.x & 31;
     const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    uint32_t* my_bnd = bnd + (size_t)warp_global * bnd_cols * kWarp + lane;   // [col][lane]
     const uint32_t n_groups = (n_work + 63) / 64;
-    const uint32_t MASK = K.mask, ONE = K.one, FOUR = K.four;
-    const int frame = 4 * (K.init - K.gap);   // top border row in the moving frame: Y(0,j) = frame*j + 1
+    ShortSweep<TYPE> sw;
+    sw.my_bnd = bnd + (size_t)warp_global * bnd_cols * kWarp + lane;   // [col][lane]
 
     for (;;) {
         uint32_t g = 0;
@@ -195,187 +384,66 @@ fill_short_kernel(const uint32_t* __restrict__ qpk, const uint32_t* __restrict__
         // my two pairs
         const uint32_t wa = g * 64 + 2 * lane, wb = wa + 1;
         uint32_t pA = 0xffffffffu, pB = 0xffffffffu;
-        uint32_t QA = 0, TA = 0, QB = 0, TB = 0;
-        const uint32_t *qwA = qpk, *twA = tpk, *qwB = qpk, *twB = tpk;
-        const uint64_t dir_off = groups[g].dir_off;
-        const uint32_t Tg = groups[g].cols;
+        sw.QA = 0; sw.TA = 0; sw.QB = 0; sw.TB = 0;
+        sw.qwA = qpk; sw.twA = tpk; sw.qwB = qpk; sw.twB = tpk;
+        sw.Tg = groups[g].cols;
+        sw.dirs_g = dirs ? dirs + groups[g].dir_off + (uint64_t)lane * 4 : nullptr;
         if (wa < n_work) {
             pA = work[wa];
             const PairDesc d = pairs[pA];
-            if (flags[pA] == 0) { QA = d.Q; TA = d.T; qwA = qpk + d.qpk_off; twA = tpk + d.tpk_off; }
+            if (flags[pA] == 0) { sw.QA = d.Q; sw.TA = d.T; sw.qwA = qpk + d.qpk_off; sw.twA = tpk + d.tpk_off; }
             else pA = 0xffffffffu;   // not pure ACGT: the generic kernel owns it
         }
         if (wb < n_work) {
             pB = work[wb];
             const PairDesc d = pairs[pB];
-            if (flags[pB] == 0) { QB = d.Q; TB = d.T; qwB = qpk + d.qpk_off; twB = tpk + d.tpk_off; }
+            if (flags[pB] == 0) { sw.QB = d.Q; sw.TB = d.T; sw.qwB = qpk + d.qpk_off; sw.twB = tpk + d.tpk_off; }
             else pB = 0xffffffffu;
         }
+        const uint32_t QA = sw.QA, TA = sw.TA, QB = sw.QB, TB = sw.TB;
         const bool liveA = QA && TA, liveB = QB && TB;   // has inner cells
-        const uint32_t Qm = max(liveA ? QA : 0u, liveB ? QB : 0u), Tm = max(liveA ? TA : 0u, liveB ? TB : 0u);
-        const uint32_t n_blocks = (Qm + R - 1) / R;
-        int resA = 0, resB = 0;
-        // semiGlobal candidates: last column (smallest i first, H(0,T) = 0 leads), last row (smallest j, H(Q,0) = 0 leads)
-        int colbestA = 0, colbestB = 0, rowbestA = 0, rowbestB = 0;
-        uint32_t coliA = 0, coliB = 0, rowjA = 0, rowjB = 0;
-        // local: running first maximum in row-major order
-        int bvA = INT_MIN, bvB = INT_MIN;
-        uint32_t biA = 0, bjA = 0, biB = 0, bjB = 0;
+        sw.liveA = liveA; sw.liveB = liveB;
+        const uint32_t Qm = max(liveA ? QA : 0u, liveB ? QB : 0u);
+        sw.Tm = max(liveA ? TA : 0u, liveB ? TB : 0u);
+        sw.n_blocks = (Qm + R - 1) / R;
+        sw.reset();
+        // The height of a block is a warp-wide decision (lanes must not diverge over the variants): full blocks
+        // everywhere except the last block of the group's longest query, which is trimmed to a multiple of 8 rows.
+        const uint32_t Qg = __reduce_max_sync(kFull, Qm);
+        const uint32_t nbg = (Qg + R - 1) / R;
+        const uint32_t last_rows = (Qg - (nbg ? nbg - 1 : 0u) * R + 7u) & ~7u;   // 8 .. 32 (0 when the group is empty)
 
-        for (uint32_t b = 0; b < n_blocks; ++b) {
-            const uint32_t i0 = b * R;   // rows i0+1 .. i0+R
-            // per-row PRMT selectors: byte0 = tabA[qA], byte1 = its sign, byte2 = tabB[qB], byte3 = sign
-            uint32_t sel[R], Y[R];
-            {
-                const uint32_t qa0 = qwA[(i0 >> 4)], qa1 = qwA[(i0 >> 4) + 1];
-                const uint32_t qb0 = qwB[(i0 >> 4)], qb1 = qwB[(i0 >> 4) + 1];
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    const uint32_t ca = ((r < 16 ? qa0 : qa1) >> (2 * (r & 15))) & 3u;
-                    const uint32_t cb = ((r < 16 ? qb0 : qb1) >> (2 * (r & 15))) & 3u;
-                    sel[r] = ca | ((8u + ca) << 4) | ((4u + cb) << 8) | ((12u + cb) << 12);
-                    Y[r] = dup16(4 * (int)((i0 + 1 + r) * (uint32_t)K.init) + 1);   // column 0, frame 0
-                }
-            }
-            uint32_t top_prev = dup16(4 * (int)(i0 * (uint32_t)K.init) + 1);       // Y(i0, 0)
-            // software prefetch: the boundary row and the packed target words are fetched one step early
-            // (two columns early: the compiler sinks the load to the end of the body, so a distance of one
-            // column would leave only a few instructions between issue and use)
-            uint32_t top_next = (b == 0) ? dup16(frame * 1 + 1) : my_bnd[(size_t)1 * kWarp];
-            uint32_t top_next2 = (b == 0) ? dup16(frame * 2 + 1) : my_bnd[(size_t)2 * kWarp];
-            uint32_t tA_next = twA[0], tB_next = twB[0], tA = 0, tB = 0;
-            uint32_t* dcol = dirs ? dirs + dir_off + ((uint64_t)b * Tg * 32 + lane) * 4 : nullptr;
-
-            // hoisted end-cell test: the column at which this block holds cell (Q,T) of either pair
-            const uint32_t jhitA = (TYPE == 0 && liveA && (QA - 1) / R == b) ? TA : 0u;
-            const uint32_t jhitB = (TYPE == 0 && liveB && (QB - 1) / R == b) ? TB : 0u;
-            // rows of each pair inside this block, and whether the block holds the pair's row Q
-            const uint32_t nvA = (liveA && QA > i0) ? min((uint32_t)R, QA - i0) : 0u;
-            const uint32_t nvB = (liveB && QB > i0) ? min((uint32_t)R, QB - i0) : 0u;
-            const bool lastA = nvA && QA <= i0 + R, lastB = nvB && QB <= i0 + R;
-            const uint32_t rqA = lastA ? QA - 1 - i0 : 0u, rqB = lastB ? QB - 1 - i0 : 0u;
-            const bool full_rows = nvA == (uint32_t)R && nvB == (uint32_t)R;
-            const uint32_t Tmin = min(TA, TB);
-#pragma unroll 2
-            for (uint32_t j = 1; j <= Tm; ++j) {
-                if (((j - 1) & 15u) == 0) {
-                    tA = tA_next; tB = tB_next;
-                    tA_next = twA[((j - 1) >> 4) + 1]; tB_next = twB[((j - 1) >> 4) + 1];
-                }
-                const uint32_t cA = tA & 3u, cB = tB & 3u;
-                tA >>= 2; tB >>= 2;
-                // per-column byte tables: entry c = S'(c, target) (match where c == target code)
-                const uint32_t tabA = K.tab_mis ^ (K.tab_diff << (8 * cA));
-                const uint32_t tabB = K.tab_mis ^ (K.tab_diff << (8 * cB));
-                const uint32_t top = top_next;
-                top_next = top_next2;
-                if (j + 2 <= Tm) top_next2 = (b == 0) ? dup16(frame * (int)(j + 2) + 1) : my_bnd[(size_t)(j + 2) * kWarp];
-                uint32_t up = top;        // Y of the row above, this column's frame
-                uint32_t dg = top_prev;   // Y(i0, j-1), previous column's frame
-                top_prev = top;
-                uint32_t accZ = 0, accY = 0, w[4];
-                const uint32_t clampv = dup16(3 - 4 * K.gap * (int)j);   // local: H = 0 with the stop tag, this column's frame
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    const uint32_t S = prmt(tabA, tabB, sel[r]);
-                    const uint32_t m1 = __viaddmax_s16x2(dg, S, Y[r]);
-                    uint32_t Z = __viaddmax_s16x2(up, K.cu, m1);
-                    if (TYPE == 1) Z = __vmaxs2(Z, clampv);   // clamp at 0 (team_alignment.cpp:185), tag 3 = stop
-                    dg = Y[r];
-                    Y[r] = lop3_and_or(Z, MASK, ONE);
-                    up = Y[r];
-                    // direction tags: two multiply-add chains on the fma pipe; (Z - Y) = tag - 1 per half
-                    accZ = accZ * FOUR + Z;
-                    accY = accY * FOUR + Y[r];
-                    if ((r & 7) == 7) { w[r >> 3] = accZ - accY + 0x55555555u; accZ = 0; accY = 0; }
-                }
-                if (b + 1 < n_blocks) my_bnd[(size_t)j * kWarp] = up;
-                // streaming store: the direction matrix is written once and must not evict the boundary rows from L2
-                if (dcol) __stcs(reinterpret_cast<uint4*>(dcol + (uint64_t)(j - 1) * 128), make_uint4(w[0], w[1], w[2], w[3]));
-                // end-cell capture (global): the cell (Q, T) of either pair
-                if (TYPE == 0) {
-                    const bool hitA = j == jhitA, hitB = j == jhitB;
-                    if (hitA || hitB) {
-                        const uint32_t rA = (QA - 1) % R, rB = (QB - 1) % R;
-                        uint32_t vA = Y[0], vB = Y[0];
-#pragma unroll
-                        for (int r = 1; r < R; ++r) { if ((uint32_t)r == rA) vA = Y[r]; if ((uint32_t)r == rB) vB = Y[r]; }
-                        if (hitA) resA = (half_lo(vA) - 1 + 4 * K.gap * (int)j) >> 2;
-                        if (hitB) resB = (half_hi(vB) - 1 + 4 * K.gap * (int)j) >> 2;
-                    }
-                }
-                const int back = 4 * K.gap * (int)j - 1;   // H = (Y + back) >> 2 in this column's frame
-                if (TYPE == 2) {
-                    if ((j == TA && nvA) || (j == TB && nvB)) {   // a pair's last column: rows ascend, strict '>' keeps the smallest i
-#pragma unroll
-                        for (int r = 0; r < R; ++r) {
-                            const int hA = (half_lo(Y[r]) + back) >> 2, hB = (half_hi(Y[r]) + back) >> 2;
-                            if (j == TA && (uint32_t)r < nvA && hA > colbestA) { colbestA = hA; coliA = i0 + 1 + r; }
-                            if (j == TB && (uint32_t)r < nvB && hB > colbestB) { colbestB = hB; coliB = i0 + 1 + r; }
-                        }
-                    }
-                    if (lastA || lastB) {   // row Q of a pair, every column: strict '>' keeps the smallest j
-                        const int hA = (half_lo(pick_any(Y, rqA)) + back) >> 2, hB = (half_hi(pick_any(Y, rqB)) + back) >> 2;
-                        if (lastA && j <= TA && hA > rowbestA) { rowbestA = hA; rowjA = j; }
-                        if (lastB && j <= TB && hB > rowbestB) { rowbestB = hB; rowjB = j; }
-                    }
-                }
-                if (TYPE == 1) {
-                    int mA, mB;   // column maxima over the valid rows, as register halves
-                    if (full_rows && j <= Tmin) {
-                        const uint32_t cm = max_tree16(Y);
-                        mA = half_lo(cm); mB = half_hi(cm);
-                    } else {
-                        mA = INT_MIN; mB = INT_MIN;
-#pragma unroll
-                        for (int r = 0; r < R; ++r) {
-                            if ((uint32_t)r < nvA) mA = max(mA, half_lo(Y[r]));
-                            if ((uint32_t)r < nvB) mB = max(mB, half_hi(Y[r]));
-                        }
-                    }
-                    const int hA = (nvA && j <= TA) ? (mA + back) >> 2 : INT_MIN;
-                    const int hB = (nvB && j <= TB) ? (mB + back) >> 2 : INT_MIN;
-                    // a new maximum, or a tie that may sit on a smaller row of this block than the current holder
-                    if (hA > bvA || (hA == bvA && biA > i0 + 1)) {
-                        uint32_t rr = R;
-#pragma unroll
-                        for (int r = R - 1; r >= 0; --r) if ((uint32_t)r < nvA && half_lo(Y[r]) == mA) rr = r;
-                        if (hA > bvA || i0 + 1 + rr < biA) { bvA = hA; biA = i0 + 1 + rr; bjA = j; }
-                    }
-                    if (hB > bvB || (hB == bvB && biB > i0 + 1)) {
-                        uint32_t rr = R;
-#pragma unroll
-                        for (int r = R - 1; r >= 0; --r) if ((uint32_t)r < nvB && half_hi(Y[r]) == mB) rr = r;
-                        if (hB > bvB || i0 + 1 + rr < biB) { bvB = hB; biB = i0 + 1 + rr; bjB = j; }
-                    }
-                }
-            }
+        for (uint32_t b = 0; b < sw.n_blocks; ++b) {
+            if (b + 1 < nbg || last_rows == 32u) sw.template block<32>(K, b);
+            else if (last_rows == 24u) short_block_trimmed<TYPE, 24>(&sw, &K, b);
+            else if (last_rows == 16u) short_block_trimmed<TYPE, 16>(&sw, &K, b);
+            else short_block_trimmed<TYPE, 8>(&sw, &K, b);
         }
         if (TYPE == 0) {
             if (pA != 0xffffffffu) {
-                score[pA] = liveA ? resA : (int)((QA + TA) * (uint32_t)K.init);
+                score[pA] = liveA ? sw.resA : (int)((QA + TA) * (uint32_t)K.init);
                 end_i[pA] = QA; end_j[pA] = TA;
             }
             if (pB != 0xffffffffu) {
-                score[pB] = liveB ? resB : (int)((QB + TB) * (uint32_t)K.init);
+                score[pB] = liveB ? sw.resB : (int)((QB + TB) * (uint32_t)K.init);
                 end_i[pB] = QB; end_j[pB] = TB;
             }
         }
         if (TYPE == 2) {   // last column wins ties, the last row only if strictly greater (team_alignment.cpp:265-278)
             if (pA != 0xffffffffu) {
                 if (!liveA) { score[pA] = 0; end_i[pA] = 0; end_j[pA] = TA; }
-                else if (rowbestA > colbestA) { score[pA] = rowbestA; end_i[pA] = QA; end_j[pA] = rowjA; }
-                else { score[pA] = colbestA; end_i[pA] = coliA; end_j[pA] = TA; }
+                else if (sw.rowbestA > sw.colbestA) { score[pA] = sw.rowbestA; end_i[pA] = QA; end_j[pA] = sw.rowjA; }
+                else { score[pA] = sw.colbestA; end_i[pA] = sw.coliA; end_j[pA] = TA; }
             }
             if (pB != 0xffffffffu) {
                 if (!liveB) { score[pB] = 0; end_i[pB] = 0; end_j[pB] = TB; }
-                else if (rowbestB > colbestB) { score[pB] = rowbestB; end_i[pB] = QB; end_j[pB] = rowjB; }
-                else { score[pB] = colbestB; end_i[pB] = coliB; end_j[pB] = TB; }
+                else if (sw.rowbestB > sw.colbestB) { score[pB] = sw.rowbestB; end_i[pB] = QB; end_j[pB] = sw.rowjB; }
+                else { score[pB] = sw.colbestB; end_i[pB] = sw.coliB; end_j[pB] = TB; }
             }
         }
         if (TYPE == 1) {
-            if (pA != 0xffffffffu) { score[pA] = liveA ? bvA : 0; end_i[pA] = liveA ? biA : 0u; end_j[pA] = liveA ? bjA : 0u; }
-            if (pB != 0xffffffffu) { score[pB] = liveB ? bvB : 0; end_i[pB] = liveB ? biB : 0u; end_j[pB] = liveB ? bjB : 0u; }
+            if (pA != 0xffffffffu) { score[pA] = liveA ? sw.bvA : 0; end_i[pA] = liveA ? sw.biA : 0u; end_j[pA] = liveA ? sw.bjA : 0u; }
+            if (pB != 0xffffffffu) { score[pB] = liveB ? sw.bvB : 0; end_i[pB] = liveB ? sw.biB : 0u; end_j[pB] = liveB ? sw.bjB : 0u; }
         }
     }
 }
