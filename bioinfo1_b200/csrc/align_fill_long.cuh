@@ -58,6 +58,9 @@ struct StripeResult {      // per stripe, reduced per pair by finalize_long_kern
     int rowbest; uint32_t rowj;     // semi: best of row Q (last stripe only), smallest j
     int final_h; uint32_t pad;      // global: H(Q,T) (last stripe only)
 };
+// local: colbest = the stripe's maximum. fill_long_kernel leaves the cell to locate_long_kernel; fill_long16_kernel
+// finds it during the fill and says so in `pad`, with the cell in (coli, rowj).
+constexpr uint32_t kStripeLocated = 0x80000000u;
 
 constexpr int kLongChunk = 64;     // columns between progress publications / polls
 
@@ -283,6 +286,10 @@ __device__ __forceinline__ void finalize_pair(uint32_t p, uint32_t Q, uint32_t T
         score[p] = M;
         // M == 0: the reference's strict '>' scan keeps the very first cell (team_alignment.cpp:186-192)
         if (M <= 0) { end_i[p] = 1; end_j[p] = 1; }
+        else if ((uint32_t)__ldcg(r2 + 3 * (t0 + sfirst) + 2).y & kStripeLocated) {   // the first stripe with the maximum knows its first cell
+            end_i[p] = (uint32_t)__ldcg(r2 + 3 * (t0 + sfirst)).y;
+            end_j[p] = (uint32_t)__ldcg(r2 + 3 * (t0 + sfirst) + 1).y;
+        }
         else { end_i[p] = 0x80000000u | sfirst; end_j[p] = 0; }   // to be resolved by the locate kernel
         return;
     }

@@ -55,10 +55,28 @@ __device__ __forceinline__ uint32_t pick_uniform(const uint32_t (&Y)[32], uint32
 }
 #undef B200_PICK4
 
-// One stripe sweep. LOCATE = false: the fill (directions, boundary row, progress, end-cell candidates).
-// LOCATE = true: local alignments' second pass over the first stripe that attains the maximum M; no
-// outputs except the first cell in row-major order whose score equals M (team_alignment.cpp:186-192).
-template <int TYPE, bool LOCATE>
+// For both halves at once: 31 - (the smallest r whose half of Y[r] equals that half of `cm`, the packed maximum of
+// the 32 registers). Y[r] - cm is 0 where equal and at most -4 elsewhere (values carry the same tag, and a block's
+// values lie within the 16-bit window of each other, so the packed subtraction cannot wrap): max(Y[r] - cm, -1) is a
+// 0 / -1 mask, (mask & 0xffc0) | (31 - r) is 31 - r where equal and negative elsewhere, and a packed max tree picks
+// the smallest r. 32 VIADDMNMX + 32 LOP3 + 16 VIMNMX3 for the two blocks of a lane.
+__device__ __forceinline__ uint32_t first_rows_of_max(const uint32_t (&Y)[32], uint32_t cm) {
+    const uint32_t negm = __vneg2(cm);
+    const uint32_t keep = 0xffc0ffc0u;
+    auto key = [&](int r) { return lop3_and_or(__viaddmax_s16x2(Y[r], negm, 0xffffffffu), keep, dup16(31 - r)); };
+    uint32_t a = key(0), b = key(1);   // two running maxima (keys are folded as they are made: no 32-register array)
+#pragma unroll
+    for (int r = 2; r + 3 < 32; r += 4) { a = __vimax3_s16x2(a, key(r), key(r + 1)); b = __vimax3_s16x2(b, key(r + 2), key(r + 3)); }
+    a = __vimax3_s16x2(a, key(30), key(31));
+    return __vmaxs2(a, b);
+}
+
+// One stripe sweep: directions, boundary row, progress, end-cell candidates. Local alignments keep, per
+// 32-row block, the first cell in row-major order that attains the block's maximum (team_alignment.cpp:186-192:
+// the reference's running strict '>' keeps exactly that cell); the rows of a column are only searched when the
+// column maximum reaches the warp-wide running maximum `thr` (refreshed every chunk) -- a cell below it cannot
+// be the stripe's maximum -- so off-diagonal blocks pay nothing and no second pass is needed.
+template <int TYPE>
 struct Sweep16 {
     // inputs
     const uint32_t* qw; const uint32_t* tw_base;
@@ -66,12 +84,12 @@ struct Sweep16 {
     bool last_stripe;
     const int32_t* row_in; int32_t* row_out;
     const uint32_t* prog_in; uint32_t* prog_out; uint32_t* stall_flag;
+    const uint32_t* lb_in; uint32_t* lb_out;   // local: running maximum handed down the stripes of a pair (biased by 2^31, 0 = none yet)
     uint32_t* drow;      // this lane's direction row (or nullptr)
-    int M;               // LOCATE: the maximum to find
     // outputs
     int colbest; uint32_t coli; int rowbest; uint32_t rowj; int final_h;
-    int lbest_lo, lbest_hi;
-    uint32_t bi, bj;
+    int lbest_lo, lbest_hi;                       // local: maximum of the lane's low / high block ...
+    uint32_t bi_lo, bj_lo, bi_hi, bj_hi;          // ... and the first cell (row-major) that attains it
 
     __device__ __forceinline__ void run(const ShortConsts& K, int lane) {
         constexpr int R = 32;
@@ -86,8 +104,9 @@ struct Sweep16 {
         const bool full = (vlo == 32u) && (vhi == 32u);
 
         colbest = INT_MIN; coli = 0; rowbest = INT_MIN; rowj = 0; final_h = 0;
-        lbest_lo = INT_MIN; lbest_hi = INT_MIN; bi = 0xffffffffu; bj = 0;
-        if (TYPE == 2 && !LOCATE) {
+        lbest_lo = INT_MIN; lbest_hi = INT_MIN; bi_lo = 0xffffffffu; bj_lo = 0; bi_hi = 0xffffffffu; bj_hi = 0;
+        int thr = INT_MIN;   // local: lower bound of the stripe's maximum
+        if (TYPE == 2) {
             if (s == 0 && lane == 0) { colbest = 0; coli = 0; }               // H(0,T) = 0 comes first
             if (last_stripe && lane == (int)lq) { rowbest = 0; rowj = 0; }    // H(Q,0) = 0
         }
@@ -112,7 +131,6 @@ struct Sweep16 {
 
         int nxt0 = 0, nxt1 = 0, cur0 = 0, cur1 = 0;
         auto wait_for = [&](uint32_t need) {   // stripe above has published at least `need` columns
-            if (LOCATE) return;
             if (lane == 0) {
                 uint32_t spins = 0;
                 while (ld_acquire(prog_in) < need) {
@@ -145,6 +163,14 @@ struct Sweep16 {
                 up_prev = __vadd2(up_prev, nd);
                 Blo += dlo; Bhi += dhi;
             }
+            if (TYPE == 1) {
+                // lower bound of the pair's maximum: this stripe's own running maximum, and what the stripes above have
+                // seen (they are at least a chunk ahead and closer to the alignment that is still on its way down here --
+                // without it the rising scores below the diagonal would pass for maxima on every step). Any stale value is
+                // a valid bound.
+                thr = __reduce_max_sync(kFull, max(lbest_lo, lbest_hi));
+                if (s > 0) thr = max(thr, (int)(__ldcg(lb_in) ^ 0x80000000u));
+            }
             const int Bab = __shfl_up_sync(kFull, Bhi, 1);
             const uint32_t conv = pack16(Bab - Blo, Blo - Bhi);   // base shifts for the two rows above
 #pragma unroll 1
@@ -160,7 +186,7 @@ struct Sweep16 {
                 const bool active = lane_on && jlo >= 1 && jlo <= (int)T + 1;
                 if (active) {
                     const bool alo = jlo <= (int)T, ahi = jlo >= 2;   // which blocks work on a real column
-                    if (!alo && !LOCATE) {
+                    if (!alo) {
                         // the low block is done (this step only the high block has a column): take what the
                         // end-cell rules need from column T before the registers are reused
                         if (TYPE == 2) {
@@ -195,46 +221,49 @@ struct Sweep16 {
                         dg = Y[r];
                         Y[r] = lop3_and_or(Z, MASK, ONE);
                         up = Y[r];
-                        if (!LOCATE) {
-                            accZ = accZ * FOUR + Z;
-                            accY = accY * FOUR + Y[r];
-                            if ((r & 7) == 7) { w[r >> 3] = accZ - accY + 0x55555555u; accZ = 0; accY = 0; }
-                        }
+                        accZ = accZ * FOUR + Z;
+                        accY = accY * FOUR + Y[r];
+                        if ((r & 7) == 7) { w[r >> 3] = accZ - accY + 0x55555555u; accZ = 0; accY = 0; }
                     }
                     tabB = tabA;
-                    if (!LOCATE) {
-                        if (lane == kWarp - 1 && !last_stripe && ahi) __stcg(row_out + (jlo - 1), half_hi(Y[R - 1]) + Bhi);
-                        if (drow) __stcs(reinterpret_cast<uint4*>(drow + (uint64_t)(jlo - 1) * 4), make_uint4(w[0], w[1], w[2], w[3]));
-                    }
+                    if (lane == kWarp - 1 && !last_stripe && ahi) __stcg(row_out + (jlo - 1), half_hi(Y[R - 1]) + Bhi);
+                    if (drow) __stcs(reinterpret_cast<uint4*>(drow + (uint64_t)(jlo - 1) * 4), make_uint4(w[0], w[1], w[2], w[3]));
                     if (TYPE == 1) {
                         const uint32_t cm = max_tree16(Y);
-                        int hlo = alo ? ((half_lo(cm) + Blo - 1) >> 2) + gap * jlo : INT_MIN;
-                        int hhi = ahi ? ((half_hi(cm) + Bhi - 1) >> 2) + gap * (jlo - 1) : INT_MIN;
-                        if (!LOCATE) {
-                            if (full) { lbest_lo = max(lbest_lo, hlo); lbest_hi = max(lbest_hi, hhi); }
-                            else if (hlo > lbest_lo || hhi > lbest_hi) {   // rows past Q may be in the tree: redo with masks
-                                int mlo = INT_MIN, mhi = INT_MIN;
+                        int mlo = half_lo(cm), mhi = half_hi(cm);   // column maxima as register halves (rows past Q included)
+                        int hlo = (alo && vlo) ? ((mlo + Blo - 1) >> 2) + gap * jlo : INT_MIN;
+                        int hhi = (ahi && vhi) ? ((mhi + Bhi - 1) >> 2) + gap * (jlo - 1) : INT_MIN;
+                        // a new block maximum, or a tie that may sit on a smaller row than the current holder -- and not below `thr`
+                        if ((hlo >= thr && (hlo > lbest_lo || (hlo == lbest_lo && bi_lo > i0 + 1))) ||
+                            (hhi >= thr && (hhi > lbest_hi || (hhi == lbest_hi && bi_hi > i0 + 33)))) {
+                            uint32_t rlo = R, rhi = R;   // smallest row of each block that holds the block's column maximum
+                            if (full && (cm & 0xffffu) != 0x8000u && (cm >> 16) != 0x8000u) {   // (-32768 has no packed negative)
+                                const uint32_t km = first_rows_of_max(Y, cm);
+                                rlo = 31u - (uint32_t)half_lo(km); rhi = 31u - (uint32_t)half_hi(km);
+                            } else {   // rows past Q may be in the tree: redo with masks
+                                mlo = INT_MIN; mhi = INT_MIN;
 #pragma unroll
                                 for (int r = 0; r < R; ++r) {
                                     if ((uint32_t)r < vlo) mlo = max(mlo, half_lo(Y[r]));
                                     if ((uint32_t)r < vhi) mhi = max(mhi, half_hi(Y[r]));
                                 }
-                                if (alo && vlo) lbest_lo = max(lbest_lo, ((mlo + Blo - 1) >> 2) + gap * jlo);
-                                if (ahi && vhi) lbest_hi = max(lbest_hi, ((mhi + Bhi - 1) >> 2) + gap * (jlo - 1));
-                            }
-                        } else if (hlo >= M || hhi >= M) {   // a cell of this column may equal the maximum: find the smallest row
-                            const int tlo = 4 * (M - gap * jlo) + 1 - Blo, thi = 4 * (M - gap * (jlo - 1)) + 1 - Bhi;
+                                hlo = (alo && vlo) ? ((mlo + Blo - 1) >> 2) + gap * jlo : INT_MIN;
+                                hhi = (ahi && vhi) ? ((mhi + Bhi - 1) >> 2) + gap * (jlo - 1) : INT_MIN;
 #pragma unroll
-                            for (int r = R - 1; r >= 0; --r) {   // descending, so the smallest matching row is kept
-                                if (ahi && (uint32_t)r < vhi && half_hi(Y[r]) == thi && i0 + 33 + r < bi) { bi = i0 + 33 + r; bj = (uint32_t)(jlo - 1); }
+                                for (int r = R - 1; r >= 0; --r) {
+                                    if ((uint32_t)r < vlo && half_lo(Y[r]) == mlo) rlo = r;
+                                    if ((uint32_t)r < vhi && half_hi(Y[r]) == mhi) rhi = r;
+                                }
                             }
-#pragma unroll
-                            for (int r = R - 1; r >= 0; --r) {
-                                if (alo && (uint32_t)r < vlo && half_lo(Y[r]) == tlo && i0 + 1 + r < bi) { bi = i0 + 1 + r; bj = (uint32_t)jlo; }
+                            if (hlo != INT_MIN && (hlo > lbest_lo || (hlo == lbest_lo && i0 + 1 + rlo < bi_lo))) {
+                                lbest_lo = hlo; bi_lo = i0 + 1 + rlo; bj_lo = (uint32_t)jlo;
+                            }
+                            if (hhi != INT_MIN && (hhi > lbest_hi || (hhi == lbest_hi && i0 + 33 + rhi < bi_hi))) {
+                                lbest_hi = hhi; bi_hi = i0 + 33 + rhi; bj_hi = (uint32_t)(jlo - 1);
                             }
                         }
                     }
-                    if (TYPE == 2 && !LOCATE && last_stripe) {   // row Q, every column (smallest j wins ties)
+                    if (TYPE == 2 && last_stripe) {   // row Q, every column (smallest j wins ties)
                         const uint32_t yq = pick_uniform(Y, rq);
                         if (lane == (int)lq) {
                             const int jq = hq ? jlo - 1 : jlo;
@@ -251,13 +280,13 @@ struct Sweep16 {
                     }
                 }
             }
-            if (!LOCATE && !last_stripe && lane == kWarp - 1) {
+            if (!last_stripe && lane == kWarp - 1) {
                 // the high block of lane 31 has finished columns 1 .. st1-63 of the stripe's bottom row: publish them
                 const int done = (int)st1 - (2 * (kWarp - 1) + 1);
+                if (TYPE == 1) __stcg(lb_out, (uint32_t)thr ^ 0x80000000u);
                 st_release(prog_out, (uint32_t)max(0, min(done, (int)T)));
             }
         }
-        if (LOCATE) return;
         // the high blocks now hold column T (frame T)
         if (TYPE == 0 && last_stripe && lane == (int)lq && hq == 1u)
             final_h = ((half_hi(pick_any(Y, rq)) + Bhi - 1) >> 2) + gap * (int)T;
@@ -277,7 +306,7 @@ fill_long16_kernel(const uint32_t* __restrict__ qpk, const uint32_t* __restrict_
                    const PairDesc* __restrict__ pairs, const uint32_t* __restrict__ work, uint32_t n_work,
                    const uint32_t* __restrict__ task_off, const uint64_t* __restrict__ bnd_off,
                    uint32_t* __restrict__ work_counter, const uint8_t* __restrict__ flags, ShortConsts K,
-                   uint32_t* __restrict__ dirs, int32_t* bnd, uint32_t* progress,
+                   uint32_t* __restrict__ dirs, int32_t* bnd, uint32_t* progress, uint32_t lb_offset,
                    StripeResult* results, uint32_t* __restrict__ stall_flag,
                    // concurrent walk (all null otherwise): the warp that finishes a pair's last outstanding stripe
                    // finalises the pair and raises its ready flag, so a walker can start while the fill goes on
@@ -296,7 +325,7 @@ fill_long16_kernel(const uint32_t* __restrict__ qpk, const uint32_t* __restrict_
         const uint32_t p = work[k];
         if (flags[p]) continue;   // not pure ACGT: the generic kernel owns the whole pair
         const PairDesc pd = pairs[p];
-        Sweep16<TYPE, false> sw;
+        Sweep16<TYPE> sw;
         sw.qw = qpk + pd.qpk_off; sw.tw_base = tpk + pd.tpk_off;
         sw.Q = pd.Q; sw.T = pd.T; sw.s = s;
         const uint32_t n_stripes = div_up(pd.Q, kL16Stripe);
@@ -306,12 +335,12 @@ fill_long16_kernel(const uint32_t* __restrict__ qpk, const uint32_t* __restrict_
         sw.row_out = bnd + bnd_off[k] + (uint64_t)s * row_pitch;
         sw.row_in = sw.row_out - row_pitch;             // written by stripe s-1 (valid when s > 0)
         sw.prog_out = progress + task; sw.prog_in = progress + task - 1; sw.stall_flag = stall_flag;
+        sw.lb_out = progress + lb_offset + task; sw.lb_in = sw.lb_out - 1;   // second half of the progress buffer
         sw.drow = dirs ? dirs + pd.dir_off + (uint64_t)(s * kWarp + lane) * pd.pitch * 4 : nullptr;
-        sw.M = 0;
         sw.run(K, lane);
 
         int colbest = sw.colbest; uint32_t coli = sw.coli;
-        uint32_t first_block = 0;
+        int rowbest_l = 0; uint32_t rowj_l = 0, located = 0;
         if (TYPE == 2) {
 #pragma unroll
             for (int o = 16; o; o >>= 1) {
@@ -320,21 +349,25 @@ fill_long16_kernel(const uint32_t* __restrict__ qpk, const uint32_t* __restrict_
                 if (ob > colbest || (ob == colbest && oi < coli)) { colbest = ob; coli = oi; }
             }
         }
-        if (TYPE == 1) {   // stripe maximum (travels in the colbest slot) and the first 32-row block that attains it
-            int m = max(sw.lbest_lo, sw.lbest_hi);
+        if (TYPE == 1) {
+            // stripe maximum and the first cell in row-major order that attains it: (value, row, column) travel in
+            // the colbest / coli / rowj slots, kStripeLocated tells finalize_pair that no locate pass is needed
+            int m = sw.lbest_lo; uint32_t bi = sw.bi_lo, bj = sw.bj_lo;
+            if (sw.lbest_hi > m) { m = sw.lbest_hi; bi = sw.bi_hi; bj = sw.bj_hi; }   // a tie keeps the low block (smaller rows)
 #pragma unroll
-            for (int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(kFull, m, o));
-            uint32_t fb = sw.lbest_lo == m ? 2u * lane : (sw.lbest_hi == m ? 2u * lane + 1u : 0xffffu);
-#pragma unroll
-            for (int o = 16; o; o >>= 1) fb = min(fb, __shfl_xor_sync(kFull, fb, o));
-            colbest = m; first_block = fb;
+            for (int o = 16; o; o >>= 1) {
+                const int om = __shfl_xor_sync(kFull, m, o);
+                const uint32_t oi = __shfl_xor_sync(kFull, bi, o), oj = __shfl_xor_sync(kFull, bj, o);
+                if (om > m || (om == m && oi < bi)) { m = om; bi = oi; bj = oj; }
+            }
+            colbest = m; coli = bi; rowj_l = bj; located = kStripeLocated;
         }
         const uint32_t lq = ((pd.Q - 1) >> 6) & 31u;
         const int final_h = __shfl_sync(kFull, sw.final_h, (int)lq);
-        const int rowbest = __shfl_sync(kFull, sw.rowbest, (int)lq);
-        const uint32_t rowj = __shfl_sync(kFull, sw.rowj, (int)lq);
-        if (lane == 0) results[task] = StripeResult{colbest, coli, rowbest, rowj, final_h, first_block};
-        if (TYPE != 1 && ready != nullptr) {
+        const int rowbest = TYPE == 1 ? rowbest_l : __shfl_sync(kFull, sw.rowbest, (int)lq);
+        const uint32_t rowj = TYPE == 1 ? rowj_l : __shfl_sync(kFull, sw.rowj, (int)lq);
+        if (lane == 0) results[task] = StripeResult{colbest, coli, rowbest, rowj, final_h, located};
+        if (ready != nullptr) {
             if (lane == 0) {
                 __threadfence();                                           // this stripe's result before the count
                 if (atomicAdd(pair_done + k, 1u) + 1 == n_stripes) {       // every stripe of the pair has reported
@@ -347,46 +380,6 @@ fill_long16_kernel(const uint32_t* __restrict__ qpk, const uint32_t* __restrict_
             __syncwarp();
         }
     }
-}
-
-// Local alignments, second pass (see locate_long_kernel): one warp per pair re-sweeps the first stripe
-// that attains the maximum, down to the first 32-row block that attains it, and keeps the first cell in
-// row-major order whose score equals the maximum.
-__global__ void __launch_bounds__(128)
-locate_long16_kernel(const uint32_t* __restrict__ qpk, const uint32_t* __restrict__ tpk,
-                     const PairDesc* __restrict__ pairs, const uint32_t* __restrict__ work, uint32_t n_work,
-                     const uint32_t* __restrict__ task_off, const uint64_t* __restrict__ bnd_off,
-                     const uint8_t* __restrict__ flags, ShortConsts K, const int32_t* __restrict__ bnd,
-                     const StripeResult* __restrict__ results, const int32_t* __restrict__ score,
-                     uint32_t* __restrict__ end_i, uint32_t* __restrict__ end_j) {
-    const int lane = threadIdx.x & 31;
-    const uint32_t k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (k >= n_work) return;
-    const uint32_t p = work[k];
-    if (flags[p]) return;
-    const uint32_t marker = end_i[p];
-    if (!(marker & 0x80000000u)) return;
-    const uint32_t s = marker & 0x7fffffffu;
-    const PairDesc pd = pairs[p];
-    const uint32_t fb = results[task_off[k] + s].pad;   // first block (2 * lane + half) that holds the maximum
-    Sweep16<1, true> sw;
-    sw.qw = qpk + pd.qpk_off; sw.tw_base = tpk + pd.tpk_off;
-    sw.Q = min(pd.Q, s * kL16Stripe + (fb + 1) * 32u);   // rows below that block cannot hold the first maximum
-    sw.T = pd.T; sw.s = s;
-    sw.lanes_used = div_up(sw.Q - s * kL16Stripe, kL16LaneRows);
-    sw.last_stripe = true;
-    sw.row_out = nullptr;
-    sw.row_in = bnd + bnd_off[k] + (uint64_t)s * (pd.T + 4) - (pd.T + 4);
-    sw.prog_out = nullptr; sw.prog_in = nullptr; sw.stall_flag = nullptr; sw.drow = nullptr;
-    sw.M = score[p];
-    sw.run(K, lane);
-    uint32_t bi = sw.bi, bj = sw.bj;
-#pragma unroll
-    for (int o = 16; o; o >>= 1) {
-        const uint32_t oi = __shfl_xor_sync(kFull, bi, o), oj = __shfl_xor_sync(kFull, bj, o);
-        if (oi < bi) { bi = oi; bj = oj; }
-    }
-    if (lane == 0) { end_i[p] = bi; end_j[p] = bj; }
 }
 
 }  // namespace b200

@@ -43,7 +43,7 @@ __device__ __forceinline__ uint32_t dec_digits(uint32_t v) {
 template <int TYPE>
 __global__ void __launch_bounds__(128)
 walk_kernel(const PairDesc* __restrict__ pairs, const uint32_t* __restrict__ work, uint32_t n_work, uint32_t spread,
-            const uint32_t* __restrict__ dirs, const uint32_t* __restrict__ end_i,
+            const uint8_t* __restrict__ skip_flags, const uint32_t* __restrict__ dirs, const uint32_t* __restrict__ end_i,
             const uint32_t* __restrict__ end_j, uint32_t* __restrict__ runs,
             uint32_t* __restrict__ n_runs, uint32_t* __restrict__ cigar_len) {
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -51,6 +51,7 @@ walk_kernel(const PairDesc* __restrict__ pairs, const uint32_t* __restrict__ wor
     const uint32_t w = tid / spread;
     if (w >= n_work) return;
     const uint32_t p = work[w];
+    if (skip_flags && skip_flags[p]) return;   // not pure ACGT: filled and walked by the repair pass (capi.cu)
     const PairDesc pd = pairs[p];
     const uint32_t Q = pd.Q, T = pd.T;
     uint32_t i = end_i[p], j = end_j[p];
@@ -259,7 +260,7 @@ __device__ __forceinline__ void walk_pair_tiles(const PairDesc& pd, uint32_t p, 
 template <int TYPE>
 __global__ void __launch_bounds__(128)
 walk_tile_kernel(const PairDesc* __restrict__ pairs, const uint32_t* __restrict__ work, uint32_t n_work,
-                 const uint32_t* __restrict__ dirs, const uint32_t* __restrict__ end_i,
+                 const uint8_t* __restrict__ skip_flags, const uint32_t* __restrict__ dirs, const uint32_t* __restrict__ end_i,
                  const uint32_t* __restrict__ end_j, uint32_t* __restrict__ runs,
                  uint32_t* __restrict__ n_runs, uint32_t* __restrict__ cigar_len) {
     __shared__ __align__(16) uint32_t tiles[4][kWalkTileWords];
@@ -267,6 +268,7 @@ walk_tile_kernel(const PairDesc* __restrict__ pairs, const uint32_t* __restrict_
     const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (w >= n_work) return;
     const uint32_t p = work[w];
+    if (skip_flags && skip_flags[p]) return;         // the repair pass's
     const PairDesc pd = pairs[p];
     if ((pd.klass & 0xffu) == kClassShort) return;   // walk_kernel's
     walk_pair_tiles<TYPE, false>(pd, p, dirs, end_i[p], end_j[p], tiles[threadIdx.x >> 5], runs, n_runs, cigar_len, lane);
@@ -275,7 +277,7 @@ walk_tile_kernel(const PairDesc* __restrict__ pairs, const uint32_t* __restrict_
 // Persistent walkers for the wave that is still being filled: warps take pairs in work order (largest first, the
 // order the fill hands its stripes out in), wait for the pair's ready flag -- raised by the fill warp that finished
 // the pair's last stripe -- and walk it while the fill goes on with the other pairs. Pairs the 2-bit fill does not
-// own (flags != 0) are skipped; they are walked after their fallback fill.
+// own (flags != 0) are skipped; they are walked after their fallback fill (the repair pass in capi.cu).
 template <int TYPE>
 __global__ void __launch_bounds__(128)
 walk_tile_wait_kernel(const PairDesc* __restrict__ pairs, const uint32_t* __restrict__ work, uint32_t n_work,

@@ -135,6 +135,8 @@ struct b200_ctx {
     int64_t overlap_waves = 1;              // 0 = all waves on the caller's stream, one after the other
     int64_t concurrent_walk = 1;            // 0 = a wave's pairs are walked after its fill kernel has finished
     DevBuf qpk, tpk, end_i, end_j, runs, n_runs, cigar_len, scan_tmp, flags, total;
+    DevBuf wave_flagged;                    // per wave of a run: pairs planned for a 2-bit kernel that are not pure ACGT
+    HostBuf h_small;                        // pinned landing zone of the small read-backs of a run
     // staging for the host-buffer entry points
     DevBuf d_q, d_t, d_score, d_tb, d_cigar, d_cigar_off, d_seq, d_hash, d_pos, d_flag;
     HostBuf h_q, h_t, h_off;
@@ -239,7 +241,6 @@ extern "C" int b200_ctx_create(int device, b200_ctx** out) {
         cudaFuncSetAttribute(fill_long16_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
         cudaFuncSetAttribute(fill_long16_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
         cudaFuncSetAttribute(fill_long16_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-        cudaFuncSetAttribute(locate_long16_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
         cudaFuncSetAttribute(fill_long_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
         cudaFuncSetAttribute(fill_long_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
         cudaFuncSetAttribute(fill_long_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
@@ -247,6 +248,7 @@ extern "C" int b200_ctx_create(int device, b200_ctx** out) {
         cudaFuncSetAttribute(walk_tile_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
         cudaFuncSetAttribute(walk_tile_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
         cudaFuncSetAttribute(walk_tile_wait_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        cudaFuncSetAttribute(walk_tile_wait_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
         cudaFuncSetAttribute(walk_tile_wait_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
         cudaGetLastError();
     }
@@ -283,10 +285,10 @@ extern "C" void b200_ctx_destroy(b200_ctx* c) {
         if (w.walk_event) cudaEventDestroy(w.walk_event);
     }
     for (DevBuf* b : {&c->qpk, &c->tpk, &c->end_i, &c->end_j, &c->runs, &c->n_runs,
-                      &c->cigar_len, &c->scan_tmp, &c->flags, &c->total, &c->d_q, &c->d_t, &c->d_score, &c->d_tb,
+                      &c->cigar_len, &c->scan_tmp, &c->flags, &c->total, &c->wave_flagged, &c->d_q, &c->d_t, &c->d_score, &c->d_tb,
                       &c->d_cigar, &c->d_cigar_off, &c->d_seq, &c->d_hash, &c->d_pos, &c->d_flag})
         b->release();
-    for (HostBuf* b : {&c->h_q, &c->h_t, &c->h_off}) b->release();
+    for (HostBuf* b : {&c->h_q, &c->h_t, &c->h_off, &c->h_small}) b->release();
     delete c;
 }
 
@@ -815,18 +817,21 @@ static int launch_fill_long(b200_align_plan* p, const Wave& wv, const RunBufs& r
     // every CTA must be resident: stripes wait (poll) on the stripe handed out just before them
     const int n_blocks = (int)std::min<uint64_t>((uint64_t)c->sm_count * per_sm, div_up64(std::max(p->max_long_tasks, 1u), 4));
     TRY(rb.ws->bnd.ensure((p->max_long_bnd_words + 8) * sizeof(int32_t)));
-    TRY(rb.ws->progress.ensure(((size_t)p->max_long_tasks + 8) * 4));
+    const size_t prog_words = (size_t)p->max_long_tasks + 8;   // progress counters, then (long16, local) the running maxima
+    TRY(rb.ws->progress.ensure(2 * prog_words * 4));
     TRY(rb.ws->stripe_res.ensure(((size_t)p->max_long_tasks + 8) * sizeof(StripeResult)));
     CU(cudaMemsetAsync(rb.ws->counter.p, 0, 64, rb.st));
     CU(cudaMemsetAsync(rb.ws->counter.as<uint32_t>() + 24, 0, 4, rb.st));
-    CU(cudaMemsetAsync(rb.ws->progress.p, 0, ((size_t)p->max_long_tasks + 8) * 4, rb.st));
+    CU(cudaMemsetAsync(rb.ws->progress.p, 0, 2 * prog_words * 4, rb.st));
     const uint32_t* d_work = p->d_work.as<uint32_t>() + wv.first;
     if (p->long16) {
         const ShortConsts K16 = make_short_consts(p->sc, p->type);
         // Global and semi-global waves with CIGARs: the walkers start with the fill and take each pair as soon as
-        // its last stripe is in (the traceback of the longest pairs no longer trails the whole wave).
+        // its last stripe is in (the traceback of the longest pairs no longer trails the whole wave). Local alignments
+        // could (the fill itself keeps the first maximum, so the end cell is known when the last stripe reports), but
+        // fill_long16_kernel<1> needs 168 registers: three of its CTAs leave no room on an SM for a walker CTA.
         WaveSlot& ws = *rb.ws;
-        const bool cw = c->concurrent_walk && !c->profile && p->want_cigar && p->type != 1 && rb.dirs != nullptr;
+        const bool cw = c->concurrent_walk && !c->profile && p->want_cigar && rb.dirs != nullptr && p->type != 1;
         uint32_t *d_done = nullptr, *d_ready = nullptr;
         if (cw) {
             TRY(ws.pair_state.ensure(((size_t)wv.count + 8) * 8));
@@ -849,7 +854,8 @@ static int launch_fill_long(b200_align_plan* p, const Wave& wv, const RunBufs& r
     }                                                                                                                  \
     fill_long16_kernel<TY><<<n_blocks, 128, 0, rb.st>>>(c->qpk.as<uint32_t>(), c->tpk.as<uint32_t>(), p->d_pairs.as<PairDesc>(), \
         d_work, wv.count, d_task_off, d_bnd_off, rb.ws->counter.as<uint32_t>(), c->flags.as<uint8_t>(), K16, rb.dirs,  \
-        rb.ws->bnd.as<int32_t>(), rb.ws->progress.as<uint32_t>(), rb.ws->stripe_res.as<StripeResult>(),                \
+        rb.ws->bnd.as<int32_t>(), rb.ws->progress.as<uint32_t>(), (uint32_t)prog_words,                                \
+        rb.ws->stripe_res.as<StripeResult>(),                                                                          \
         rb.ws->counter.as<uint32_t>() + 24, d_done, d_ready, cw ? rb.score : nullptr,                                  \
         cw ? c->end_i.as<uint32_t>() : nullptr, cw ? c->end_j.as<uint32_t>() : nullptr);                               \
     if (cw) {                                                                                                          \
@@ -865,14 +871,7 @@ static int launch_fill_long(b200_align_plan* p, const Wave& wv, const RunBufs& r
     finalize_long_kernel<TY><<<(unsigned)div_up64(wv.count, 128), 128, 0, rb.st>>>(p->d_pairs.as<PairDesc>(), d_work,  \
         wv.count, d_task_off, c->flags.as<uint8_t>(), rb.ws->stripe_res.as<StripeResult>(), K16.init, rb.score,        \
         c->end_i.as<uint32_t>(), c->end_j.as<uint32_t>(), 0, nullptr)
-        if (p->type == 0) { LONG16K(0); } else if (p->type == 2) { LONG16K(2); } else {
-            LONG16K(1);
-            locate_long16_kernel<<<(unsigned)div_up64((uint64_t)wv.count * 32, 128), 128, 0, rb.st>>>(
-                c->qpk.as<uint32_t>(), c->tpk.as<uint32_t>(), p->d_pairs.as<PairDesc>(), d_work, wv.count, d_task_off, d_bnd_off,
-                c->flags.as<uint8_t>(), K16, rb.ws->bnd.as<int32_t>(), rb.ws->stripe_res.as<StripeResult>(), rb.score,
-                c->end_i.as<uint32_t>(), c->end_j.as<uint32_t>());
-            c->kernel_launches++;
-        }
+        if (p->type == 0) { LONG16K(0); } else if (p->type == 2) { LONG16K(2); } else { LONG16K(1); }
 #undef LONG16K
         prof_end(c, rb.st);
         c->kernel_launches += 2;
@@ -901,7 +900,8 @@ static int launch_fill_long(b200_align_plan* p, const Wave& wv, const RunBufs& r
     return B200_OK;
 }
 
-static int launch_walk(b200_align_plan* p, uint32_t wave_klass, const uint32_t* d_work, uint32_t count, const RunBufs& rb) {
+static int launch_walk(b200_align_plan* p, uint32_t wave_klass, const uint32_t* d_work, uint32_t count, const RunBufs& rb,
+                       const uint8_t* skip_flags) {
     b200_ctx* c = p->ctx;
     if (!count) return B200_OK;
     prof_begin(c, rb.st, 1);
@@ -910,14 +910,14 @@ static int launch_walk(b200_align_plan* p, uint32_t wave_klass, const uint32_t* 
         uint32_t spread = 1;
         while (spread < 32 && (uint64_t)count * spread * 2 <= (uint64_t)c->sm_count * 512) spread *= 2;
         const unsigned wb = (unsigned)div_up64((uint64_t)count * spread, 128);
-#define WALK(TY) walk_kernel<TY><<<wb, 128, 0, rb.st>>>(p->d_pairs.as<PairDesc>(), d_work, count, spread, rb.dirs, c->end_i.as<uint32_t>(), \
+#define WALK(TY) walk_kernel<TY><<<wb, 128, 0, rb.st>>>(p->d_pairs.as<PairDesc>(), d_work, count, spread, skip_flags, rb.dirs, c->end_i.as<uint32_t>(), \
         c->end_j.as<uint32_t>(), c->runs.as<uint32_t>(), c->n_runs.as<uint32_t>(), c->cigar_len.as<uint32_t>())
         switch (p->type) { case 0: WALK(0); break; case 1: WALK(1); break; default: WALK(2); break; }
 #undef WALK
     } else {
         // warp per pair, tile by tile (long and generic layouts)
         const unsigned wb = (unsigned)div_up64((uint64_t)count * 32, 128);
-#define WALK(TY) walk_tile_kernel<TY><<<wb, 128, 0, rb.st>>>(p->d_pairs.as<PairDesc>(), d_work, count, rb.dirs, c->end_i.as<uint32_t>(), \
+#define WALK(TY) walk_tile_kernel<TY><<<wb, 128, 0, rb.st>>>(p->d_pairs.as<PairDesc>(), d_work, count, skip_flags, rb.dirs, c->end_i.as<uint32_t>(), \
         c->end_j.as<uint32_t>(), c->runs.as<uint32_t>(), c->n_runs.as<uint32_t>(), c->cigar_len.as<uint32_t>())
         switch (p->type) { case 0: WALK(0); break; case 1: WALK(1); break; default: WALK(2); break; }
 #undef WALK
@@ -994,8 +994,16 @@ static int plan_run_impl(b200_align_plan* p, const char* d_q_buf, const char* d_
         CU(cudaStreamSynchronize(st));
         p->patched = false;
     }
-    std::vector<PairDesc> patched;   // run-specific descriptors, only materialised if a fallback is needed
-    std::vector<uint8_t> h_flags;
+    // Pairs planned for a 2-bit kernel that turn out not to be pure ACGT are content, not plan: pack_kernel flags and
+    // counts them (one counter per wave), every kernel of the wave skips them, and the counters are read back together
+    // with the first read-back the run needs anyway (no host round trip per wave). Flagged pairs are rare; when there
+    // are any, the repair pass below gives them to the generic kernel after everything else has finished.
+    const size_t n_waves = p->waves.size();
+    TRY(c->wave_flagged.ensure(n_waves * 4 + 16));
+    TRY(c->h_small.ensure((n_waves + 8) * 8));
+    uint32_t* h_flagged = c->h_small.as<uint32_t>() + 4;   // [n_waves], after the 8-byte slot of the CIGAR total
+    std::memset(c->h_small.p, 0, (n_waves + 8) * 8);
+    CU(cudaMemsetAsync(c->wave_flagged.p, 0, n_waves * 4 + 16, st));
     if (overlap) {   // the second stream starts after everything already queued on the caller's stream
         CU(cudaEventRecord(c->fork_event, st));
         CU(cudaStreamWaitEvent(c->aux_stream, c->fork_event, 0));
@@ -1018,14 +1026,11 @@ static int plan_run_impl(b200_align_plan* p, const char* d_q_buf, const char* d_
         WaveSlot& ws = c->slot[overlap ? (k & 1) : 0];
         cudaStream_t wst = (overlap && (k & 1)) ? c->aux_stream : st;
         RunBufs rb{reinterpret_cast<const uint8_t*>(d_q_buf), reinterpret_cast<const uint8_t*>(d_t_buf), nullptr, d_score, wst, &ws};
-        uint32_t* d_nflag = ws.counter.as<uint32_t>() + 16;
+        uint32_t* d_nflag = c->wave_flagged.as<uint32_t>() + k;
         const uint32_t* work = p->d_work.as<uint32_t>() + wv.first;
         if (k < p->wave_events.size() && p->wave_events[k]) CU(cudaStreamWaitEvent(wst, p->wave_events[k], 0));
-        std::vector<uint32_t> fix;   // pairs of this wave that must fall back to the generic kernel
-        uint64_t wave_words = wv.dir_words;
         prof_begin(c, wst, 3);
         if (wv.klass != kClassGeneric) {
-            CU(cudaMemsetAsync(d_nflag, 0, 4, wst));
             const uint32_t wpp = std::max(1u, div_up(wv.klass == kClassLong ? std::max(p->max_Q, p->max_T)
                                                                            : std::max(p->max_Q_short, p->max_T_short), 16));
             dim3 grid((unsigned)div_up64((uint64_t)wv.count * wpp, 256), 2);
@@ -1037,59 +1042,22 @@ static int plan_run_impl(b200_align_plan* p, const char* d_q_buf, const char* d_
         }
         prof_end(c, wst);
         c->kernel_launches++;
-        if (wv.klass != kClassGeneric) {
-            // Pairs planned for a 2-bit kernel that turn out not to be pure ACGT fall back to the generic kernel;
-            // their direction matrices go behind the wave's own region. Content-dependent, hence decided here
-            // (one 4-byte read-back per wave) and not in the plan.
-            uint32_t n_flagged = 0;
-            CU(cudaMemcpyAsync(&n_flagged, d_nflag, 4, cudaMemcpyDeviceToHost, wst));
-            CU(cudaStreamSynchronize(wst));
-            if (n_flagged) {
-                materialize_uniform_host(p);
-                h_flags.resize(n);
-                CU(cudaMemcpyAsync(h_flags.data(), c->flags.p, n, cudaMemcpyDeviceToHost, wst));
-                CU(cudaStreamSynchronize(wst));
-                if (patched.empty()) patched = p->h_pairs;
-                for (uint32_t w = wv.first; w < wv.first + wv.count; ++w) {
-                    const uint32_t idx = p->h_order[w];
-                    if (!h_flags[idx]) continue;
-                    PairDesc& d = patched[idx];
-                    d.klass = kClassGeneric;
-                    d.pitch = (d.T + 3u) & ~3u;
-                    d.dir_off = (wave_words + 3) & ~3ull;
-                    wave_words = d.dir_off + (p->want_cigar ? generic_dir_words(d.Q, d.T) : 0);
-                    fix.push_back(idx);
-                }
-                // (descriptors of pairs owned by the other stream's wave are rewritten with identical bytes)
-                CU(cudaMemcpyAsync(p->d_pairs.p, patched.data(), n * sizeof(PairDesc), cudaMemcpyHostToDevice, wst));
-                CU(cudaStreamSynchronize(wst));
-                p->patched = true;
-                if (p->want_cigar) TRY(ws.dirs.ensure(std::max<uint64_t>(wave_words, 4) * 4 + 64));
-            }
-        }
         rb.dirs = p->want_cigar ? ws.dirs.as<uint32_t>() : nullptr;
         tl_mark(c, wst, "pack" + std::to_string(k));
-        if (wv.klass != kClassGeneric) {
-            if (wv.klass == kClassShort) TRY(launch_fill_short(p, wv, rb));
-            else TRY(launch_fill_long(p, wv, rb));
-            if (!fix.empty()) {
-                TRY(ws.fix_work.ensure(fix.size() * 4));
-                CU(cudaMemcpyAsync(ws.fix_work.p, fix.data(), fix.size() * 4, cudaMemcpyHostToDevice, wst));
-                CU(cudaStreamSynchronize(wst));
-                TRY(launch_fill_generic(p, ws.fix_work.as<uint32_t>(), (uint32_t)fix.size(), rb));
-            }
-        } else {
-            TRY(launch_fill_generic(p, work, wv.count, rb));
-        }
+        // in a wave of a 2-bit class a non-zero flag means "not this wave's pair"; in a generic wave the flags only
+        // describe the content (classify_kernel) and every pair is the wave's own
+        const uint8_t* skip = wv.klass != kClassGeneric ? c->flags.as<uint8_t>() : nullptr;
+        if (wv.klass == kClassShort) TRY(launch_fill_short(p, wv, rb));
+        else if (wv.klass != kClassGeneric) TRY(launch_fill_long(p, wv, rb));
+        else TRY(launch_fill_generic(p, work, wv.count, rb));
         tl_mark(c, wst, "fill" + std::to_string(k));
         if (ws.walk_inflight) {
-            // the wave's own pairs are being walked next to the fill; pairs that fell back to the generic kernel follow
-            // here, and the wave's stream waits for the walkers so that everything after it sees every pair walked
+            // the wave's pairs are being walked next to the fill; the wave's stream waits for the walkers so that
+            // everything after it sees every pair walked
             ws.walk_inflight = false;
-            if (!fix.empty()) TRY(launch_walk(p, kClassGeneric, ws.fix_work.as<uint32_t>(), (uint32_t)fix.size(), rb));
             CU(cudaStreamWaitEvent(wst, ws.walk_event, 0));
             tl_mark(c, wst, "cwalk" + std::to_string(k));
-        } else if (p->want_cigar) TRY(launch_walk(p, wv.klass, work, wv.count, rb));
+        } else if (p->want_cigar) TRY(launch_walk(p, wv.klass, work, wv.count, rb, skip));
         tl_mark(c, wst, "walk" + std::to_string(k));
         if (piped) {
             const uint32_t a = wv.first, b = wv.first + wv.count;
@@ -1109,64 +1077,143 @@ static int plan_run_impl(b200_align_plan* p, const char* d_q_buf, const char* d_
         target_begin_kernel<<<(unsigned)div_up64(n, 256), 256, 0, st>>>(0u, (uint32_t)n, p->type, c->end_j.as<uint32_t>(), d_target_begin);
         c->kernel_launches++;
     }
-    if (p->want_cigar) {
-        // CIGAR offsets (scan of the text lengths) and text, for pairs [a, b) on stream es; `base` = bytes before pair a
-        // (device scalar d_cigar_off[a] is final by then). Returns the byte count up to pair b through *total_out.
-        auto scan_emit = [&](uint32_t a, uint32_t b, cudaStream_t es, uint64_t* total_out) -> int {
-            cub::TransformInputIterator<uint64_t, U32ToU64, const uint32_t*> in(c->cigar_len.as<uint32_t>() + a, U32ToU64());
-            size_t tmp_bytes = 0;
-            CU(cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, in, d_cigar_off + a + 1, (int)(b - a), es));
-            TRY(c->scan_tmp.ensure(tmp_bytes));
-            if (a == 0) CU(cudaMemsetAsync(d_cigar_off, 0, sizeof(uint64_t), es));
-            prof_begin(c, es, 3);
-            CU(cub::DeviceScan::InclusiveSum(c->scan_tmp.p, tmp_bytes, in, d_cigar_off + a + 1, (int)(b - a), es));
-            if (a) add_offset_kernel<<<(unsigned)div_up64(b - a, 256), 256, 0, es>>>(d_cigar_off + a + 1, b - a, d_cigar_off + a);
-            prof_end(c, es);
-            c->kernel_launches += 2 + (a ? 1 : 0);
+    // The per-wave counts of flagged pairs (see above) ride on the read-back that is needed anyway: the copy of waves
+    // [k0, k1) is queued on a stream that is ordered after their pack kernels, the caller's next synchronise lands it.
+    auto queue_flag_counts = [&](size_t k0, size_t k1, cudaStream_t es) -> int {
+        if (n_packed && k1 > k0)
+            CU(cudaMemcpyAsync(h_flagged + k0, c->wave_flagged.as<uint32_t>() + k0, (k1 - k0) * 4, cudaMemcpyDeviceToHost, es));
+        return B200_OK;
+    };
+    auto any_flagged = [&](size_t k0, size_t k1) { for (size_t k = k0; k < k1; ++k) if (h_flagged[k]) return true; return false; };
+    // CIGAR offsets (scan of the text lengths) and text, for pairs [a, b) on stream es (device scalar d_cigar_off[a] is
+    // final by then). Returns the byte count up to pair b through *total_out. If one of the waves [fk0, fk1) counted a
+    // flagged pair, *flagged is set and nothing is emitted: the texts of those pairs do not exist yet.
+    uint64_t* h_total = c->h_small.as<uint64_t>();
+    auto scan_emit = [&](uint32_t a, uint32_t b, cudaStream_t es, uint64_t* total_out, size_t fk0, size_t fk1, bool* flagged) -> int {
+        cub::TransformInputIterator<uint64_t, U32ToU64, const uint32_t*> in(c->cigar_len.as<uint32_t>() + a, U32ToU64());
+        size_t tmp_bytes = 0;
+        CU(cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, in, d_cigar_off + a + 1, (int)(b - a), es));
+        TRY(c->scan_tmp.ensure(tmp_bytes));
+        if (a == 0) CU(cudaMemsetAsync(d_cigar_off, 0, sizeof(uint64_t), es));
+        prof_begin(c, es, 3);
+        CU(cub::DeviceScan::InclusiveSum(c->scan_tmp.p, tmp_bytes, in, d_cigar_off + a + 1, (int)(b - a), es));
+        if (a) add_offset_kernel<<<(unsigned)div_up64(b - a, 256), 256, 0, es>>>(d_cigar_off + a + 1, b - a, d_cigar_off + a);
+        prof_end(c, es);
+        c->kernel_launches += 2 + (a ? 1 : 0);
+        CU(cudaMemcpyAsync(h_total, d_cigar_off + b, sizeof(uint64_t), cudaMemcpyDeviceToHost, es));
+        TRY(queue_flag_counts(fk0, fk1, es));
+        CU(cudaStreamSynchronize(es));
+        if (any_flagged(fk0, fk1)) { *flagged = true; return B200_OK; }
+        const uint64_t total = *h_total;
+        *total_out = total;
+        if (total > cigar_cap)
+            return fail(B200_E_CAP, "CIGAR buffer too small: need " + std::to_string(total) + " bytes, have " + std::to_string(cigar_cap));
+        prof_begin(c, es, 2);
+        // many short pairs: a thread each; fewer, longer pairs (thousands of runs): a warp each
+        if (p->n_short * 2 >= n)
+            emit_kernel<<<(unsigned)div_up64(b - a, 128), 128, 0, es>>>(p->d_pairs.as<PairDesc>(), a, b, c->runs.as<uint32_t>(), c->n_runs.as<uint32_t>(), d_cigar_off, d_cigar);
+        else
+            emit_warp_kernel<<<(unsigned)div_up64((uint64_t)(b - a) * 32, 128), 128, 0, es>>>(p->d_pairs.as<PairDesc>(), a, b, c->runs.as<uint32_t>(), c->n_runs.as<uint32_t>(), d_cigar_off, d_cigar);
+        prof_end(c, es);
+        c->kernel_launches++;
+        return B200_OK;
+    };
+    bool flagged = false;
+    if (p->want_cigar && piped) {
+        // Offsets, texts and their download go group by group on the emit stream while later waves still run: two
+        // waves at a time (one of each wave stream), the last wave alone -- so that what is left to do after the last
+        // wave is its own share and not the download of everything before it.
+        const size_t nw = n_waves;
+        std::vector<size_t> gb{0};
+        for (size_t k = 2; k + 1 < nw; k += 2) gb.push_back(k);
+        gb.push_back(nw - 1);
+        gb.push_back(nw);
+        cudaStream_t es = c->emit_stream;
+        uint64_t done_bytes = 0;
+        for (size_t g = 0; g + 1 < gb.size() && !flagged; ++g) {
+            const size_t k0 = gb[g], k1 = gb[g + 1];
+            const uint32_t a = p->waves[k0].first, b = k1 < nw ? p->waves[k1].first : (uint32_t)n;
+            CU(cudaStreamWaitEvent(es, c->wave_done[k1 - 1], 0));
+            if (k1 >= 2) CU(cudaStreamWaitEvent(es, c->wave_done[k1 - 2], 0));   // the other wave stream
+            tl_mark(c, es, "ready" + std::to_string(g));
             uint64_t total = 0;
-            CU(cudaMemcpyAsync(&total, d_cigar_off + b, sizeof(uint64_t), cudaMemcpyDeviceToHost, es));
-            CU(cudaStreamSynchronize(es));
-            *total_out = total;
-            if (total > cigar_cap)
-                return fail(B200_E_CAP, "CIGAR buffer too small: need " + std::to_string(total) + " bytes, have " + std::to_string(cigar_cap));
-            prof_begin(c, es, 2);
-            // many short pairs: a thread each; fewer, longer pairs (thousands of runs): a warp each
-            if (p->n_short * 2 >= n)
-                emit_kernel<<<(unsigned)div_up64(b - a, 128), 128, 0, es>>>(p->d_pairs.as<PairDesc>(), a, b, c->runs.as<uint32_t>(), c->n_runs.as<uint32_t>(), d_cigar_off, d_cigar);
-            else
-                emit_warp_kernel<<<(unsigned)div_up64((uint64_t)(b - a) * 32, 128), 128, 0, es>>>(p->d_pairs.as<PairDesc>(), a, b, c->runs.as<uint32_t>(), c->n_runs.as<uint32_t>(), d_cigar_off, d_cigar);
-            prof_end(c, es);
-            c->kernel_launches++;
-            return B200_OK;
-        };
-        if (piped) {
-            // group A = every wave but the last: scanned, emitted and downloaded on the emit stream while the last wave runs
-            const size_t nw = p->waves.size();
-            const uint32_t nA = p->waves[nw - 1].first;
-            cudaStream_t es = c->emit_stream;
-            CU(cudaStreamWaitEvent(es, c->wave_done[nw - 2], 0));
-            CU(cudaStreamWaitEvent(es, c->wave_done[nw - 3], 0));
-            uint64_t totalA = 0, total = 0;
-            tl_mark(c, es, "A-ready");
-            TRY(scan_emit(0, nA, es, &totalA));
-            if (ho->cigar_cap < totalA) return fail(B200_E_CAP, "CIGAR buffer too small: need " + std::to_string(totalA));
-            CU(cudaMemcpyAsync(ho->cigar_off, d_cigar_off, ((size_t)nA + 1) * 8, cudaMemcpyDeviceToHost, es));
-            if (totalA) CU(cudaMemcpyAsync(ho->cigar, d_cigar, totalA, cudaMemcpyDeviceToHost, es));
-            // group B = the last wave, after everything else (st has joined the other wave stream above)
-            tl_mark(c, es, "A-down");
-            CU(cudaStreamWaitEvent(es, c->wave_done[nw - 1], 0));
-            tl_mark(c, es, "B-ready");
-            TRY(scan_emit(nA, (uint32_t)n, es, &total));
+            TRY(scan_emit(a, b, es, &total, k0, k1, &flagged));
+            if (flagged) break;
             if (ho->cigar_cap < total) return fail(B200_E_CAP, "CIGAR buffer too small: need " + std::to_string(total));
-            CU(cudaMemcpyAsync(ho->cigar_off + nA + 1, d_cigar_off + nA + 1, ((size_t)n - nA) * 8, cudaMemcpyDeviceToHost, es));
-            if (total > totalA) CU(cudaMemcpyAsync(ho->cigar + totalA, d_cigar + totalA, total - totalA, cudaMemcpyDeviceToHost, es));
-            tl_mark(c, es, "B-down");
+            if (a == 0) CU(cudaMemcpyAsync(ho->cigar_off, d_cigar_off, ((size_t)b + 1) * 8, cudaMemcpyDeviceToHost, es));
+            else CU(cudaMemcpyAsync(ho->cigar_off + a + 1, d_cigar_off + a + 1, ((size_t)b - a) * 8, cudaMemcpyDeviceToHost, es));
+            if (total > done_bytes) CU(cudaMemcpyAsync(ho->cigar + done_bytes, d_cigar + done_bytes, total - done_bytes, cudaMemcpyDeviceToHost, es));
+            done_bytes = total;
+            tl_mark(c, es, "down" + std::to_string(g));
+        }
+        if (!flagged) {
             CU(cudaStreamSynchronize(es));
-            c->d2h_bytes += ((uint64_t)n + 1) * 8 + total;
+            c->d2h_bytes += ((uint64_t)n + 1) * 8 + done_bytes;
             ho->done = true;
-        } else {
+        }
+    } else if (p->want_cigar) {
+        uint64_t total = 0;
+        TRY(scan_emit(0, (uint32_t)n, st, &total, 0, n_waves, &flagged));
+    } else if (n_packed) {
+        TRY(queue_flag_counts(0, n_waves, st));
+        CU(cudaStreamSynchronize(st));
+        flagged = any_flagged(0, n_waves);
+    }
+    if (flagged) {
+        // Repair pass (rare): the flagged pairs go to the generic kernel once everything queued so far has finished,
+        // in chunks whose direction matrices fit the wave budget (they live in the first slot's buffer, free by then);
+        // then target_begin, offsets and texts are redone for the whole batch and the caller downloads all of it.
+        CU(cudaStreamSynchronize(st));
+        if (c->aux_stream) CU(cudaStreamSynchronize(c->aux_stream));
+        if (c->emit_stream) CU(cudaStreamSynchronize(c->emit_stream));
+        materialize_uniform_host(p);
+        std::vector<uint8_t> h_flags(n);
+        CU(cudaMemcpy(h_flags.data(), c->flags.p, n, cudaMemcpyDeviceToHost));
+        std::vector<PairDesc> patched = p->h_pairs;
+        std::vector<uint32_t> fix;
+        std::vector<size_t> chunk_start{0};
+        const uint64_t budget = wave_budget_words(c);
+        uint64_t words = 0, max_words = 4;
+        for (const Wave& wv : p->waves) {
+            if (wv.klass == kClassGeneric) continue;
+            for (uint32_t w = wv.first; w < wv.first + wv.count; ++w) {
+                const uint32_t idx = p->h_order[w];
+                if (!h_flags[idx]) continue;
+                PairDesc& d = patched[idx];
+                const uint64_t need = p->want_cigar ? generic_dir_words(d.Q, d.T) : 0;
+                if (words && ((words + 3) & ~3ull) + need > budget) { chunk_start.push_back(fix.size()); words = 0; }
+                d.klass = kClassGeneric;
+                d.pitch = (d.T + 3u) & ~3u;
+                d.dir_off = (words + 3) & ~3ull;
+                words = d.dir_off + need;
+                max_words = std::max(max_words, words);
+                fix.push_back(idx);
+            }
+        }
+        chunk_start.push_back(fix.size());
+        WaveSlot& ws = c->slot[0];
+        if (p->want_cigar) TRY(ws.dirs.ensure(max_words * 4 + 64));
+        TRY(ws.fix_work.ensure(std::max<size_t>(fix.size(), 1) * 4));
+        CU(cudaMemcpyAsync(p->d_pairs.p, patched.data(), n * sizeof(PairDesc), cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(ws.fix_work.p, fix.data(), fix.size() * 4, cudaMemcpyHostToDevice, st));
+        CU(cudaStreamSynchronize(st));   // `patched` and `fix` are pageable
+        p->patched = true;
+        RunBufs rb{reinterpret_cast<const uint8_t*>(d_q_buf), reinterpret_cast<const uint8_t*>(d_t_buf),
+                   p->want_cigar ? ws.dirs.as<uint32_t>() : nullptr, d_score, st, &ws};
+        for (size_t ch = 0; ch + 1 < chunk_start.size(); ++ch) {
+            const uint32_t* d_fix = ws.fix_work.as<uint32_t>() + chunk_start[ch];
+            const uint32_t cnt = (uint32_t)(chunk_start[ch + 1] - chunk_start[ch]);
+            TRY(launch_fill_generic(p, d_fix, cnt, rb));
+            if (p->want_cigar) TRY(launch_walk(p, kClassGeneric, d_fix, cnt, rb, nullptr));
+        }
+        if (d_target_begin) {
+            target_begin_kernel<<<(unsigned)div_up64(n, 256), 256, 0, st>>>(0u, (uint32_t)n, p->type, c->end_j.as<uint32_t>(), d_target_begin);
+            c->kernel_launches++;
+        }
+        if (p->want_cigar) {
             uint64_t total = 0;
-            TRY(scan_emit(0, (uint32_t)n, st, &total));
+            bool again = false;
+            TRY(scan_emit(0, (uint32_t)n, st, &total, 0, 0, &again));
         }
     }
     CU(cudaGetLastError());
