@@ -71,6 +71,23 @@ __device__ __forceinline__ uint32_t first_rows_of_max(const uint32_t (&Y)[32], u
     return __vmaxs2(a, b);
 }
 
+// The same search restricted to the first vlo / vhi rows of the two blocks (the lanes that hold the end of the query):
+// {max of the low halves, max of the high halves, first row of each}. A real call on a copy of the registers: rare,
+// and inlined it costs the fill kernel 16 registers -- the room a traceback CTA needs next to it.
+__device__ __noinline__ uint4 masked_max_rows(const uint32_t* Y, uint32_t vlo, uint32_t vhi) {
+    int mlo = INT_MIN, mhi = INT_MIN;
+    for (uint32_t r = 0; r < 32; ++r) {
+        if (r < vlo) mlo = max(mlo, half_lo(Y[r]));
+        if (r < vhi) mhi = max(mhi, half_hi(Y[r]));
+    }
+    uint32_t rlo = 32, rhi = 32;
+    for (uint32_t r = 32; r-- > 0;) {
+        if (r < vlo && half_lo(Y[r]) == mlo) rlo = r;
+        if (r < vhi && half_hi(Y[r]) == mhi) rhi = r;
+    }
+    return make_uint4((uint32_t)mlo, (uint32_t)mhi, rlo, rhi);
+}
+
 // One stripe sweep: directions, boundary row, progress, end-cell candidates. Local alignments keep, per
 // 32-row block, the first cell in row-major order that attains the block's maximum (team_alignment.cpp:186-192:
 // the reference's running strict '>' keeps exactly that cell); the rows of a column are only searched when the
@@ -240,20 +257,14 @@ struct Sweep16 {
                             if (full && (cm & 0xffffu) != 0x8000u && (cm >> 16) != 0x8000u) {   // (-32768 has no packed negative)
                                 const uint32_t km = first_rows_of_max(Y, cm);
                                 rlo = 31u - (uint32_t)half_lo(km); rhi = 31u - (uint32_t)half_hi(km);
-                            } else {   // rows past Q may be in the tree: redo with masks
-                                mlo = INT_MIN; mhi = INT_MIN;
+                            } else {   // rows past Q may be in the tree: redo with masks (the lanes that hold the end of the query)
+                                uint32_t ycopy[R];
 #pragma unroll
-                                for (int r = 0; r < R; ++r) {
-                                    if ((uint32_t)r < vlo) mlo = max(mlo, half_lo(Y[r]));
-                                    if ((uint32_t)r < vhi) mhi = max(mhi, half_hi(Y[r]));
-                                }
+                                for (int r = 0; r < R; ++r) ycopy[r] = Y[r];
+                                const uint4 mr = masked_max_rows(ycopy, vlo, vhi);
+                                mlo = (int)mr.x; mhi = (int)mr.y; rlo = mr.z; rhi = mr.w;
                                 hlo = (alo && vlo) ? ((mlo + Blo - 1) >> 2) + gap * jlo : INT_MIN;
                                 hhi = (ahi && vhi) ? ((mhi + Bhi - 1) >> 2) + gap * (jlo - 1) : INT_MIN;
-#pragma unroll
-                                for (int r = R - 1; r >= 0; --r) {
-                                    if ((uint32_t)r < vlo && half_lo(Y[r]) == mlo) rlo = r;
-                                    if ((uint32_t)r < vhi && half_hi(Y[r]) == mhi) rhi = r;
-                                }
                             }
                             if (hlo != INT_MIN && (hlo > lbest_lo || (hlo == lbest_lo && i0 + 1 + rlo < bi_lo))) {
                                 lbest_lo = hlo; bi_lo = i0 + 1 + rlo; bj_lo = (uint32_t)jlo;
@@ -300,8 +311,9 @@ struct Sweep16 {
     }
 };
 
+// 152 registers: three fill CTAs and one traceback CTA (walk_tile_wait_kernel, 128 threads x 40) fit an SM together.
 template <int TYPE>
-__global__ void __launch_bounds__(128, 3)
+__global__ void __maxnreg__(152)
 fill_long16_kernel(const uint32_t* __restrict__ qpk, const uint32_t* __restrict__ tpk,
                    const PairDesc* __restrict__ pairs, const uint32_t* __restrict__ work, uint32_t n_work,
                    const uint32_t* __restrict__ task_off, const uint64_t* __restrict__ bnd_off,

@@ -826,12 +826,12 @@ static int launch_fill_long(b200_align_plan* p, const Wave& wv, const RunBufs& r
     const uint32_t* d_work = p->d_work.as<uint32_t>() + wv.first;
     if (p->long16) {
         const ShortConsts K16 = make_short_consts(p->sc, p->type);
-        // Global and semi-global waves with CIGARs: the walkers start with the fill and take each pair as soon as
-        // its last stripe is in (the traceback of the longest pairs no longer trails the whole wave). Local alignments
-        // could (the fill itself keeps the first maximum, so the end cell is known when the last stripe reports), but
-        // fill_long16_kernel<1> needs 168 registers: three of its CTAs leave no room on an SM for a walker CTA.
+        // Waves with CIGARs: the walkers start with the fill and take each pair as soon as its last stripe is in
+        // (the traceback of the longest pairs no longer trails the whole wave). Local alignments too: the fill
+        // itself keeps the first maximum, so the end cell is known when the last stripe reports. The fill is capped
+        // at 152 registers so that three of its CTAs leave room on an SM for a walker CTA.
         WaveSlot& ws = *rb.ws;
-        const bool cw = c->concurrent_walk && !c->profile && p->want_cigar && rb.dirs != nullptr && p->type != 1;
+        const bool cw = c->concurrent_walk && !c->profile && p->want_cigar && rb.dirs != nullptr;
         uint32_t *d_done = nullptr, *d_ready = nullptr;
         if (cw) {
             TRY(ws.pair_state.ensure(((size_t)wv.count + 8) * 8));

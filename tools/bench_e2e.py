@@ -17,7 +17,7 @@ hc, ho = torch.empty(cap, dtype=torch.uint8).pin_memory(), torch.empty(n + 1, dt
 def step():
     capi.check(L.b200_align_batch_packed(ctx.h, n, hq.data_ptr(), qo.ctypes.data, ht.data_ptr(), to.ctypes.data, 0, 1, -1, -1,
                                          hs.data_ptr(), hb.data_ptr(), hc.data_ptr(), ho.data_ptr(), cap))
-for chunk in (n, n // 2, n // 4, n // 8, n // 16):
+for chunk in (0, n // 4, 151552, n // 8, 98304, 75776, n // 16):
     ctx.set_option("chunk_pairs", chunk)
     for _ in range(3): step()
     ctx.set_option("profile", 1); ctx.set_option("reset_counters", 1)
