@@ -425,7 +425,7 @@ def main():
     # DRAM bytes of one fill launch from the committed `ncu --set full` capture of this kernel on this workload
     traffic = None
     try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")))
+        tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r01b.json")))
         if args.pairs == tr["fill_short_kernel"]["pairs"] and args.length == 150 and args.type == 0:
             traffic = tr["fill_short_kernel"]["dram_bytes_per_launch"]
     except Exception:
