@@ -23,6 +23,8 @@
 #include <functional>
 #include <iostream>
 #include <string>
+#include <atomic>
+#include <mutex>
 #include <thread>
 #include <unordered_map>
 #include <vector>
@@ -148,38 +150,69 @@ int map_slice(int device, const Options& o, const std::string& ref, const std::v
     b200_index* ix = nullptr;
     if (b200_index_build(ctx, ref.data(), ref.size(), o.k, o.w, o.f, &ix) != B200_OK) { err = b200_last_error(); b200_ctx_destroy(ctx); return 1; }
     if (trace) std::fprintf(stderr, "[b200_mapper trace] gpu %d: context %.3f s, index %.3f s\n", device, t1 - t0, now_s() - t1);
-    int rc = 0;
-    size_t i = lo;
-    while (i < hi && rc == 0) {
+    // Batches of bounded size, taken in turn by up to two workers. b200_map_batch is a blocking call on one context;
+    // with a second context (own streams and workspaces, the index shared) one batch's seeding, chaining, planning
+    // and downloads overlap the other's alignment kernels.
+    // (B200_MAPPER_BATCH_READS / B200_MAPPER_WORKERS: test knobs -- small batches, a single worker)
+    const char* env_batch = std::getenv("B200_MAPPER_BATCH_READS");
+    const char* env_workers = std::getenv("B200_MAPPER_WORKERS");
+    // A second context costs its own start-up (about half a second: tens of GB of workspace), so small inputs go
+    // through one context in large batches, as before; from 32 k reads on, batches of 8 k reads and two workers.
+    const bool small = hi - lo < 32768;
+    const size_t max_reads = env_batch && std::atol(env_batch) > 0 ? (size_t)std::atol(env_batch) : (small ? 65536 : 8192);
+    const uint64_t max_bases = small ? (256ull << 20) : (64ull << 20);
+    const int max_workers = env_workers && std::atoi(env_workers) > 0 ? std::atoi(env_workers) : (small ? 1 : 2);
+    std::vector<std::pair<size_t, size_t>> batches;
+    for (size_t i = lo; i < hi;) {
         size_t j = i; uint64_t bases = 0;
-        while (j < hi && j - i < 65536 && bases < (256ull << 20)) bases += reads[j++].seq.size();
-        std::string buf; buf.reserve(bases);
-        std::vector<uint64_t> off(j - i + 1, 0);
-        for (size_t r = i; r < j; ++r) { buf += reads[r].seq; off[r - i + 1] = buf.size(); }
-        std::vector<b200_mapping> m(j - i);
-        const uint64_t cap = o.cigar ? 4 * bases + 64 * (j - i) + 64 : 0;
-        std::vector<char> cig(cap ? cap : 1);
-        std::vector<uint64_t> coff(j - i + 1, 0);
-        const double tb0 = now_s();
-        const int e = b200_map_batch(ctx, ix, j - i, buf.data(), off.data(), fastq ? 1 : 0, o.type, o.match, o.mismatch, o.gap,
-                                     o.cigar ? 1 : 0, m.data(), o.cigar ? cig.data() : nullptr, o.cigar ? coff.data() : nullptr, cap);
-        if (trace) std::fprintf(stderr, "[b200_mapper trace] gpu %d: batch of %zu reads mapped in %.3f s\n", device, j - i, now_s() - tb0);
-        if (e != B200_OK) {
-            // the reference logs and skips a read whose Align throws (:680-683); a batch failure is fatal here
-            err = std::string("ERROR: Exception during Align: ") + b200_last_error();
-            rc = 1;
-            break;
-        }
-        for (size_t r = i; r < j; ++r) {
-            out[r].m = m[r - i];
-            if (o.cigar) out[r].cigar.assign(cig.data() + coff[r - i], cig.data() + coff[r - i + 1]);
-        }
+        while (j < hi && j - i < max_reads && bases < max_bases) bases += reads[j++].seq.size();
+        batches.emplace_back(i, j);
         i = j;
     }
+    std::atomic<size_t> next{0};
+    std::atomic<int> rc{0};
+    std::mutex err_mutex;
+    auto worker = [&](b200_ctx* wctx, int wi) {
+        for (;;) {
+            const size_t bi = next.fetch_add(1);
+            if (bi >= batches.size() || rc.load()) return;
+            const size_t i = batches[bi].first, j = batches[bi].second;
+            uint64_t bases = 0;
+            for (size_t r = i; r < j; ++r) bases += reads[r].seq.size();
+            std::string buf; buf.reserve(bases);
+            std::vector<uint64_t> off(j - i + 1, 0);
+            for (size_t r = i; r < j; ++r) { buf += reads[r].seq; off[r - i + 1] = buf.size(); }
+            std::vector<b200_mapping> m(j - i);
+            const uint64_t cap = o.cigar ? 4 * bases + 64 * (j - i) + 64 : 0;
+            std::vector<char> cig(cap ? cap : 1);
+            std::vector<uint64_t> coff(j - i + 1, 0);
+            const double tb0 = now_s();
+            const int e = b200_map_batch(wctx, ix, j - i, buf.data(), off.data(), fastq ? 1 : 0, o.type, o.match, o.mismatch, o.gap,
+                                         o.cigar ? 1 : 0, m.data(), o.cigar ? cig.data() : nullptr, o.cigar ? coff.data() : nullptr, cap);
+            if (trace) std::fprintf(stderr, "[b200_mapper trace] gpu %d worker %d: batch of %zu reads mapped in %.3f s\n", device, wi, j - i, now_s() - tb0);
+            if (e != B200_OK) {
+                // the reference logs and skips a read whose Align throws (:680-683); a batch failure is fatal here
+                std::lock_guard<std::mutex> g(err_mutex);
+                err = std::string("ERROR: Exception during Align: ") + b200_last_error();
+                rc.store(1);
+                return;
+            }
+            for (size_t r = i; r < j; ++r) {
+                out[r].m = m[r - i];
+                if (o.cigar) out[r].cigar.assign(cig.data() + coff[r - i], cig.data() + coff[r - i + 1]);
+            }
+        }
+    };
+    b200_ctx* ctx2 = nullptr;
+    if (batches.size() >= 2 && max_workers >= 2 && b200_ctx_create(device, &ctx2) != B200_OK) ctx2 = nullptr;   // one worker is still correct
+    std::thread second;
+    if (ctx2) second = std::thread(worker, ctx2, 1);
+    worker(ctx, 0);
+    if (second.joinable()) second.join();
     // The index and the context (tens of GB of device workspace) are deliberately not destroyed: the process is
     // about to exit, and returning that memory piece by piece costs about a second.
     (void)ix;
-    return rc;
+    return rc.load();
 }
 
 }  // namespace

@@ -108,3 +108,19 @@ def test_cli_statistics_go_to_stderr_and_two_gpus_option_is_accepted():
     with open(os.path.join(GOLD, "synth_fq_semi_c.paf"), "rb") as f:
         assert r.stdout == f.read()          # stdout carries PAF only
     assert b"N50 length" in r.stderr and b"Number of distinct minimizers" in r.stderr
+
+
+def test_cli_two_workers_over_small_batches_keep_the_output(monkeypatch):
+    """Batches of 3 reads taken in turn by two contexts / host threads: same bytes, same (input) order."""
+    import subprocess
+    exe = os.path.join(ROOT, "bioinfo1_b200", "b200_mapper")
+    argv = ["-a", "semiGlobal", "-c", "-f", "0", "ref.fa", "reads.fq"]
+    with open(os.path.join(GOLD, "synth_fq_semi_c.paf"), "rb") as f:
+        exp = f.read()
+    for workers in ("2", "1"):
+        env = dict(os.environ, B200_MAPPER_BATCH_READS="3", B200_MAPPER_WORKERS=workers, B200_TRACE="1")
+        r = subprocess.run([exe] + argv, cwd=GOLD, capture_output=True, timeout=300, env=env)
+        assert r.returncode == 0, r.stderr.decode(errors="replace")
+        assert r.stdout == exp
+        if workers == "2":
+            assert b"worker 1: batch of" in r.stderr      # the second context really took batches
