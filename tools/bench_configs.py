@@ -32,7 +32,7 @@ def main():
     ap.add_argument("--configs", default="c3,c4,c5")
     ap.add_argument("--reads", type=int, default=100_000)
     ap.add_argument("--pairs", type=int, default=10_000)
-    ap.add_argument("--batch", type=int, default=16384, help="reads per b200_map_batch / MinimizeBatch call")
+    ap.add_argument("--batch", type=int, default=8192, help="reads per b200_map_batch / MinimizeBatch call")
     ap.add_argument("--inflight", type=int, default=2, help="c4: batches in flight per GPU (contexts / host threads)")
     ap.add_argument("--cpu", action="store_true",
                     help="rank 0 also times the UNMODIFIED reference (oracle/_ref, one thread) on samples of each config "
