@@ -969,6 +969,7 @@ static int plan_run_impl(b200_align_plan* p, const char* d_q_buf, const char* d_
     if (!c->fork_event) CU(cudaEventCreateWithFlags(&c->fork_event, cudaEventDisableTiming));
     for (int k = 0; k < n_slots; ++k) {
         WaveSlot& ws = c->slot[k];
+        ws.walk_inflight = false;   // (a run that failed between a fill and its join must not leak into this one)
         TRY(ws.counter.ensure(128));
         if (!ws.done) CU(cudaEventCreateWithFlags(&ws.done, cudaEventDisableTiming));
         if (p->want_cigar) TRY(ws.dirs.ensure(std::max<uint64_t>(max_dir_words, 4) * 4 + 64));
