@@ -171,6 +171,32 @@ def test_short_kernel_uniform_150(ctx):
     _check_packed_vs_oracle(ctx, qb, qo, tb, to, 0, 1, -1, 1, 37)     # positive gap
 
 
+@pytest.mark.parametrize("typ", [0, 1, 2])
+def test_short_kernel_trimmed_last_block(ctx, typ):
+    """Uniform batches whose last row block is trimmed to 8 / 16 / 24 rows (and not at all): every pair against the
+    oracle's scores, a sample against its CIGARs."""
+    for length in (8, 40, 44, 50, 64, 90):
+        qb, qo, tb, to = seqgen.short_pairs(300 + length, 8192, length=length)
+        _check_packed_vs_oracle(ctx, qb, qo, tb, to, typ, 1, -1, -1, 211)
+
+
+def test_uniform_batch_with_flagged_pairs_goes_through_the_repair_pass(ctx):
+    """Uniform (device-built plan) K1 batch in which a few pairs are not pure ACGT: they are flagged, skipped by the wave
+    and repaired by the generic kernel; a clean batch right after must not see the patched descriptors."""
+    qb, qo, tb, to = seqgen.short_pairs(5150, 16384)
+    qb = qb.copy(); tb = tb.copy()
+    for k in (0, 63, 64, 777, 9000, 16383):
+        qb[int(qo[k]) + 7] = ord("N")
+    tb[int(to[4242]) + 3] = ord("-")
+    ctx.set_option("chunk_pairs", 4096)            # several waves, so the host path pipelines its downloads
+    try:
+        _check_packed_vs_oracle(ctx, qb, qo, tb, to, 0, 1, -1, -1, 97)
+        qb2, qo2, tb2, to2 = seqgen.short_pairs(5151, 16384)
+        _check_packed_vs_oracle(ctx, qb2, qo2, tb2, to2, 0, 1, -1, -1, 97)
+    finally:
+        ctx.set_option("chunk_pairs", 0)
+
+
 def test_short_kernel_ragged_lengths_and_fallback(ctx):
     rng = np.random.default_rng(77)
     n = 12000
