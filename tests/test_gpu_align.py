@@ -116,6 +116,27 @@ def test_multiple_waves_give_identical_results(ctx):
     assert one == many
 
 
+@pytest.mark.parametrize("typ", [0, 1, 2])
+def test_repair_pass_in_chunks_under_a_small_budget(ctx, typ):
+    """Long pairs that are not pure ACGT, with a direction budget of about one matrix: the flagged pairs of every wave are
+    repaired by the generic kernel in several chunks that reuse the first slot's buffer."""
+    rng = np.random.default_rng(4100 + typ)
+    qs, ts = [], []
+    for k in range(9):
+        t = seqgen.random_dna(rng, int(rng.integers(1500, 2300)))
+        q = seqgen.mutate(rng, t, sub=0.04, ins=0.03, dele=0.03)
+        if k % 3 != 1:
+            q = q.copy(); q[len(q) // 3] = ord("N-n"[k % 3])
+        qs.append(q.tobytes()); ts.append(t.tobytes())
+    ctx.set_option("dir_budget_bytes", 3 << 20)
+    try:
+        got = ctx.align(qs, ts, typ)
+    finally:
+        ctx.set_option("dir_budget_bytes", 48 << 30)
+    for q, t, g in zip(qs, ts, got):
+        assert g == ORACLE.align(q, t, typ), (typ, len(q), len(t))
+
+
 def test_pointer_array_entry_point_and_errors(ctx):
     from bioinfo1_b200 import capi
     qs = [b"GTACC", b"", b"ACG", b"TGACGTACATGGACA"]
