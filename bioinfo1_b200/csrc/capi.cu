@@ -127,6 +127,8 @@ struct b200_ctx {
     WaveSlot slot[2];
     cudaStream_t aux_stream = nullptr;      // second wave stream of a run
     cudaStream_t emit_stream = nullptr;     // host path: scan / emit / download of finished waves while later ones run
+    cudaStream_t pack_stream = nullptr;     // host path: 2-bit packing of a wave as soon as its bytes have landed
+    std::vector<cudaEvent_t> pack_done;     // one event per wave of the current run
     std::vector<cudaEvent_t> wave_done;     // one event per wave of the current run
     // B200_TRACE=2: device timeline of a run (events with timing, printed relative to the first)
     struct TlMark { std::string what; cudaEvent_t e; };
@@ -275,6 +277,8 @@ extern "C" void b200_ctx_destroy(b200_ctx* c) {
     for (auto e : c->event_pool) cudaEventDestroy(e);
     if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
     if (c->emit_stream) cudaStreamDestroy(c->emit_stream);
+    if (c->pack_stream) cudaStreamDestroy(c->pack_stream);
+    for (cudaEvent_t e : c->pack_done) cudaEventDestroy(e);
     for (auto e : c->wave_done) cudaEventDestroy(e);
     if (c->fork_event) cudaEventDestroy(c->fork_event);
     for (WaveSlot& w : c->slot) {
@@ -1019,6 +1023,19 @@ static int plan_run_impl(b200_align_plan* p, const char* d_q_buf, const char* d_
         }
     }
 
+    // When the host entry point pipelines the upload, the packing of a wave does not queue behind the traceback of the
+    // wave two before it (same stream): it runs on a stream of its own as soon as the wave's bytes are resident, and
+    // the wave's stream waits for it. The 2-bit copies and flags of different waves are disjoint.
+    const bool pack_ahead = overlap && !p->wave_events.empty();
+    if (pack_ahead) {
+        if (!c->pack_stream) CU(cudaStreamCreateWithFlags(&c->pack_stream, cudaStreamNonBlocking));
+        while (c->pack_done.size() < n_waves) {
+            cudaEvent_t e; CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            c->pack_done.push_back(e);
+        }
+        CU(cudaStreamWaitEvent(c->pack_stream, c->fork_event, 0));   // after the memsets queued on the caller's stream
+    }
+
     if (!ho) tl_mark(c, st, "start");
     // A wave = classify (+ 2-bit pack) -> fill -> traceback walk, in order on its stream; when the host entry
     // point pipelines the upload, wave k first waits for the event that marks its bytes as resident.
@@ -1029,22 +1046,27 @@ static int plan_run_impl(b200_align_plan* p, const char* d_q_buf, const char* d_
         RunBufs rb{reinterpret_cast<const uint8_t*>(d_q_buf), reinterpret_cast<const uint8_t*>(d_t_buf), nullptr, d_score, wst, &ws};
         uint32_t* d_nflag = c->wave_flagged.as<uint32_t>() + k;
         const uint32_t* work = p->d_work.as<uint32_t>() + wv.first;
-        if (k < p->wave_events.size() && p->wave_events[k]) CU(cudaStreamWaitEvent(wst, p->wave_events[k], 0));
-        prof_begin(c, wst, 3);
+        cudaStream_t pst = pack_ahead ? c->pack_stream : wst;
+        if (k < p->wave_events.size() && p->wave_events[k]) CU(cudaStreamWaitEvent(pst, p->wave_events[k], 0));
+        prof_begin(c, pst, 3);
         if (wv.klass != kClassGeneric) {
             const uint32_t wpp = std::max(1u, div_up(wv.klass == kClassLong ? std::max(p->max_Q, p->max_T)
                                                                            : std::max(p->max_Q_short, p->max_T_short), 16));
             dim3 grid((unsigned)div_up64((uint64_t)wv.count * wpp, 256), 2);
-            pack_kernel<<<grid, 256, 0, wst>>>(rb.dq, rb.dt, p->d_pairs.as<PairDesc>(), work, wv.count, wpp,
+            pack_kernel<<<grid, 256, 0, pst>>>(rb.dq, rb.dt, p->d_pairs.as<PairDesc>(), work, wv.count, wpp,
                                                c->flags.as<uint8_t>(), c->qpk.as<uint32_t>(), c->tpk.as<uint32_t>(), d_nflag);
         } else {
-            classify_kernel<<<(unsigned)div_up64((uint64_t)wv.count * 32, 256), 256, 0, wst>>>(
+            classify_kernel<<<(unsigned)div_up64((uint64_t)wv.count * 32, 256), 256, 0, pst>>>(
                 rb.dq, rb.dt, p->d_pairs.as<PairDesc>(), work, wv.count, c->flags.as<uint8_t>());
         }
-        prof_end(c, wst);
+        prof_end(c, pst);
         c->kernel_launches++;
+        tl_mark(c, pst, "pack" + std::to_string(k));
+        if (pack_ahead) {
+            CU(cudaEventRecord(c->pack_done[k], pst));
+            CU(cudaStreamWaitEvent(wst, c->pack_done[k], 0));
+        }
         rb.dirs = p->want_cigar ? ws.dirs.as<uint32_t>() : nullptr;
-        tl_mark(c, wst, "pack" + std::to_string(k));
         // in a wave of a 2-bit class a non-zero flag means "not this wave's pair"; in a generic wave the flags only
         // describe the content (classify_kernel) and every pair is the wave's own
         const uint8_t* skip = wv.klass != kClassGeneric ? c->flags.as<uint8_t>() : nullptr;
@@ -1167,6 +1189,7 @@ static int plan_run_impl(b200_align_plan* p, const char* d_q_buf, const char* d_
         CU(cudaStreamSynchronize(st));
         if (c->aux_stream) CU(cudaStreamSynchronize(c->aux_stream));
         if (c->emit_stream) CU(cudaStreamSynchronize(c->emit_stream));
+        if (c->pack_stream) CU(cudaStreamSynchronize(c->pack_stream));
         materialize_uniform_host(p);
         std::vector<uint8_t> h_flags(n);
         CU(cudaMemcpy(h_flags.data(), c->flags.p, n, cudaMemcpyDeviceToHost));
