@@ -18,7 +18,7 @@
 //   row 16k+x of the block sits at bits [2*(15-x), 2*(15-x)+1] as TAG (2 diag, 1 left, 0 up).
 // Each lane stores two columns at a time as one 16-byte vector.
 //
-// Eligibility (capi.cu): pure ACGT content (run-time flags; others fall back to the generic
+// Eligibility (align_plan.cu): pure ACGT content (run-time flags; others fall back to the generic
 // kernel), |4(s-gap)+1| <= 127. Local alignments take a second, one-stripe pass (locate_long_kernel).
 #pragma once
 #include "align_fill_short.cuh"
@@ -26,7 +26,6 @@
 
 namespace b200 {
 
-constexpr int kLongRows = 32;   // rows per lane
 
 struct LongConsts {
     uint32_t tab_diff, tab_mis;   // byte tables as in ShortConsts

@@ -18,7 +18,7 @@
 // Each (lane, half) block therefore keeps a private int32 base B (a multiple of 4, so the tag bits
 // survive) with register value = Y - B:
 //   * neighbouring cells differ by a bounded amount (gap <= dH <= max(gap, s_max - gap, 0) per step,
-//     see long16_scores_ok in capi.cu), so inside a 32-row block and over one 64-column chunk the
+//     see long16_scores_ok in align_plan.cu), so inside a 32-row block and over one 64-column chunk the
 //     values stay within a few thousand of each other;
 //   * at every chunk start a block re-centres itself on its row 0 (32 VIADD.16x2 per 64 columns);
 //   * values that cross blocks (the row above) are shifted by the difference of the two bases, in
@@ -39,9 +39,6 @@
 
 namespace b200 {
 
-constexpr int kL16LaneRows = 64;                     // query rows per lane (two blocks of 32)
-constexpr int kL16Stripe = kL16LaneRows * kWarp;     // 2048 rows per stripe
-constexpr int kL16Chunk = 64;                        // steps between progress publications / polls / re-centring
 
 // Y[r] for a warp-uniform r without 31 selects: a jump on r.
 #define B200_PICK4(k) case k: v = Y[k]; break; case k + 1: v = Y[k + 1]; break; case k + 2: v = Y[k + 2]; break; case k + 3: v = Y[k + 3]; break;
@@ -380,6 +377,11 @@ fill_long16_kernel(const uint32_t* __restrict__ qpk, const uint32_t* __restrict_
         const uint32_t rowj = TYPE == 1 ? rowj_l : __shfl_sync(kFull, sw.rowj, (int)lq);
         if (lane == 0) results[task] = StripeResult{colbest, coli, rowbest, rowj, final_h, located};
         if (ready != nullptr) {
+            // Every lane has written direction words of this stripe: each lane's own stores are made visible
+            // device-wide by its own fence, and the warp barrier orders all of them before lane 0's count / flag
+            // (shuffles are not memory barriers; a walker acquires `ready` and then reads those words).
+            __threadfence();
+            __syncwarp();
             if (lane == 0) {
                 __threadfence();                                           // this stripe's result before the count
                 if (atomicAdd(pair_done + k, 1u) + 1 == n_stripes) {       // every stripe of the pair has reported

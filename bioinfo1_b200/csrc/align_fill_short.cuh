@@ -22,15 +22,13 @@
 // maximum in row-major order (:186-192): a packed max tree per column gives the column maximum, and only
 // when it beats -- or, inside the same block, ties -- the running best are the rows scanned for the cell.
 //
-// Eligibility (decided on the host, capi.cu): both sequences pure ACGT, |s - gap| <= 31 for
+// Eligibility (decided on the host, align_plan.cu): both sequences pure ACGT, |s - gap| <= 31 for
 // s in {match, mismatch}, and 4 * ((Q+T+2) * max|score| + |gap| * T + 4) <= 32767 so nothing leaves int16.
 #pragma once
 #include "common.cuh"
 
 namespace b200 {
 
-constexpr int kShortRows = 32;       // rows per register block
-constexpr int kShortThreads = 64;    // 2 warps per CTA, every warp independent
 
 // Sequences packed 2 bits per base, 16 bases per word, base k of a word at bits [2k, 2k+1].
 // Codes: A=0 C=1 T=2 G=3. Pair p's query words start at PairDesc::qpk_off (see pack_kernel).
@@ -90,12 +88,6 @@ pack_kernel(const uint8_t* __restrict__ qbuf, const uint8_t* __restrict__ tbuf,
         if (((old >> (8 * (p & 3u))) & 0xffu) == 0) atomicAdd(n_flagged, 1u);
     }
 }
-
-struct ShortGroup {   // one per 64-pair group (one warp's worth of work)
-    uint64_t dir_off;  // word offset of the group's direction block inside the wave buffer
-    uint32_t cols;     // Tg: columns per row block = max T over the group
-    uint32_t pad;
-};
 
 struct ShortConsts {
     uint32_t tab_diff;    // (S'match ^ S'mismatch) in byte 0

@@ -51,7 +51,7 @@ walk_kernel(const PairDesc* __restrict__ pairs, const uint32_t* __restrict__ wor
     const uint32_t w = tid / spread;
     if (w >= n_work) return;
     const uint32_t p = work[w];
-    if (skip_flags && skip_flags[p]) return;   // not pure ACGT: filled and walked by the repair pass (capi.cu)
+    if (skip_flags && skip_flags[p]) return;   // not pure ACGT: filled and walked by the repair pass (align_run.cu)
     const PairDesc pd = pairs[p];
     const uint32_t Q = pd.Q, T = pd.T;
     uint32_t i = end_i[p], j = end_j[p];
@@ -277,7 +277,7 @@ walk_tile_kernel(const PairDesc* __restrict__ pairs, const uint32_t* __restrict_
 // Persistent walkers for the wave that is still being filled: warps take pairs in work order (largest first, the
 // order the fill hands its stripes out in), wait for the pair's ready flag -- raised by the fill warp that finished
 // the pair's last stripe -- and walk it while the fill goes on with the other pairs. Pairs the 2-bit fill does not
-// own (flags != 0) are skipped; they are walked after their fallback fill (the repair pass in capi.cu).
+// own (flags != 0) are skipped; they are walked after their fallback fill (the repair pass in align_run.cu).
 template <int TYPE>
 __global__ void __launch_bounds__(128)
 walk_tile_wait_kernel(const PairDesc* __restrict__ pairs, const uint32_t* __restrict__ work, uint32_t n_work,

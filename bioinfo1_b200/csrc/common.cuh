@@ -36,6 +36,20 @@ constexpr uint32_t kClassLong16 = 3;   // align_fill_long16.cuh layout: 4 words 
 constexpr uint8_t kFlagDash = 1;     // pair contains a '-' byte (free gap, team_alignment.cpp:25-28)
 constexpr uint8_t kFlagNonACGT = 2;  // pair contains a byte outside "ACGT"
 
+// Geometry of the fill kernels' register blocks and direction layouts (the planner sizes waves with them).
+constexpr int kShortRows = 32;                       // align_fill_short.cuh: rows per register block
+constexpr int kShortThreads = 64;                    //   2 warps per CTA, every warp independent
+constexpr int kLongRows = 32;                        // align_fill_long.cuh: rows per lane (stripe = 32 lanes x 32 rows)
+constexpr int kL16LaneRows = 64;                     // align_fill_long16.cuh: query rows per lane (two blocks of 32)
+constexpr int kL16Stripe = kL16LaneRows * kWarp;     //   2048 rows per stripe
+constexpr int kL16Chunk = 64;                        //   steps between progress publications / polls / re-centring
+
+struct ShortGroup {   // one per 64-pair group of the short class (one warp's worth of work)
+    uint64_t dir_off;  // word offset of the group's direction block inside the wave buffer
+    uint32_t cols;     // Tg: columns per row block = max T over the group
+    uint32_t pad;
+};
+
 struct Scores {
     int match, mismatch, gap;
 };

@@ -95,7 +95,11 @@ int b200_align_batch_packed(b200_ctx* ctx, size_t n,
  * cudaStream_t used as given (0 = the CUDA default stream). `d_target_begin`, `d_cigar`,
  * `d_cigar_off` may be NULL when the plan was created with want_cigar = 0.
  * On return the work is enqueued and, if want_cigar, the total CIGAR byte count has been
- * checked against cigar_cap (that check synchronises `stream` once). */
+ * checked against cigar_cap (that check synchronises `stream` once).
+ * `d_q_buf` / `d_t_buf`: the 2-bit packing pass reads whole aligned 32-bit words, so both buffers
+ * must be readable from the 4-byte boundary at or below their first byte to the 4-byte boundary at
+ * or above their last byte (any cudaMalloc'ed or framework-allocated buffer is; a sub-allocation
+ * cut at an odd byte inside a larger buffer is too, as long as the neighbouring bytes are mapped). */
 int b200_align_plan_create(b200_ctx* ctx, size_t n, const uint64_t* q_off, const uint64_t* t_off,
                            int type, int match, int mismatch, int gap, int want_cigar,
                            b200_align_plan** out);
