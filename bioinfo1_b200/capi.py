@@ -186,19 +186,32 @@ class Index:
             lib().b200_index_destroy(self.h)
             self.h = C.c_void_p()
 
+    def map_packed(self, buf, off, fastq_semantics=True, typ=0, match=1, mismatch=-1, gap=-1, want_cigar=True,
+                   ctx=None, out=None, cig=None, coff=None):
+        """Packed reads (uint8 buffer + uint64 offsets[n+1]) -> (MAPPING_DTYPE array, cigar bytes, cigar_off).
+        `ctx` may be another context of the same device (two batches in flight share one index); the result
+        arrays may be passed in to be reused."""
+        n = len(off) - 1
+        if out is None:
+            out = np.zeros(max(n, 1), dtype=MAPPING_DTYPE)
+        cap = int(2 * (int(off[n] - off[0]) + n) + 64) * 2 if want_cigar else 0
+        if want_cigar and (cig is None or len(cig) < cap):
+            cig = np.empty(max(cap, 1), dtype=np.uint8)
+        if want_cigar and coff is None:
+            coff = np.zeros(n + 1, dtype=np.uint64)
+        check(lib().b200_map_batch((ctx or self.ctx).h, self.h, n, buf.ctypes.data, off.ctypes.data,
+                                   1 if fastq_semantics else 0, typ, match, mismatch, gap, 1 if want_cigar else 0,
+                                   out.ctypes.data, cig.ctypes.data if want_cigar else None,
+                                   coff.ctypes.data if want_cigar else None, len(cig) if want_cigar else 0))
+        return out[:n], (cig if want_cigar else None), (coff if want_cigar else None)
+
     def map_batch(self, reads, fastq_semantics=True, typ=0, match=1, mismatch=-1, gap=-1, want_cigar=True):
         """list of bytes -> (structured array of MAPPING_DTYPE, list of cigar bytes | None)"""
         buf, off = pack(reads)
         n = len(reads)
-        out = np.zeros(max(n, 1), dtype=MAPPING_DTYPE)
-        cap = int(2 * (int(off[-1]) + n) + 64) * 2 if want_cigar else 0
-        cig = np.empty(max(cap, 1), dtype=np.uint8)
-        coff = np.zeros(n + 1, dtype=np.uint64)
-        check(lib().b200_map_batch(self.ctx.h, self.h, n, buf.ctypes.data, off.ctypes.data, 1 if fastq_semantics else 0,
-                                   typ, match, mismatch, gap, 1 if want_cigar else 0, out.ctypes.data,
-                                   cig.ctypes.data if want_cigar else None, coff.ctypes.data if want_cigar else None, cap))
+        out, cig, coff = self.map_packed(buf, off, fastq_semantics, typ, match, mismatch, gap, want_cigar)
         cigs = [bytes(cig[int(coff[i]):int(coff[i + 1])]) for i in range(n)] if want_cigar else None
-        return out[:n], cigs
+        return out, cigs
 
 
 def align_batch_pointers(device, queries, targets, typ, match=1, mismatch=-1, gap=-1, want_cigar=True):

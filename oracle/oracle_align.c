@@ -184,3 +184,24 @@ int64_t oracle_align_batch(uint64_t n, const char* qbuf, const uint64_t* qoff, c
     if (cigar_bytes) *cigar_bytes = bytes;
     return (int64_t)n;
 }
+
+/* Same batch with every output kept: CIGAR texts are written back to back into cigar_buf and cigar_off[i] /
+ * cigar_off[i+1] bracket pair i's bytes (relative to this call's first byte). Returns n, -2 when cigar_cap is
+ * too small, or oracle_align's error code. Re-entrant (tests run one call per host thread on disjoint slices). */
+int64_t oracle_align_batch_cigar(uint64_t n, const char* qbuf, const uint64_t* qoff, const char* tbuf,
+                                 const uint64_t* toff, int type, int match, int mismatch, int gap,
+                                 int32_t* score, uint32_t* target_begin, char* cigar_buf, uint64_t cigar_cap,
+                                 uint64_t* cigar_off) {
+    uint64_t at = 0;
+    cigar_off[0] = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+        const uint64_t ql = qoff[i + 1] - qoff[i], tl = toff[i + 1] - toff[i];
+        uint64_t len = 0;
+        int rc = oracle_align(qbuf + qoff[i], (uint32_t)ql, tbuf + toff[i], (uint32_t)tl, type, match, mismatch,
+                              gap, 1, &score[i], &target_begin[i], cigar_buf + at, cigar_cap - at, &len);
+        if (rc) return rc;
+        at += len;
+        cigar_off[i + 1] = at;
+    }
+    return (int64_t)n;
+}

@@ -62,3 +62,25 @@ int64_t oracle_minimize(const char* seq, uint32_t len, uint32_t k, uint32_t w, i
     free(h);
     return (int64_t)o;
 }
+
+/* Packed batch: tuples of sequence i at out_off[i] .. out_off[i+1]. Returns the tuple total, -2 when cap is too
+ * small (out_off is still filled), -3 out of memory. The sequence buffer is read only inside each sequence. */
+int64_t oracle_minimize_batch(uint64_t n, const char* buf, const uint64_t* off, uint32_t k, uint32_t w, int is_fwd,
+                              uint32_t* hash, uint32_t* pos, uint8_t* flag, uint64_t cap, uint64_t* out_off) {
+    uint64_t at = 0;
+    int over = 0;
+    out_off[0] = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+        const uint32_t len = (uint32_t)(off[i + 1] - off[i]);
+        const int64_t cnt = oracle_minimize(buf + off[i], len, k, w, is_fwd, 0, 0, 0, 0);
+        if (cnt < 0) return cnt;
+        if (at + (uint64_t)cnt > cap) over = 1;
+        if (!over && cnt) {
+            const int64_t c2 = oracle_minimize(buf + off[i], len, k, w, is_fwd, hash + at, pos + at, flag + at, (uint64_t)cnt);
+            if (c2 != cnt) return -3;
+        }
+        at += (uint64_t)cnt;
+        out_off[i + 1] = at;
+    }
+    return over ? -2 : (int64_t)at;
+}

@@ -33,7 +33,73 @@ class _Checker:
         self._align_batch.restype = C.c_int64
         self._align_batch.argtypes = [C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                       C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
+        self._align_batch_cigar = getattr(self.lib, prefix + "_align_batch_cigar")
+        self._align_batch_cigar.restype = C.c_int64
+        self._align_batch_cigar.argtypes = [C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                            C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+        self._minimize_batch = getattr(self.lib, prefix + "_minimize_batch")
+        self._minimize_batch.restype = C.c_int64
+        self._minimize_batch.argtypes = [C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int,
+                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
         self.kind = "reference" if prefix == "ref" else "port"
+
+    def align_batch_full(self, qbuf, qoff, tbuf, toff, typ, match=1, mismatch=-1, gap=-1, threads=1):
+        """Packed numpy buffers -> (score[], target_begin[], cigar bytes (uint8[]), cigar_off[n+1]) with every
+        CIGAR kept; the batch is cut into one slice per thread (Align is re-entrant; calls release the GIL)."""
+        import threading
+        import numpy as np
+        n = len(qoff) - 1
+        score = np.empty(max(n, 1), dtype=np.int32)
+        tb = np.empty(max(n, 1), dtype=np.uint32)
+        threads = max(1, min(threads, n)) if n else 1
+        cuts = [n * k // threads for k in range(threads + 1)]
+        parts = [None] * threads
+        err = []
+
+        def work(k):
+            a, b = cuts[k], cuts[k + 1]
+            ql = qoff[a:b + 1]
+            tl = toff[a:b + 1]
+            cap = int(2 * ((ql[-1] - ql[0]) + (tl[-1] - tl[0])) + 16 * (b - a) + 64)
+            buf = np.empty(cap, dtype=np.uint8)
+            off = np.zeros(b - a + 1, dtype=np.uint64)
+            rc = self._align_batch_cigar(b - a, qbuf.ctypes.data, ql.ctypes.data, tbuf.ctypes.data, tl.ctypes.data, typ,
+                                         match, mismatch, gap, score.ctypes.data + 4 * a, tb.ctypes.data + 4 * a,
+                                         buf.ctypes.data, cap, off.ctypes.data)
+            if rc != b - a:
+                err.append(rc)
+            parts[k] = (buf, off)
+        th = [threading.Thread(target=work, args=(k,)) for k in range(threads)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        if err:
+            raise ValueError(f"align_batch_cigar rc={err[0]}")
+        coff = np.zeros(n + 1, dtype=np.uint64)
+        base = 0
+        for k in range(threads):
+            a, b = cuts[k], cuts[k + 1]
+            coff[a + 1:b + 1] = parts[k][1][1:] + np.uint64(base)
+            base += int(parts[k][1][-1])
+        cig = np.concatenate([parts[k][0][:int(parts[k][1][-1])] for k in range(threads)]) if n else np.zeros(0, np.uint8)
+        return score[:n], tb[:n], cig, coff
+
+    def minimize_batch(self, buf, off, k, w, is_fwd=True):
+        """Packed sequences -> (hash[], pos[], flag[], out_off[n+1]); single thread (the reference's Minimize keeps
+        process-global state). `buf` must be readable a few bytes past every sequence (callers pass packed buffers)."""
+        import numpy as np
+        n = len(off) - 1
+        cap = int(sum(int(off[i + 1] - off[i]) + w for i in range(n))) + 8
+        h = np.empty(cap, dtype=np.uint32)
+        p = np.empty(cap, dtype=np.uint32)
+        f = np.empty(cap, dtype=np.uint8)
+        oo = np.zeros(n + 1, dtype=np.uint64)
+        tot = self._minimize_batch(n, buf.ctypes.data, off.ctypes.data, k, w, 1 if is_fwd else 0, h.ctypes.data,
+                                   p.ctypes.data, f.ctypes.data, cap, oo.ctypes.data)
+        if tot < 0:
+            raise ValueError(f"minimize_batch rc={tot}")
+        return h[:tot], p[:tot], f[:tot], oo
 
     def align_batch(self, qbuf, qoff, tbuf, toff, typ, match=1, mismatch=-1, gap=-1, want_cigar=True):
         """Packed numpy buffers -> (score[], target_begin[], total cigar bytes); releases the GIL."""
