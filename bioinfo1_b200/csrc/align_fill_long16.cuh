@@ -90,8 +90,9 @@ __device__ __noinline__ uint4 masked_max_rows(const uint32_t* Y, uint32_t vlo, u
 // the reference's running strict '>' keeps exactly that cell); the rows of a column are only searched when the
 // column maximum reaches the warp-wide running maximum `thr` (refreshed every chunk) -- a cell below it cannot
 // be the stripe's maximum -- so off-diagonal blocks pay nothing and no second pass is needed.
-template <int TYPE>
+template <int TYPE, int SUB>   // SUB as in align_fill_short.cuh: 1 = substitution term from the shared-memory table
 struct Sweep16 {
+    uint32_t tab_at;     // SUB = 1: shared address of the lane's column of the substitution table
     // inputs
     const uint32_t* qw; const uint32_t* tw_base;
     uint32_t Q, T, s, lanes_used;
@@ -135,13 +136,15 @@ struct Sweep16 {
             for (int r = 0; r < R; ++r) {
                 const uint32_t ca = ((r < 16 ? a0 : a1) >> (2 * (r & 15))) & 3u;
                 const uint32_t cb = ((r < 16 ? b0 : b1) >> (2 * (r & 15))) & 3u;
-                sel[r] = ca | ((8u + ca) << 4) | ((4u + cb) << 8) | ((12u + cb) << 12);
+                sel[r] = SUB ? tab_at + subst_row_part(ca, cb)
+                             : ca | ((8u + ca) << 4) | ((4u + cb) << 8) | ((12u + cb) << 12);
                 Y[r] = dup16(4 * (r + 1) * init + 1);   // column 0, relative to the block's base
             }
         }
         uint32_t up_prev = dup16(1);                      // Y(i0, 0) - Blo (the high half is set by the first step)
         uint32_t tw = 0, tw_next = lane_on ? tw_base[0] : 0u;
         uint32_t tabB = 0;                                // the previous step's low table = this step's high table
+        uint32_t c_prev = 0;                              // SUB = 1: the previous step's column code (the high block's column)
 
         int nxt0 = 0, nxt1 = 0, cur0 = 0, cur1 = 0;
         auto wait_for = [&](uint32_t need) {   // stripe above has published at least `need` columns
@@ -216,7 +219,8 @@ struct Sweep16 {
                     if (((jlo - 1) & 15) == 0) { tw = tw_next; tw_next = tw_base[((jlo - 1) >> 4) + 1]; }
                     const uint32_t c = tw & 3u;
                     tw >>= 2;
-                    const uint32_t tabA = K.tab_mis ^ (K.tab_diff << (8 * c));
+                    const uint32_t tabA = SUB ? subst_col_part(c, c_prev) : K.tab_mis ^ (K.tab_diff << (8 * c));
+                    if (SUB) tabB = K.one32;
                     uint32_t up = fa, dg = up_prev;
                     up_prev = fa;
                     uint32_t clampv = 0;
@@ -228,7 +232,7 @@ struct Sweep16 {
                     uint32_t accZ = 0, accY = 0, w[4];
 #pragma unroll
                     for (int r = 0; r < R; ++r) {
-                        const uint32_t S = prmt(tabA, tabB, sel[r]);
+                        const uint32_t S = SUB ? subst_lookup(sel[r], tabA, tabB) : prmt(tabA, tabB, sel[r]);
                         const uint32_t m1 = __viaddmax_s16x2(dg, S, Y[r]);
                         uint32_t Z = __viaddmax_s16x2(up, K.cu, m1);
                         if (TYPE == 1) Z = __vmaxs2(Z, clampv);   // clamp at 0 (team_alignment.cpp:185), tag 3 = stop
@@ -239,7 +243,7 @@ struct Sweep16 {
                         accY = accY * FOUR + Y[r];
                         if ((r & 7) == 7) { w[r >> 3] = accZ - accY + 0x55555555u; accZ = 0; accY = 0; }
                     }
-                    tabB = tabA;
+                    if (SUB) c_prev = c; else tabB = tabA;
                     if (lane == kWarp - 1 && !last_stripe && ahi) __stcg(row_out + (jlo - 1), half_hi(Y[R - 1]) + Bhi);
                     if (drow) __stcs(reinterpret_cast<uint4*>(drow + (uint64_t)(jlo - 1) * 4), make_uint4(w[0], w[1], w[2], w[3]));
                     if (TYPE == 1) {
@@ -309,7 +313,7 @@ struct Sweep16 {
 };
 
 // 152 registers: three fill CTAs and one traceback CTA (walk_tile_wait_kernel, 128 threads x 40) fit an SM together.
-template <int TYPE>
+template <int TYPE, int SUB>
 __global__ void __maxnreg__(152)
 fill_long16_kernel(const uint32_t* __restrict__ qpk, const uint32_t* __restrict__ tpk,
                    const PairDesc* __restrict__ pairs, const uint32_t* __restrict__ work, uint32_t n_work,
@@ -322,6 +326,13 @@ fill_long16_kernel(const uint32_t* __restrict__ qpk, const uint32_t* __restrict_
                    uint32_t* pair_done, uint32_t* ready, int32_t* score, uint32_t* end_i, uint32_t* end_j) {
     const int lane = threadIdx.x & 31;
     const uint32_t n_tasks = task_off[n_work];
+    uint32_t tab_at = 0;
+    if (SUB) {
+        __shared__ uint32_t subst_tab[kSubstWords];
+        subst_table_fill(subst_tab, K, threadIdx.x, blockDim.x);
+        __syncthreads();
+        tab_at = (uint32_t)__cvta_generic_to_shared(subst_tab) + (uint32_t)lane * 4u;
+    }
     for (;;) {
         uint32_t task = 0;
         if (lane == 0) task = atomicAdd(work_counter, 1u);
@@ -334,7 +345,8 @@ fill_long16_kernel(const uint32_t* __restrict__ qpk, const uint32_t* __restrict_
         const uint32_t p = work[k];
         if (flags[p]) continue;   // not pure ACGT: the generic kernel owns the whole pair
         const PairDesc pd = pairs[p];
-        Sweep16<TYPE> sw;
+        Sweep16<TYPE, SUB> sw;
+        sw.tab_at = tab_at;
         sw.qw = qpk + pd.qpk_off; sw.tw_base = tpk + pd.tpk_off;
         sw.Q = pd.Q; sw.T = pd.T; sw.s = s;
         const uint32_t n_stripes = div_up(pd.Q, kL16Stripe);

@@ -97,7 +97,41 @@ struct ShortConsts {
     // immediate, and a literal multiplier of 4 would be strength-reduced onto the (saturated) alu pipe.
     uint32_t mask, one, four;
     int gap, init;
+    // substitution terms as int16 (both halves of a table word are built from them) and an opaque 1 for the
+    // address multiply-add of the shared-memory lookup (see SubstTable)
+    int sm, sx;
+    uint32_t one32;
 };
+
+// Substitution term from shared memory instead of PRMT (PRMT issues at half rate on the saturated alu pipe: 2 of
+// the 5 alu slots a cell pair costs; the LSU pipe is idle). A table word holds both halves' terms; it is indexed
+// by the two row codes (a per-register constant) PLUS the two column codes (one value per column): with
+// ia = qa + ((4 - ca) & 3) in 0..6, equality of the 2-bit codes is (ia & 3) == 0, so
+//     index = ia | ib << 3        = (qa | qb << 3) + (((4 - ca) & 3) | ((4 - cb) & 3) << 3)
+// is a plain sum of a row part and a column part (one IMAD on the fma pipe) and the table has 64 entries.
+// Every entry is replicated per lane (word = tab[index * 32 + lane]), so a warp's 32 lookups hit 32 different
+// banks whatever their indices: 8 KB per CTA, conflict-free.
+constexpr int kSubstEntries = 64;
+constexpr int kSubstWords = kSubstEntries * kWarp;
+
+__device__ __forceinline__ void subst_table_fill(uint32_t* tab, const ShortConsts& K, int tid, int nthreads) {
+    for (int e = tid; e < kSubstWords; e += nthreads) {
+        const uint32_t idx = (uint32_t)e >> 5, ia = idx & 7u, ib = idx >> 3;
+        const int lo = (ia & 3u) == 0u ? K.sm : K.sx, hi = (ib & 3u) == 0u ? K.sm : K.sx;
+        tab[e] = ((uint32_t)hi << 16) | ((uint32_t)lo & 0xffffu);
+    }
+}
+__device__ __forceinline__ uint32_t subst_row_part(uint32_t qa, uint32_t qb) { return (qa | (qb << 3)) << 7; }
+__device__ __forceinline__ uint32_t subst_col_part(uint32_t ca, uint32_t cb) { return (((4u - ca) & 3u) | (((4u - cb) & 3u) << 3)) << 7; }
+// row part (already holding the table's shared address and the lane's byte offset) + column part -> table word.
+// The add is written as a multiply-add with an opaque 1 so that it issues on the fma pipe; the load is a plain
+// (non-volatile) asm: the table never changes after the CTA's first barrier, the scheduler may hoist it freely.
+__device__ __forceinline__ uint32_t subst_lookup(uint32_t row_part, uint32_t col_part, uint32_t one32) {
+    uint32_t addr, v;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(addr) : "r"(row_part), "r"(one32), "r"(col_part));
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
 
 __host__ __device__ inline uint32_t dup16(int v) { return ((uint32_t)(uint16_t)(int16_t)v) * 0x10001u; }
 
@@ -110,6 +144,7 @@ __host__ inline ShortConsts make_short_consts(const Scores& sc, int type) {
     k.mask = 0xfffcfffcu; k.one = 0x00010001u; k.four = 4u;
     k.gap = sc.gap;
     k.init = (type == 0) ? sc.gap : 0;
+    k.sm = sm; k.sx = sx; k.one32 = 1u;
     return k;
 }
 
@@ -182,8 +217,9 @@ __device__ __forceinline__ uint32_t max_tree16(const uint32_t (&Y)[N]) {
 // (8, 16, 24 or 32) register rows over every column. Blocks are 32 rows apart whatever RB is: only the LAST
 // block of a group is trimmed (150-row pairs: 4 x 32 + 24 rows instead of 5 x 32), its unused direction words
 // are stored as zeros and never read (the walker only visits rows <= Q).
-template <int TYPE>
+template <int TYPE, int SUB>   // SUB: 0 = substitution term by PRMT, 1 = by shared-memory lookup (SubstTable)
 struct ShortSweep {
+    uint32_t tab_at;       // SUB = 1: shared address of the lane's column of the substitution table
     // the thread's two pairs
     uint32_t QA, TA, QB, TB;
     const uint32_t *qwA, *twA, *qwB, *twB;
@@ -224,7 +260,8 @@ struct ShortSweep {
             for (int r = 0; r < RB; ++r) {
                 const uint32_t ca = ((r < 16 ? qa0 : qa1) >> (2 * (r & 15))) & 3u;
                 const uint32_t cb = ((r < 16 ? qb0 : qb1) >> (2 * (r & 15))) & 3u;
-                sel[r] = ca | ((8u + ca) << 4) | ((4u + cb) << 8) | ((12u + cb) << 12);
+                sel[r] = SUB ? tab_at + subst_row_part(ca, cb)
+                             : ca | ((8u + ca) << 4) | ((4u + cb) << 8) | ((12u + cb) << 12);
                 Y[r] = dup16(4 * (int)((i0 + 1 + r) * (uint32_t)K.init) + 1);   // column 0, frame 0
             }
         }
@@ -255,9 +292,10 @@ struct ShortSweep {
             }
             const uint32_t cA = tA & 3u, cB = tB & 3u;
             tA >>= 2; tB >>= 2;
-            // per-column byte tables: entry c = S'(c, target) (match where c == target code)
-            const uint32_t tabA = K.tab_mis ^ (K.tab_diff << (8 * cA));
-            const uint32_t tabB = K.tab_mis ^ (K.tab_diff << (8 * cB));
+            // per-column byte tables: entry c = S'(c, target) (match where c == target code); or the column part
+            // of the shared-memory table index
+            const uint32_t tabA = SUB ? subst_col_part(cA, cB) : K.tab_mis ^ (K.tab_diff << (8 * cA));
+            const uint32_t tabB = SUB ? K.one32 : K.tab_mis ^ (K.tab_diff << (8 * cB));
             const uint32_t top = top_next;
             top_next = top_next2;
             if (j + 2 <= Tm) top_next2 = (b == 0) ? dup16(frame * (int)(j + 2) + 1) : my_bnd[(size_t)(j + 2) * kWarp];
@@ -268,7 +306,7 @@ struct ShortSweep {
             const uint32_t clampv = dup16(3 - 4 * K.gap * (int)j);   // local: H = 0 with the stop tag, this column's frame
 #pragma unroll
             for (int r = 0; r < RB; ++r) {
-                const uint32_t S = prmt(tabA, tabB, sel[r]);
+                const uint32_t S = SUB ? subst_lookup(sel[r], tabA, tabB) : prmt(tabA, tabB, sel[r]);
                 const uint32_t m1 = __viaddmax_s16x2(dg, S, Y[r]);
                 uint32_t Z = __viaddmax_s16x2(up, K.cu, m1);
                 if (TYPE == 1) Z = __vmaxs2(Z, clampv);   // clamp at 0 (team_alignment.cpp:185), tag 3 = stop
@@ -344,15 +382,15 @@ struct ShortSweep {
 
 // The trimmed variants are real calls: inlined next to the 32-row loop they cost that loop its register
 // allocation (measured: -8 % on every block); a call per group is free.
-template <int TYPE, int RB>
-__device__ __noinline__ void short_block_trimmed(ShortSweep<TYPE>* sw, const ShortConsts* K, uint32_t b) {
-    ShortSweep<TYPE> s = *sw;   // by value: nothing the loop reads may alias its stores
+template <int TYPE, int SUB, int RB>
+__device__ __noinline__ void short_block_trimmed(ShortSweep<TYPE, SUB>* sw, const ShortConsts* K, uint32_t b) {
+    ShortSweep<TYPE, SUB> s = *sw;   // by value: nothing the loop reads may alias its stores
     const ShortConsts k = *K;
     s.template block<RB>(k, b);
     *sw = s;
 }
 
-template <int TYPE>
+template <int TYPE, int SUB>
 __global__ void __launch_bounds__(kShortThreads, 7)
 fill_short_kernel(const uint32_t* __restrict__ qpk, const uint32_t* __restrict__ tpk,
                   const PairDesc* __restrict__ pairs, const uint32_t* __restrict__ work, uint32_t n_work,
@@ -364,8 +402,15 @@ fill_short_kernel(const uint32_t* __restrict__ qpk, const uint32_t* __restrict__
     const int lane = threadIdx.x & 31;
     const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t n_groups = (n_work + 63) / 64;
-    ShortSweep<TYPE> sw;
+    ShortSweep<TYPE, SUB> sw;
     sw.my_bnd = bnd + (size_t)warp_global * bnd_cols * kWarp + lane;   // [col][lane]
+    sw.tab_at = 0;
+    if (SUB) {
+        __shared__ uint32_t subst_tab[kSubstWords];
+        subst_table_fill(subst_tab, K, threadIdx.x, kShortThreads);
+        __syncthreads();
+        sw.tab_at = (uint32_t)__cvta_generic_to_shared(subst_tab) + (uint32_t)lane * 4u;
+    }
 
     for (;;) {
         uint32_t g = 0;
@@ -407,9 +452,9 @@ fill_short_kernel(const uint32_t* __restrict__ qpk, const uint32_t* __restrict__
 
         for (uint32_t b = 0; b < sw.n_blocks; ++b) {
             if (b + 1 < nbg || last_rows == 32u) sw.template block<32>(K, b);
-            else if (last_rows == 24u) short_block_trimmed<TYPE, 24>(&sw, &K, b);
-            else if (last_rows == 16u) short_block_trimmed<TYPE, 16>(&sw, &K, b);
-            else short_block_trimmed<TYPE, 8>(&sw, &K, b);
+            else if (last_rows == 24u) short_block_trimmed<TYPE, SUB, 24>(&sw, &K, b);
+            else if (last_rows == 16u) short_block_trimmed<TYPE, SUB, 16>(&sw, &K, b);
+            else short_block_trimmed<TYPE, SUB, 8>(&sw, &K, b);
         }
         if (TYPE == 0) {
             if (pA != 0xffffffffu) {

@@ -4,47 +4,65 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
+#include <atomic>
+#include <functional>
 #include <new>
+#include <thread>
+#include <vector>
 
 #include "internal.hpp"
 
 using namespace b200;
 
-extern "C" int b200_align_batch_packed(b200_ctx* c, size_t n, const char* q_buf, const uint64_t* q_off,
-                                       const char* t_buf, const uint64_t* t_off, int type, int match,
-                                       int mismatch, int gap, int32_t* score, uint32_t* target_begin,
-                                       char* cigar_buf, uint64_t* cigar_off, uint64_t cigar_cap) {
-    if (!c) return fail(B200_E_ARG, "null context");
-    if (type < 0 || type > 2) return fail(B200_E_TYPE, "Unknown AlignmentType provided.");
-    if (n && (!q_off || !t_off || !score)) return fail(B200_E_ARG, "null argument");
+// Where the packed sequence bytes of a host-buffer call come from. The packed entry point's bytes are simply there;
+// the pointer-array entry point gathers them into pinned staging with a few threads while earlier slices are already
+// on their way to the device, and `wait` blocks until a prefix of the bytes is in place.
+struct HostSource {
+    const char* q = nullptr;
+    const char* t = nullptr;
+    std::function<int(uint64_t q_end, uint64_t t_end)> wait;   // optional; returns B200_OK or the producer's error
+};
+
+static int align_batch_host(b200_ctx* c, size_t n, const HostSource& src, const uint64_t* q_off, const uint64_t* t_off,
+                            int type, int match, int mismatch, int gap, int32_t* score, uint32_t* target_begin,
+                            char* cigar_buf, uint64_t* cigar_off, uint64_t cigar_cap) {
     const bool want_cigar = cigar_off != nullptr;
-    if (want_cigar && !cigar_buf && cigar_cap) return fail(B200_E_ARG, "cigar_buf is null");
-    if (n == 0) { if (cigar_off) cigar_off[0] = 0; return B200_OK; }
     TRY(set_device(c));
     // rebase offsets so that only the referenced byte ranges are copied
     const uint64_t q0 = q_off[0], q1 = q_off[n], t0 = t_off[0], t1 = t_off[n];
-    if (((q1 > q0) && !q_buf) || ((t1 > t0) && !t_buf)) return fail(B200_E_ARG, "null sequence buffer");
+    if (((q1 > q0) && !src.q) || ((t1 > t0) && !src.t)) return fail(B200_E_ARG, "null sequence buffer");
     PhaseTrace tr;
-    // Start the sequence upload first, in kPipe byte slices on a separate copy stream with an event after
-    // each slice: the host-side planning below overlaps the DMA, and the plan's waves (for uniform batches,
-    // equal chunks of pairs) start as soon as the slice holding their last byte has landed.
+    // Start the sequence upload first, in byte slices on a separate copy stream with an event after each slice: the
+    // host-side planning below overlaps the DMA, and the plan's waves start as soon as the slice holding their last
+    // byte has landed. The first half goes in kHead equal slices before the plan exists; the second half is cut where
+    // the plan's waves end (uniform batches), so that no wave waits for bytes it does not need.
     TRY(c->d_q.ensure(q1 - q0 + 64));
     TRY(c->d_t.ensure(t1 - t0 + 64));
     cudaStream_t st = c->stream;
-    constexpr int kPipe = 16;
+    constexpr int kHead = 8, kSlices = 16;
     if (!c->copy_stream) CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-    while (c->copy_events.size() < (size_t)kPipe) {
-        cudaEvent_t e; CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        c->copy_events.push_back(e);
-    }
     const uint64_t qn = q1 - q0, tn = t1 - t0;
+    struct Cut { uint64_t q_end, t_end; };
+    std::vector<Cut> cuts;   // cuts[s] = bytes resident once copy_events[s] has fired
+    auto upload_to = [&](uint64_t q_end, uint64_t t_end) -> int {
+        const uint64_t qa = cuts.empty() ? 0 : cuts.back().q_end, ta = cuts.empty() ? 0 : cuts.back().t_end;
+        q_end = std::min(std::max(q_end, qa), qn); t_end = std::min(std::max(t_end, ta), tn);
+        if (src.wait) TRY(src.wait(q_end, t_end));
+        if (q_end > qa) CU(cudaMemcpyAsync(c->d_q.as<char>() + qa, src.q + q0 + qa, q_end - qa, cudaMemcpyHostToDevice, c->copy_stream));
+        if (t_end > ta) CU(cudaMemcpyAsync(c->d_t.as<char>() + ta, src.t + t0 + ta, t_end - ta, cudaMemcpyHostToDevice, c->copy_stream));
+        if (c->copy_events.size() <= cuts.size()) {
+            cudaEvent_t e; CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            c->copy_events.push_back(e);
+        }
+        CU(cudaEventRecord(c->copy_events[cuts.size()], c->copy_stream));
+        cuts.push_back(Cut{q_end, t_end});
+        return B200_OK;
+    };
     tl_mark(c, c->copy_stream, "start");
-    for (int s = 0; s < kPipe; ++s) {
-        const uint64_t qa = qn * s / kPipe, qb = qn * (s + 1) / kPipe, ta = tn * s / kPipe, tb = tn * (s + 1) / kPipe;
-        if (qb > qa) CU(cudaMemcpyAsync(c->d_q.as<char>() + qa, q_buf + q0 + qa, qb - qa, cudaMemcpyHostToDevice, c->copy_stream));
-        if (tb > ta) CU(cudaMemcpyAsync(c->d_t.as<char>() + ta, t_buf + t0 + ta, tb - ta, cudaMemcpyHostToDevice, c->copy_stream));
-        CU(cudaEventRecord(c->copy_events[s], c->copy_stream));
-        if (s == 0 || s == kPipe / 2 - 1 || s == kPipe - 1) tl_mark(c, c->copy_stream, "h2d" + std::to_string(s));
+    for (int s = 0; s < kHead; ++s) {
+        TRY(upload_to(qn * (s + 1) / kSlices, tn * (s + 1) / kSlices));
+        if (s == 0 || s == kHead - 1) tl_mark(c, c->copy_stream, "h2d" + std::to_string(s));
     }
     c->h2d_bytes += qn + tn;
     tr.mark("enqueue-h2d");
@@ -55,28 +73,46 @@ extern "C" int b200_align_batch_packed(b200_ctx* c, size_t n, const char* q_buf,
     }
     b200_align_plan* plan = c->host_plan;   // recycled: its device and host buffers keep their capacity
     // Uniform short batches are cut into chunks of whole ROUNDS of the thread-per-pair kernel (every resident warp
-    // takes one 64-pair group per round): any other size leaves a partly empty last round in every chunk, and the
-    // smaller the last chunk, the less work is left when the last byte of the upload lands.
+    // takes one 64-pair group per round): any other size leaves a partly empty last round in every chunk.
+    // The batch ends with a few shrinking waves: a wave of one warp per SM sub-partition fills in a quarter of the
+    // time a full round takes (its warps do not queue for the alu pipe), and each wave before it is sized so that its
+    // fill is over when the next, smaller wave's bytes have landed (fill time / upload time of a wave is ~0.7) -- what
+    // is left to do after the last byte of the upload is the smallest wave's work.
     size_t chunk_pairs = (size_t)c->chunk_pairs;
+    std::vector<uint32_t> tail;
     if (chunk_pairs == 0) {
         size_t round_pairs = 0;
         TRY(align_short_round_pairs(c, type, &round_pairs));
+        if (c->taper_tail) {
+            std::vector<uint32_t> rev;
+            for (double g = (double)c->sm_count * 4; g < (double)round_pairs / 64 && rev.size() < 8; g *= 1.38) rev.push_back((uint32_t)g);
+            tail.assign(rev.rbegin(), rev.rend());
+        }
         const size_t rounds_per_chunk = std::max<size_t>(1, div_up64(div_up64(n, round_pairs), 16));   // at most 16 chunks
         chunk_pairs = round_pairs * rounds_per_chunk;
     }
-    TRY(plan_build(plan, c, n, q_off, t_off, true, false, type, match, mismatch, gap, want_cigar ? 1 : 0, chunk_pairs));
-    // which upload slice does each wave have to wait for
-    plan->wave_events.assign(plan->waves.size(), c->copy_events[kPipe - 1]);
+    TRY(plan_build(plan, c, n, q_off, t_off, true, false, type, match, mismatch, gap, want_cigar ? 1 : 0, chunk_pairs, &tail));
+    tr.mark("plan");
+    // second half of the upload, and which slice each wave has to wait for
+    plan->wave_events.assign(plan->waves.size(), nullptr);
     if (plan->uniform) {
         for (size_t k = 0; k < plan->waves.size(); ++k) {
             const uint64_t last_pair = (uint64_t)plan->waves[k].first + plan->waves[k].count;   // exclusive
             const uint64_t qe = last_pair * plan->uQ, te = last_pair * plan->uT;                // bytes needed (exclusive)
-            int need = 0;
-            while (need < kPipe - 1 && (qn * (need + 1) / kPipe < qe || tn * (need + 1) / kPipe < te)) ++need;
+            if (qe > cuts.back().q_end || te > cuts.back().t_end) {
+                TRY(upload_to(qe, te));
+                tl_mark(c, c->copy_stream, "h2dw" + std::to_string(k));
+            }
+            size_t need = 0;
+            while (need + 1 < cuts.size() && (cuts[need].q_end < qe || cuts[need].t_end < te)) ++need;
             plan->wave_events[k] = c->copy_events[need];
         }
+        if (cuts.back().q_end < qn || cuts.back().t_end < tn) TRY(upload_to(qn, tn));
+    } else {
+        for (int s = kHead; s < kSlices; ++s) TRY(upload_to(qn * (s + 1) / kSlices, tn * (s + 1) / kSlices));
+        plan->wave_events.assign(plan->waves.size(), c->copy_events[cuts.size() - 1]);
     }
-    tr.mark("plan");
+    tl_mark(c, c->copy_stream, "h2d-end");
 
     const uint64_t dev_cigar_cap = want_cigar ? std::min<uint64_t>(plan->cigar_bound, std::max<uint64_t>(cigar_cap, 2)) : 0;
     TRY(c->d_score.ensure(n * 4));
@@ -110,32 +146,154 @@ extern "C" int b200_align_batch_packed(b200_ctx* c, size_t n, const char* q_buf,
     return B200_OK;
 }
 
+extern "C" int b200_align_batch_packed(b200_ctx* c, size_t n, const char* q_buf, const uint64_t* q_off,
+                                       const char* t_buf, const uint64_t* t_off, int type, int match,
+                                       int mismatch, int gap, int32_t* score, uint32_t* target_begin,
+                                       char* cigar_buf, uint64_t* cigar_off, uint64_t cigar_cap) {
+    if (!c) return fail(B200_E_ARG, "null context");
+    if (type < 0 || type > 2) return fail(B200_E_TYPE, "Unknown AlignmentType provided.");
+    if (n && (!q_off || !t_off || !score)) return fail(B200_E_ARG, "null argument");
+    if (cigar_off && !cigar_buf && cigar_cap) return fail(B200_E_ARG, "cigar_buf is null");
+    if (n == 0) { if (cigar_off) cigar_off[0] = 0; return B200_OK; }
+    HostSource src;
+    src.q = q_buf; src.t = t_buf;
+    const int rc = align_batch_host(c, n, src, q_off, t_off, type, match, mismatch, gap, score, target_begin, cigar_buf,
+                                    cigar_off, cigar_cap);
+    if (rc != B200_OK) {   // the upload of a call that failed half-way must not outlive it
+        const std::string msg = b200_last_error();
+        ctx_sync_all_streams(c);
+        b200_fail(rc, msg);
+    }
+    return rc;
+}
+
+// ---- pointer arrays -> packed pinned staging, gathered by a few threads while the upload is already running ----
+namespace {
+
+unsigned host_threads() {
+    static const unsigned n = [] {
+        const char* e = std::getenv("B200_HOST_THREADS");
+        unsigned v = e ? (unsigned)std::atoi(e) : 0;
+        if (v == 0) v = std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+        return std::max(1u, std::min(v, 64u));
+    }();
+    return n;
+}
+
+// Gathers n (pointer, length) sequences of two arrays into two packed buffers with their n+1 offsets. Pairs are cut
+// into blocks taken in order from a shared counter, so a prefix of the packed bytes is complete early and grows
+// steadily; wait_pairs(p) returns once every pair below p is in place.
+struct Gatherer {
+    size_t n = 0;
+    const char* const* src[2] = {nullptr, nullptr};
+    const uint32_t* len[2] = {nullptr, nullptr};
+    char* dst[2] = {nullptr, nullptr};
+    uint64_t* off[2] = {nullptr, nullptr};
+    static constexpr size_t kBlock = 2048;
+    size_t n_blocks = 0;
+    std::vector<std::thread> workers;
+    std::vector<std::atomic<uint8_t>> done;
+    std::atomic<size_t> next{0};
+    std::atomic<int> bad{0};
+    size_t prefix = 0;   // blocks [0, prefix) are known to be done (consumer side only)
+
+    void offsets(unsigned T) {   // parallel prefix sum of the lengths
+        std::vector<uint64_t> part(2 * (size_t)T, 0);
+        auto range = [&](unsigned t) { return std::pair<size_t, size_t>(n * t / T, n * (t + 1) / T); };
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < T; ++t)
+            th.emplace_back([&, t] {
+                auto [a, b] = range(t);
+                for (int w = 0; w < 2; ++w) { uint64_t s = 0; for (size_t i = a; i < b; ++i) s += len[w][i]; part[2 * t + w] = s; }
+            });
+        for (auto& x : th) x.join();
+        th.clear();
+        uint64_t base[2] = {0, 0};
+        std::vector<uint64_t> start(2 * (size_t)T);
+        for (unsigned t = 0; t < T; ++t)
+            for (int w = 0; w < 2; ++w) { start[2 * t + w] = base[w]; base[w] += part[2 * t + w]; }
+        off[0][n] = base[0]; off[1][n] = base[1];
+        for (unsigned t = 0; t < T; ++t)
+            th.emplace_back([&, t] {
+                auto [a, b] = range(t);
+                for (int w = 0; w < 2; ++w) { uint64_t s = start[2 * t + w]; for (size_t i = a; i < b; ++i) { off[w][i] = s; s += len[w][i]; } }
+            });
+        for (auto& x : th) x.join();
+    }
+    void start(unsigned T) {
+        n_blocks = (n + kBlock - 1) / kBlock;
+        done = std::vector<std::atomic<uint8_t>>(n_blocks);
+        for (auto& d : done) d.store(0, std::memory_order_relaxed);
+        for (unsigned t = 0; t < T; ++t)
+            workers.emplace_back([this] {
+                for (;;) {
+                    const size_t b = next.fetch_add(1, std::memory_order_relaxed);
+                    if (b >= n_blocks) return;
+                    const size_t a = b * kBlock, e = std::min(n, a + kBlock);
+                    for (int w = 0; w < 2; ++w)
+                        for (size_t i = a; i < e; ++i) {
+                            const uint32_t l = len[w][i];
+                            if (!l) continue;
+                            if (!src[w][i]) { bad.store(1, std::memory_order_relaxed); continue; }
+                            std::memcpy(dst[w] + off[w][i], src[w][i], l);
+                        }
+                    done[b].store(1, std::memory_order_release);
+                }
+            });
+    }
+    int wait_pairs(size_t p) {   // every pair below p gathered
+        const size_t need = std::min(n_blocks, (p + kBlock - 1) / kBlock);
+        while (prefix < need) {
+            while (!done[prefix].load(std::memory_order_acquire)) std::this_thread::yield();
+            ++prefix;
+        }
+        return bad.load(std::memory_order_relaxed) ? fail(B200_E_ARG, "null sequence pointer") : B200_OK;
+    }
+    void join() { for (auto& w : workers) if (w.joinable()) w.join(); workers.clear(); }
+    ~Gatherer() { join(); }
+};
+
+}  // namespace
+
 extern "C" int b200_align_batch(int device, size_t n, const char* const* query, const uint32_t* query_len,
                                 const char* const* target, const uint32_t* target_len, int type, int match,
                                 int mismatch, int gap, int32_t* score, uint32_t* target_begin,
                                 char* cigar_buf, uint64_t* cigar_off, uint64_t cigar_cap) {
     if (type < 0 || type > 2) return fail(B200_E_TYPE, "Unknown AlignmentType provided.");
     if (n && (!query || !query_len || !target || !target_len || !score)) return fail(B200_E_ARG, "null argument");
+    if (cigar_off && !cigar_buf && cigar_cap) return fail(B200_E_ARG, "cigar_buf is null");
     b200_ctx* c = nullptr;
     TRY(default_ctx(device, &c));
     if (n == 0) { if (cigar_off) cigar_off[0] = 0; return B200_OK; }
     TRY(set_device(c));
-    uint64_t qtot = 0, ttot = 0;
-    for (size_t i = 0; i < n; ++i) { qtot += query_len[i]; ttot += target_len[i]; }
-    TRY(c->h_q.ensure(qtot + 1));
-    TRY(c->h_t.ensure(ttot + 1));
     TRY(c->h_off.ensure(2 * (n + 1) * sizeof(uint64_t)));
-    uint64_t* qo = c->h_off.as<uint64_t>();
-    uint64_t* to = qo + (n + 1);
-    uint64_t qa = 0, ta = 0;
-    for (size_t i = 0; i < n; ++i) {
-        if ((query_len[i] && !query[i]) || (target_len[i] && !target[i])) return fail(B200_E_ARG, "null sequence pointer");
-        qo[i] = qa; to[i] = ta;
-        if (query_len[i]) std::memcpy(c->h_q.as<char>() + qa, query[i], query_len[i]);
-        if (target_len[i]) std::memcpy(c->h_t.as<char>() + ta, target[i], target_len[i]);
-        qa += query_len[i]; ta += target_len[i];
+    Gatherer g;
+    g.n = n;
+    g.src[0] = query; g.src[1] = target; g.len[0] = query_len; g.len[1] = target_len;
+    g.off[0] = c->h_off.as<uint64_t>(); g.off[1] = g.off[0] + (n + 1);
+    // small batches: one thread, no pipeline to feed
+    const unsigned T = n >= 4 * Gatherer::kBlock ? host_threads() : 1u;
+    g.offsets(T);
+    TRY(c->h_q.ensure(g.off[0][n] + 1));
+    TRY(c->h_t.ensure(g.off[1][n] + 1));
+    g.dst[0] = c->h_q.as<char>(); g.dst[1] = c->h_t.as<char>();
+    g.start(T);
+    HostSource src;
+    src.q = g.dst[0]; src.t = g.dst[1];
+    const uint64_t* qo = g.off[0];
+    const uint64_t* to = g.off[1];
+    src.wait = [&g, qo, to, n](uint64_t q_end, uint64_t t_end) -> int {
+        // the first pair whose bytes start at or beyond both ends: everything below it is needed
+        const size_t pq = (size_t)(std::lower_bound(qo, qo + n + 1, q_end) - qo);
+        const size_t pt = (size_t)(std::lower_bound(to, to + n + 1, t_end) - to);
+        return g.wait_pairs(std::min(n, std::max(pq, pt)));
+    };
+    int rc = align_batch_host(c, n, src, qo, to, type, match, mismatch, gap, score, target_begin, cigar_buf, cigar_off, cigar_cap);
+    g.join();
+    if (rc != B200_OK) {
+        const std::string msg = b200_last_error();
+        ctx_sync_all_streams(c);   // no copy may still read the staging buffers the next call refills
+        b200_fail(rc, msg);
     }
-    qo[n] = qa; to[n] = ta;
-    return b200_align_batch_packed(c, n, c->h_q.as<char>(), qo, c->h_t.as<char>(), to, type, match, mismatch, gap,
-                                   score, target_begin, cigar_buf, cigar_off, cigar_cap);
+    return rc;
 }

@@ -12,8 +12,15 @@ using namespace b200;
 // Uniform batches (every pair the same Q x T, e.g. fixed-length short reads): the descriptors are an
 // affine function of the pair index, so they are generated on the device instead of being built on
 // the host and copied (48 B per pair).
+__device__ __host__ inline uint32_t uniform_group_in_wave(uint32_t g, uint32_t groups_per_wave, const UniformTail& tail) {
+    if (g < tail.first_group) return g % groups_per_wave;
+    uint32_t k = 0;
+    while (k + 1 < tail.n && g >= tail.start[k + 1]) ++k;
+    return g - tail.start[k];
+}
+
 __global__ void build_uniform_plan_kernel(uint32_t n, uint32_t Q, uint32_t T, uint64_t q_base, uint64_t t_base,
-                                          uint64_t words_per_group, uint32_t groups_per_wave,
+                                          uint64_t words_per_group, uint32_t groups_per_wave, UniformTail tail,
                                           PairDesc* __restrict__ pairs,
                                           uint32_t* __restrict__ work, ShortGroup* __restrict__ groups) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -21,7 +28,7 @@ __global__ void build_uniform_plan_kernel(uint32_t n, uint32_t Q, uint32_t T, ui
     PairDesc d;
     d.q_off = q_base + (uint64_t)i * Q;
     d.t_off = t_base + (uint64_t)i * T;
-    d.dir_off = (uint64_t)((i >> 6) % groups_per_wave) * words_per_group;   // relative to the wave's buffer
+    d.dir_off = (uint64_t)uniform_group_in_wave(i >> 6, groups_per_wave, tail) * words_per_group;   // relative to the wave's buffer
     d.run_off = (uint64_t)i * ((uint64_t)Q + T + 1);
     d.qpk_off = (uint64_t)i * (Q / 16 + 2);
     d.tpk_off = (uint64_t)i * (T / 16 + 2);
@@ -41,7 +48,7 @@ void materialize_uniform_host(b200_align_plan* p) {   // only needed by the non-
     for (size_t i = 0; i < p->n; ++i) {
         PairDesc& d = p->h_pairs[i];
         d.q_off = p->u_qbase + i * p->uQ; d.t_off = p->u_tbase + i * p->uT;
-        d.dir_off = ((i >> 6) % p->u_groups_per_wave) * wpg; d.run_off = i * ((uint64_t)p->uQ + p->uT + 1);
+        d.dir_off = uniform_group_in_wave((uint32_t)(i >> 6), (uint32_t)p->u_groups_per_wave, p->u_tail) * wpg; d.run_off = i * ((uint64_t)p->uQ + p->uT + 1);
         d.qpk_off = i * (uint64_t)(p->uQ / 16 + 2); d.tpk_off = i * (uint64_t)(p->uT / 16 + 2);
         d.Q = p->uQ; d.T = p->uT; d.pitch = p->uT;
         const uint32_t slot = (uint32_t)(i & 63u);
@@ -123,7 +130,7 @@ static inline uint64_t wave_cap_words(uint64_t budget_words, uint64_t class_tota
 // t_off[0] (the host entry points copy only the referenced byte range to the device).
 int plan_build(b200_align_plan* p, b200_ctx* ctx, size_t n, const uint64_t* q_off, const uint64_t* t_off,
                bool rebase, bool sync, int type, int match, int mismatch, int gap, int want_cigar,
-               size_t chunk_pairs) {
+               size_t chunk_pairs, const std::vector<uint32_t>* tail_groups) {
     if (type < 0 || type > 2) return fail(B200_E_TYPE, "Unknown AlignmentType provided.");
     if (n > 0xfffffff0ull) return fail(B200_E_ARG, "batch too large");
     TRY(set_device(ctx));
@@ -168,9 +175,25 @@ int plan_build(b200_align_plan* p, b200_ctx* ctx, size_t n, const uint64_t* q_of
         // overlap the upload of chunk c+1 with the kernels of chunk c
         uint64_t groups_per_wave = chunk_pairs ? std::max<uint64_t>(1, chunk_pairs / 64) : n_groups;
         if (!chunk_pairs && wpg) groups_per_wave = std::max<uint64_t>(1, std::min(n_groups, wave_cap_words(budget_words, n_groups * wpg) / wpg));
+        // ... and end with a tail of explicitly sized, shrinking waves (sizes in groups, none larger than a regular
+        // chunk): what is left to do when the last byte of the upload lands is then the smallest wave's work
+        UniformTail tail{(uint32_t)n_groups, 0, {0}};
+        if (chunk_pairs && tail_groups && !tail_groups->empty()) {
+            uint64_t sum = 0;
+            size_t first = tail_groups->size();
+            while (first > 0 && tail.n < 16 && sum + (*tail_groups)[first - 1] <= n_groups && (*tail_groups)[first - 1] > 0 &&
+                   (*tail_groups)[first - 1] <= groups_per_wave) {
+                sum += (*tail_groups)[--first];
+                ++tail.n;
+            }
+            tail.first_group = (uint32_t)(n_groups - sum);
+            uint32_t at = tail.first_group;
+            for (uint32_t k = 0; k < tail.n; ++k) { tail.start[k] = at; at += (*tail_groups)[first + k]; }
+        }
         const uint64_t wave_words_u = std::min(n_groups, groups_per_wave) * wpg;
         if (uni && wave_words_u <= (groups_per_wave < n_groups ? std::max<uint64_t>(budget_words / 2, 1 << 15) : budget_words)) {
             p->uniform = true; p->uQ = (uint32_t)Q0; p->uT = (uint32_t)T0; p->u_groups_per_wave = groups_per_wave;
+            p->u_tail = tail;
             p->u_qbase = q_off[0] - qb; p->u_tbase = t_off[0] - tb;
             p->run_slots = n * (Q0 + T0 + 1);
             p->qpk_words = n * (Q0 / 16 + 2); p->tpk_words = n * (T0 / 16 + 2);
@@ -179,16 +202,17 @@ int plan_build(b200_align_plan* p, b200_ctx* ctx, size_t n, const uint64_t* q_of
             p->max_T = p->max_T_short = (uint32_t)T0;
             p->max_Q = p->max_Q_short = (uint32_t)Q0;
             p->n_short = n;
-            for (uint64_t g0 = 0; g0 < n_groups; g0 += groups_per_wave) {
-                const uint64_t g1 = std::min(n_groups, g0 + groups_per_wave);
+            auto add_wave = [&](uint64_t g0, uint64_t g1) {
                 const uint64_t first = g0 * 64, last = std::min<uint64_t>(n, g1 * 64);
                 p->waves.push_back(Wave{kClassShort, (uint32_t)first, (uint32_t)(last - first), (uint32_t)g0, (g1 - g0) * wpg});
-            }
+            };
+            for (uint64_t g0 = 0; g0 < tail.first_group; g0 += groups_per_wave) add_wave(g0, std::min<uint64_t>(tail.first_group, g0 + groups_per_wave));
+            for (uint32_t k = 0; k < tail.n; ++k) add_wave(tail.start[k], k + 1 < tail.n ? tail.start[k + 1] : n_groups);
             TRY(p->d_pairs.ensure(n * sizeof(PairDesc)));
             TRY(p->d_work.ensure(n * sizeof(uint32_t)));
             TRY(p->d_groups.ensure(n_groups * sizeof(ShortGroup)));
             build_uniform_plan_kernel<<<(unsigned)div_up64(n, 256), 256, 0, ctx->stream>>>(
-                (uint32_t)n, p->uQ, p->uT, p->u_qbase, p->u_tbase, wpg, (uint32_t)groups_per_wave, p->d_pairs.as<PairDesc>(),
+                (uint32_t)n, p->uQ, p->uT, p->u_qbase, p->u_tbase, wpg, (uint32_t)groups_per_wave, tail, p->d_pairs.as<PairDesc>(),
                 p->d_work.as<uint32_t>(), p->d_groups.as<ShortGroup>());
             ctx->kernel_launches++;
             CU(cudaGetLastError());
@@ -374,7 +398,7 @@ extern "C" int b200_align_plan_create(b200_ctx* ctx, size_t n, const uint64_t* q
     b200_align_plan* p = new (std::nothrow) b200_align_plan();
     if (!p) return fail(B200_E_NOMEM, "out of host memory");
     p->ctx = ctx;
-    const int rc = plan_build(p, ctx, n, q_off, t_off, false, true, type, match, mismatch, gap, want_cigar);
+    const int rc = plan_build(p, ctx, n, q_off, t_off, false, true, type, match, mismatch, gap, want_cigar, 0, nullptr);
     if (rc != B200_OK) { b200_align_plan_destroy(p); return rc; }
     *out = p;
     return B200_OK;

@@ -20,10 +20,13 @@ using namespace b200;
 // the fill running on the SM was over (measured: the "concurrent" walkers finished 2.9 ms after the fill; launched
 // first, they kept the fill out instead). Same explicit preference on all of them.
 void align_kernels_configure() {
-    const int pct = 20;
-    cudaFuncSetAttribute(fill_long16_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-    cudaFuncSetAttribute(fill_long16_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-    cudaFuncSetAttribute(fill_long16_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    const int pct = 30;   // 68 KB: three fill CTAs with their 8 KB substitution tables + a 16 KB walker CTA
+    cudaFuncSetAttribute(fill_long16_kernel<0, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(fill_long16_kernel<1, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(fill_long16_kernel<2, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(fill_long16_kernel<0, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(fill_long16_kernel<1, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(fill_long16_kernel<2, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
     cudaFuncSetAttribute(fill_long_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
     cudaFuncSetAttribute(fill_long_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
     cudaFuncSetAttribute(fill_long_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
@@ -36,11 +39,12 @@ void align_kernels_configure() {
     cudaGetLastError();
 }
 
-static int short_blocks_per_sm(int type, int* per_sm) {
+static int short_blocks_per_sm(int type, bool lds, int* per_sm) {
     *per_sm = 0;
-    if (type == 0) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, fill_short_kernel<0>, kShortThreads, 0));
-    else if (type == 1) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, fill_short_kernel<1>, kShortThreads, 0));
-    else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, fill_short_kernel<2>, kShortThreads, 0));
+#define OCC(TY, SB) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, fill_short_kernel<TY, SB>, kShortThreads, 0))
+    if (lds) { if (type == 0) OCC(0, 1); else if (type == 1) OCC(1, 1); else OCC(2, 1); }
+    else { if (type == 0) OCC(0, 0); else if (type == 1) OCC(1, 0); else OCC(2, 0); }
+#undef OCC
     *per_sm = std::max(*per_sm, 1);
     return B200_OK;
 }
@@ -48,7 +52,7 @@ static int short_blocks_per_sm(int type, int* per_sm) {
 // One ROUND of the thread-per-pair fill: every resident warp takes one 64-pair group.
 int align_short_round_pairs(b200_ctx* c, int type, size_t* out) {
     int per_sm = 0;
-    TRY(short_blocks_per_sm(type, &per_sm));
+    TRY(short_blocks_per_sm(type, c->subst_lds != 0, &per_sm));
     *out = (size_t)c->sm_count * per_sm * (kShortThreads / 32) * 64;
     return B200_OK;
 }
@@ -86,19 +90,24 @@ static int launch_fill_short(b200_align_plan* p, const Wave& wv, const RunBufs& 
     b200_ctx* c = p->ctx;
     const uint32_t n_groups = (wv.count + 63) / 64;
     int per_sm = 0;
-    TRY(short_blocks_per_sm(p->type, &per_sm));
+    TRY(short_blocks_per_sm(p->type, c->subst_lds != 0, &per_sm));
     const int n_blocks = (int)std::min<uint64_t>((uint64_t)c->sm_count * per_sm, div_up64(n_groups, kShortThreads / 32));
     const uint32_t bnd_cols = p->max_T_short + 4;
     TRY(rb.ws->bnd_short.ensure((size_t)n_blocks * (kShortThreads / 32) * bnd_cols * 32 * sizeof(uint32_t)));
     CU(cudaMemsetAsync(rb.ws->counter.p, 0, 64, rb.st));
     const ShortConsts K = make_short_consts(p->sc, p->type);
     prof_begin(c, rb.st, 0);
-#define SHORTK(TY) fill_short_kernel<TY><<<n_blocks, kShortThreads, 0, rb.st>>>(                                            \
+#define SHORTK(TY) SHORTK2(TY, 0)
+#define SHORTK1(TY) SHORTK2(TY, 1)
+#define SHORTK2(TY, SB) fill_short_kernel<TY, SB><<<n_blocks, kShortThreads, 0, rb.st>>>(                                         \
         c->qpk.as<uint32_t>(), c->tpk.as<uint32_t>(), p->d_pairs.as<PairDesc>(), p->d_work.as<uint32_t>() + wv.first,     \
         wv.count, p->d_groups.as<ShortGroup>() + wv.first_group, rb.ws->counter.as<uint32_t>(), c->flags.as<uint8_t>(), K, \
         rb.dirs, rb.ws->bnd_short.as<uint32_t>(), bnd_cols, rb.score, c->end_i.as<uint32_t>(), c->end_j.as<uint32_t>())
-    switch (p->type) { case 0: SHORTK(0); break; case 1: SHORTK(1); break; default: SHORTK(2); break; }
+    if (c->subst_lds) { switch (p->type) { case 0: SHORTK1(0); break; case 1: SHORTK1(1); break; default: SHORTK1(2); break; } }
+    else { switch (p->type) { case 0: SHORTK(0); break; case 1: SHORTK(1); break; default: SHORTK(2); break; } }
 #undef SHORTK
+#undef SHORTK1
+#undef SHORTK2
     prof_end(c, rb.st);
     c->kernel_launches++;
     return B200_OK;
@@ -107,7 +116,8 @@ static int launch_fill_short(b200_align_plan* p, const Wave& wv, const RunBufs& 
 static int launch_fill_long(b200_align_plan* p, const Wave& wv, const RunBufs& rb) {
     b200_ctx* c = p->ctx;
     int per_sm = 0;
-    if (p->long16) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fill_long16_kernel<1>, 128, 0));
+    if (p->long16 && c->subst_lds) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fill_long16_kernel<1, 1>, 128, 0));
+    else if (p->long16) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fill_long16_kernel<1, 0>, 128, 0));
     else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fill_long_kernel<0>, 128, 0));
     per_sm = std::max(per_sm, 1);
     const uint32_t* d_task_off = p->d_task_off.as<uint32_t>() + wv.first_group;
@@ -142,7 +152,8 @@ static int launch_fill_long(b200_align_plan* p, const Wave& wv, const RunBufs& r
             if (!ws.walk_event) CU(cudaEventCreateWithFlags(&ws.walk_event, cudaEventDisableTiming));
         }
         prof_begin(c, rb.st, 0);
-#define LONG16K(TY)                                                                                                    \
+#define LONG16K(TY) if (c->subst_lds) { LONG16K2(TY, 1); } else { LONG16K2(TY, 0); }
+#define LONG16K2(TY, SB)                                                                                               \
     if (cw) {   /* pairs without inner cells have nothing to wait for: result and ready flag now */                   \
         finalize_long_kernel<TY><<<(unsigned)div_up64(wv.count, 128), 128, 0, rb.st>>>(p->d_pairs.as<PairDesc>(), d_work, \
             wv.count, d_task_off, c->flags.as<uint8_t>(), ws.stripe_res.as<StripeResult>(), K16.init, rb.score,        \
@@ -150,7 +161,7 @@ static int launch_fill_long(b200_align_plan* p, const Wave& wv, const RunBufs& r
         CU(cudaEventRecord(ws.pre_event, rb.st));                                                                      \
         CU(cudaStreamWaitEvent(ws.walk_stream, ws.pre_event, 0));                                                      \
     }                                                                                                                  \
-    fill_long16_kernel<TY><<<n_blocks, 128, 0, rb.st>>>(c->qpk.as<uint32_t>(), c->tpk.as<uint32_t>(), p->d_pairs.as<PairDesc>(), \
+    fill_long16_kernel<TY, SB><<<n_blocks, 128, 0, rb.st>>>(c->qpk.as<uint32_t>(), c->tpk.as<uint32_t>(), p->d_pairs.as<PairDesc>(), \
         d_work, wv.count, d_task_off, d_bnd_off, rb.ws->counter.as<uint32_t>(), c->flags.as<uint8_t>(), K16, rb.dirs,  \
         rb.ws->bnd.as<int32_t>(), rb.ws->progress.as<uint32_t>(), (uint32_t)prog_words,                                \
         rb.ws->stripe_res.as<StripeResult>(),                                                                          \
@@ -171,6 +182,7 @@ static int launch_fill_long(b200_align_plan* p, const Wave& wv, const RunBufs& r
         c->end_i.as<uint32_t>(), c->end_j.as<uint32_t>(), 0, nullptr)
         if (p->type == 0) { LONG16K(0); } else if (p->type == 2) { LONG16K(2); } else { LONG16K(1); }
 #undef LONG16K
+#undef LONG16K2
         prof_end(c, rb.st);
         c->kernel_launches += 2;
         return B200_OK;

@@ -155,9 +155,11 @@ extern "C" int b200_ctx_set_option(b200_ctx* c, const char* key, int64_t value) 
     if (k == "dir_budget_bytes") c->dir_budget_bytes = std::max<int64_t>(value, 1 << 20);
     else if (k == "force_generic") c->force_generic = value;
     else if (k == "long16") c->long16 = value;
+    else if (k == "subst_lds") c->subst_lds = value;
     else if (k == "overlap_waves") c->overlap_waves = value;
     else if (k == "concurrent_walk") c->concurrent_walk = value;
     else if (k == "chunk_pairs") c->chunk_pairs = value;
+    else if (k == "taper_tail") c->taper_tail = value;
     else if (k == "profile") c->profile = value;
     else if (k == "reset_counters") {
         c->kernel_launches = c->h2d_bytes = c->d2h_bytes = 0;
@@ -173,6 +175,8 @@ extern "C" int64_t b200_ctx_get_counter(b200_ctx* c, const char* key) {
     if (k == "kernel_launches") return c->kernel_launches;
     if (k == "h2d_bytes") return c->h2d_bytes;
     if (k == "d2h_bytes") return c->d2h_bytes;
+    // alu-pipe issue slots the fill kernels spend per register (= two cells), times ten: PRMT counts double
+    if (k == "alu_slots_per_cell_pair_x10") return c->subst_lds ? 30 : 50;
     static const char* kinds[4] = {"fill", "walk", "emit", "other"};
     for (int i = 0; i < 4; ++i) {
         if (k == std::string(kinds[i]) + "_ns") return (int64_t)(c->kind_us[i] * 1e3);

@@ -120,7 +120,9 @@ struct b200_ctx {
     int64_t dir_budget_bytes = 48ll << 30;
     int64_t force_generic = 0;
     int64_t long16 = 1;                     // 0 = long pairs stay on the int32 kernel (align_fill_long.cuh)
+    int64_t subst_lds = 1;                  // 1 = substitution term from the shared-memory table, 0 = by PRMT (K1 and K3)
     int64_t chunk_pairs = 0;
+    int64_t taper_tail = 1;                 // host pipeline of uniform batches: end with a few shrinking waves
     b200_align_plan* host_plan = nullptr;   // recycled by the host-buffer entry points
     b200_align_plan* map_plan = nullptr;    // recycled by b200_map_batch (its device buffers keep their capacity)
     b200_min_plan* map_min_plan = nullptr;
@@ -174,6 +176,14 @@ struct Wave {
     uint64_t dir_words;
 };
 
+// Uniform plans: the waves are equal chunks of `u_groups_per_wave` 64-pair groups over groups [0, first_group),
+// followed by up to 16 explicitly placed waves (the host pipeline's shrinking tail).
+struct UniformTail {
+    uint32_t first_group;   // first group of the tail (= number of groups when there is no tail)
+    uint32_t n;             // waves in the tail
+    uint32_t start[16];     // first group of each tail wave
+};
+
 struct b200_align_plan {
     b200_ctx* ctx = nullptr;
     size_t n = 0;
@@ -192,6 +202,7 @@ struct b200_align_plan {
     bool uniform = false;              // every pair has the same (Q,T): descriptors were built on the device
     uint32_t uQ = 0, uT = 0;
     uint64_t u_groups_per_wave = 1;
+    UniformTail u_tail{0, 0, {0}};
     uint64_t u_qbase = 0, u_tbase = 0;
     DevBuf d_pairs, d_work, d_groups, d_task_off, d_bnd_off;
     uint64_t max_long_bnd_words = 0;   // boundary rows of the largest long wave
@@ -210,7 +221,8 @@ uint64_t generic_dir_words(uint32_t Q, uint32_t T);
 uint64_t wave_budget_words(const b200_ctx* ctx);
 void materialize_uniform_host(b200_align_plan* p);
 int plan_build(b200_align_plan* p, b200_ctx* ctx, size_t n, const uint64_t* q_off, const uint64_t* t_off, bool rebase,
-               bool sync, int type, int match, int mismatch, int gap, int want_cigar, size_t chunk_pairs = 0);
+               bool sync, int type, int match, int mismatch, int gap, int want_cigar, size_t chunk_pairs,
+               const std::vector<uint32_t>* tail_groups);
 int plan_finish(b200_align_plan* p, b200_ctx* ctx, bool short_scores, bool sync);
 
 // Host destinations of a run made through the host-buffer entry point. When given (and the batch is a uniform

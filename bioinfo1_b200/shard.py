@@ -10,14 +10,15 @@ import numpy as np
 def partition(costs, world):
     """Longest-processing-time-first split of items with the given costs (e.g. Q*T cells) over
     `world` ranks. Returns a list of index arrays (ascending inside each rank); deterministic."""
+    import heapq
     costs = np.asarray(costs, dtype=np.float64)
     order = np.argsort(-costs, kind="stable")
-    load = np.zeros(world)
+    heap = [(0.0, r) for r in range(world)]      # (load, rank): ties go to the lowest rank
     owner = np.empty(len(costs), dtype=np.int64)
     for i in order:
-        r = int(np.argmin(load))
+        load, r = heapq.heappop(heap)
         owner[i] = r
-        load[r] += costs[i]
+        heapq.heappush(heap, (load + float(costs[i]), r))
     return [np.nonzero(owner == r)[0] for r in range(world)]
 
 

@@ -1,0 +1,145 @@
+"""GPU tests of the host-side pipelines and of the kernel variants behind one ABI:
+
+* the host-buffer entry point with its shrinking tail of waves / wave-aligned upload slices, at sizes on both sides
+  of every switch (two waves, many waves, tail longer than the batch), against the CPU checker and the device path;
+* the pointer-array entry point with its threaded gather (several block counts, one thread and many);
+* both substitution-term variants of the 2-bit fill kernels (PRMT and the shared-memory table) on the same batches;
+* the stripe protocol of the long-pair fill under stress: thousands of multi-stripe pairs, tiny direction budget
+  (many waves), concurrent walkers on and off.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from cpu_checkers import load_oracle, load_ref
+import seqgen
+import synth
+
+pytestmark = pytest.mark.gpu
+CHK = load_ref() or load_oracle()
+THREADS = os.cpu_count() or 1
+
+
+@pytest.fixture()
+def ctx():
+    from bioinfo1_b200 import capi
+    c = capi.Context(0)
+    yield c
+    c.close()
+
+
+def _equal(got, exp, what):
+    n = len(exp[0])
+    assert np.array_equal(got[0][:n], exp[0]), what + ": scores"
+    assert np.array_equal(got[1][:n], exp[1]), what + ": target_begin"
+    assert np.array_equal(np.asarray(got[3][:n + 1], dtype=np.uint64), np.asarray(exp[3], dtype=np.uint64)), what + ": CIGAR offsets"
+    tot = int(exp[3][n])
+    assert np.array_equal(got[2][:tot], exp[2][:tot]), what + ": CIGAR bytes"
+
+
+@pytest.mark.parametrize("n", [8192, 70_000, 262_144, 400_001])
+def test_host_pipeline_wave_schedules(ctx, n):
+    qb, qo, tb, to = synth.short_pairs(77, n, 150)
+    exp = CHK.align_batch_full(qb, qo, tb, to, 0, 1, -1, -1, threads=THREADS)
+    for taper in (1, 0):
+        ctx.set_option("taper_tail", taper)
+        got = ctx.align_packed(qb, qo, tb, to, 0, 1, -1, -1, True, cigar_cap=64 * n)
+        _equal(got, exp, f"n={n} taper={taper}")
+    ctx.set_option("taper_tail", 1)
+    # score-only through the same pipeline
+    s, t_, _, _ = ctx.align_packed(qb, qo, tb, to, 0, 1, -1, -1, False)
+    assert np.array_equal(s, exp[0]) and np.array_equal(t_, exp[1])
+
+
+def test_host_pipeline_other_lengths_and_types(ctx):
+    for length, typ in ((100, 2), (64, 1), (33, 0)):
+        n = 150_000
+        qb, qo, tb, to = synth.pairs(5, n, length, 0.05, 0.01, 0.01)
+        exp = CHK.align_batch_full(qb, qo, tb, to, typ, 1, -1, -1, threads=THREADS)
+        got = ctx.align_packed(qb, qo, tb, to, typ, 1, -1, -1, True, cigar_cap=64 * n)
+        _equal(got, exp, f"length {length} type {typ}")
+
+
+@pytest.mark.parametrize("n", [1, 300, 9000, 150_000])
+def test_pointer_array_entry_point_threaded_gather(n):
+    from bioinfo1_b200 import capi
+    L = capi.lib()
+    qb, qo, tb, to = synth.short_pairs(78, n, 150)
+    exp = CHK.align_batch_full(qb, qo, tb, to, 0, 1, -1, -1, threads=THREADS)
+    qptr = (qb.ctypes.data + qo[:n]).astype(np.uint64)
+    tptr = (tb.ctypes.data + to[:n]).astype(np.uint64)
+    qlen = (qo[1:] - qo[:n]).astype(np.uint32)
+    tlen = (to[1:] - to[:n]).astype(np.uint32)
+    cap = 64 * n + 64
+    score = np.empty(n, dtype=np.int32); tbeg = np.empty(n, dtype=np.uint32)
+    cig = np.empty(cap, dtype=np.uint8); coff = np.zeros(n + 1, dtype=np.uint64)
+    for _ in range(2):   # second call: recycled staging and plan
+        capi.check(L.b200_align_batch(0, n, qptr.ctypes.data, qlen.ctypes.data, tptr.ctypes.data, tlen.ctypes.data, 0, 1, -1, -1,
+                                      score.ctypes.data, tbeg.ctypes.data, cig.ctypes.data, coff.ctypes.data, cap))
+        _equal((score, tbeg, cig, coff), exp, f"pointer arrays n={n}")
+    # ragged lengths (not a uniform batch), some empty sequences, pointers in scattered order
+    rng = np.random.default_rng(3)
+    m = min(n, 20_000)
+    seqs_q = [bytes(qb[int(qo[i]):int(qo[i]) + int(rng.integers(0, 151))]) for i in range(m)]
+    seqs_t = [bytes(tb[int(to[i]):int(to[i]) + int(rng.integers(0, 151))]) for i in range(m)]
+    got = capi.align_batch_pointers(0, seqs_q, seqs_t, 2, 1, -1, -1, True)
+    pq, pqo = capi.pack(seqs_q); pt, pto = capi.pack(seqs_t)
+    es, et, ec, eo = CHK.align_batch_full(pq, pqo, pt, pto, 2, 1, -1, -1, threads=THREADS)
+    for i in range(m):
+        assert got[i] == (int(es[i]), int(et[i]), bytes(ec[int(eo[i]):int(eo[i + 1])])), i
+
+
+@pytest.mark.parametrize("typ", [0, 1, 2])
+def test_substitution_by_prmt_and_by_shared_table_agree(ctx, typ):
+    """Both variants of K1 and K3 against the checker: unit scores and the largest scores the tables take."""
+    n = 20_000
+    qb, qo, tb, to = synth.short_pairs(79, n, 150)
+    qs, ts = seqgen.ont_like_pairs(31 + typ, 6, mean_len=3000, min_len=2100, max_len=4500)
+    lq, lqo = seqgen.pack_arrays(qs); lt, lto = seqgen.pack_arrays(ts)
+    for (m, x, g) in ((1, -1, -1), (2, -3, -2), (5, -4, -6)):
+        exp_s = CHK.align_batch_full(qb, qo[:4097], tb, to[:4097], typ, m, x, g, threads=THREADS)
+        exp_l = CHK.align_batch_full(lq, lqo, lt, lto, typ, m, x, g, threads=min(6, THREADS))
+        res = {}
+        for lds in (1, 0):
+            ctx.set_option("subst_lds", lds)
+            res[lds] = ctx.align_packed(qb, qo, tb, to, typ, m, x, g, True, cigar_cap=80 * n)
+            _equal(res[lds], exp_s, f"K1 lds={lds} scores {(m, x, g)}")   # (the checker saw the first 4 096 pairs)
+            got_l = ctx.align_packed(lq, lqo, lt, lto, typ, m, x, g, True)
+            _equal(got_l, exp_l, f"K3 lds={lds} scores {(m, x, g)}")
+        _equal(res[0], (res[1][0], res[1][1], res[1][2], res[1][3]), "K1 PRMT vs table, every pair")
+    ctx.set_option("subst_lds", 1)
+
+
+@pytest.mark.parametrize("typ", [0, 1, 2])
+def test_stripe_protocol_under_stress(ctx, typ):
+    """3 000 three-stripe pairs (4.2-6 kb queries): far more stripes than resident warps, tiny direction budget so the
+    batch runs as dozens of waves on two streams, walkers concurrent with the fill and after it -- every variant must
+    give the same bytes, and a sample is checked against the CPU."""
+    rng = np.random.default_rng(40 + typ)
+    base_q, base_t = [], []
+    for k in range(40):
+        L = int(rng.integers(4200, 6000))
+        t = seqgen.random_dna(rng, int(L * rng.uniform(0.3, 1.1)))
+        q = seqgen.random_dna(rng, L)
+        w = min(len(t), L) // 2
+        q[:w] = t[:w]                                   # related prefix, unrelated tail
+        base_q.append(q); base_t.append(t)
+    qs = [base_q[i % 40] for i in range(3000)]
+    ts = [base_t[(i * 7) % 40] for i in range(3000)]   # 280 distinct pairings
+    qb, qo = seqgen.pack_arrays(qs); tb, to = seqgen.pack_arrays(ts)
+    ref = None
+    for cw, budget in ((1, 1 << 28), (0, 1 << 28), (1, 48 << 30)):
+        ctx.set_option("concurrent_walk", cw)
+        ctx.set_option("dir_budget_bytes", budget)
+        got = ctx.align_packed(qb, qo, tb, to, typ, 1, -1, -1, True)
+        if ref is None:
+            ref = got
+            pick = list(range(0, 3000, 431))
+            for i in pick:
+                e = CHK.align(qs[i].tobytes(), ts[i].tobytes(), typ, 1, -1, -1, True)
+                assert (int(got[0][i]), int(got[1][i]), bytes(got[2][int(got[3][i]):int(got[3][i + 1])])) == e, i
+        else:
+            _equal(got, ref, f"concurrent_walk={cw} budget={budget}")
+    ctx.set_option("concurrent_walk", 1)
