@@ -13,18 +13,33 @@
 //     order there is implementation-defined.
 // All arithmetic of the path (minimizers, index, seeds, chaining, alignment) runs on the GPU through
 // include/b200map.h; this file is argument parsing, FASTA/FASTQ text, statistics and PAF printing.
+//
+// Host pipeline: the input files are mapped into memory and parsed in one pass (memchr over the mapping, the
+// sequences land back to back in ONE packed buffer with offsets -- exactly what b200_map_batch takes, so a batch is
+// a slice of it and nothing is copied per batch) while, on other threads, every device creates its contexts and
+// builds its copy of the index. Batches of reads are then taken from ONE queue by all workers of all devices
+// (two contexts / host threads per device), which balances itself whatever the read lengths; each worker formats
+// the PAF text of its batch from the batch's own result buffers, and the main thread writes finished batches in
+// input order while later ones are still being mapped.
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include <algorithm>
+#include <atomic>
+#include <charconv>
 #include <chrono>
+#include <condition_variable>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include <fstream>
 #include <functional>
 #include <iostream>
-#include <string>
-#include <atomic>
 #include <mutex>
+#include <string>
+#include <string_view>
 #include <thread>
 #include <unordered_map>
 #include <vector>
@@ -35,8 +50,6 @@ namespace {
 
 constexpr const char* kProgram = "toolForGenomeAllignment";   // the reference's PROGRAM_NAME, kept for scripts
 constexpr const char* kVersion = "3.1.0";
-
-struct Record { std::string name, seq; };
 
 double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
@@ -57,51 +70,97 @@ void usage(std::ostream& os) {
        << "\t  -h, --help, --version\n";
 }
 
-std::string first_token(const std::string& line) {
-    size_t e = 1;
-    while (e < line.size() && line[e] != ' ' && line[e] != '\t') ++e;
-    return line.substr(1, e - 1);
-}
-void chomp(std::string& s) { while (!s.empty() && (s.back() == '\n' || s.back() == '\r')) s.pop_back(); }
+// ---- input files: mapped read-only, parsed in place ----------------------------------------------------------
+struct MappedFile {
+    const char* p = nullptr;
+    size_t n = 0;
+    bool open(const std::string& path) {
+        const int fd = ::open(path.c_str(), O_RDONLY);
+        if (fd < 0) return false;
+        struct stat st;
+        if (fstat(fd, &st) != 0 || !S_ISREG(st.st_mode)) { ::close(fd); return false; }
+        n = (size_t)st.st_size;
+        if (n) {
+            void* m = mmap(nullptr, n, PROT_READ, MAP_PRIVATE, fd, 0);
+            if (m == MAP_FAILED) { ::close(fd); return false; }
+            madvise(m, n, MADV_SEQUENTIAL | MADV_WILLNEED);
+            p = static_cast<const char*>(m);
+        }
+        ::close(fd);
+        return true;
+    }
+};
 
-bool read_fasta(const std::string& path, std::vector<Record>& out) {
-    std::ifstream in(path);
-    if (!in) return false;
-    std::string line;
+// Sequences of a file, packed: sequence i is buf[off[i] .. off[i+1]); names point into the mapped file.
+struct SeqSet {
+    std::vector<std::string_view> names;
+    std::vector<char> buf;
+    std::vector<uint64_t> off{0};
+    size_t size() const { return names.size(); }
+    uint64_t len(size_t i) const { return off[i + 1] - off[i]; }
+};
+
+// one line [b, e) without its '\n' / '\r'; advances `at` past the newline
+inline bool next_line(const char* p, size_t n, size_t& at, const char*& b, const char*& e) {
+    if (at >= n) return false;
+    b = p + at;
+    const char* nl = static_cast<const char*>(std::memchr(b, '\n', n - at));
+    e = nl ? nl : p + n;
+    at = (size_t)(e - p) + (nl ? 1 : 0);
+    while (e > b && e[-1] == '\r') --e;
+    return true;
+}
+inline std::string_view first_token(const char* b, const char* e) {   // header without its marker, up to the first blank
+    const char* s = b + 1;
+    const char* t = s;
+    while (t < e && *t != ' ' && *t != '\t') ++t;
+    return std::string_view(s, (size_t)(t - s));
+}
+
+bool parse_fasta(const MappedFile& f, SeqSet& out) {
+    out = SeqSet();
+    out.buf.reserve(f.n);
+    size_t at = 0;
+    const char *b, *e;
     bool have = false;
-    while (std::getline(in, line)) {
-        chomp(line);
-        if (line.empty()) continue;
-        if (line[0] == '>') { out.push_back({first_token(line), ""}); have = true; }
-        else if (!have) return false;
-        else out.back().seq += line;
+    while (next_line(f.p, f.n, at, b, e)) {
+        if (b == e) continue;
+        if (*b == '>') {
+            if (have) out.off.push_back(out.buf.size());
+            out.names.push_back(first_token(b, e));
+            have = true;
+        } else if (!have) return false;
+        else out.buf.insert(out.buf.end(), b, e);
     }
-    return !out.empty();
+    if (have) out.off.push_back(out.buf.size());
+    return !out.names.empty();
 }
 
-bool read_fastq(const std::string& path, std::vector<Record>& out) {
-    std::ifstream in(path);
-    if (!in) return false;
-    std::string h, s, plus, q;
-    while (std::getline(in, h)) {
-        chomp(h);
-        if (h.empty()) continue;
-        if (h[0] != '@') return false;
-        if (!std::getline(in, s) || !std::getline(in, plus) || !std::getline(in, q)) return false;
-        chomp(s); chomp(plus); chomp(q);
-        if (plus.empty() || plus[0] != '+' || q.size() != s.size()) return false;
-        out.push_back({first_token(h), s});
+bool parse_fastq(const MappedFile& f, SeqSet& out) {
+    out = SeqSet();
+    out.buf.reserve(f.n / 2 + 64);
+    size_t at = 0;
+    const char *b, *e, *sb, *se, *pb, *pe, *qb, *qe;
+    while (next_line(f.p, f.n, at, b, e)) {
+        if (b == e) continue;
+        if (*b != '@') return false;
+        if (!next_line(f.p, f.n, at, sb, se) || !next_line(f.p, f.n, at, pb, pe) || !next_line(f.p, f.n, at, qb, qe)) return false;
+        if (pb == pe || *pb != '+' || qe - qb != se - sb) return false;
+        out.names.push_back(first_token(b, e));
+        out.buf.insert(out.buf.end(), sb, se);
+        out.off.push_back(out.buf.size());
     }
-    return !out.empty();
+    return !out.names.empty();
 }
 
-void basic_stats(const char* kind, const std::vector<Record>& recs) {   // reference :186-225 / :229-280
+void basic_stats(const char* kind, const SeqSet& recs) {   // reference :186-225 / :229-280
     size_t total = 0, mx = 0, mn = SIZE_MAX;
     std::vector<size_t> lens;
-    for (const auto& r : recs) {
-        std::cerr << "Sequence" << kind << " name: " << r.name << "\nLength of sequence: " << r.seq.size() << "\n";
-        lens.push_back(r.seq.size());
-        total += r.seq.size(); mx = std::max(mx, r.seq.size()); mn = std::min(mn, r.seq.size());
+    for (size_t i = 0; i < recs.size(); ++i) {
+        const size_t l = recs.len(i);
+        std::cerr << "Sequence" << kind << " name: " << recs.names[i] << "\nLength of sequence: " << l << "\n";
+        lens.push_back(l);
+        total += l; mx = std::max(mx, l); mn = std::min(mn, l);
     }
     std::cerr << "Total number of sequences: " << recs.size() << "\nAverage length of sequences: " << total / recs.size()
               << "\nMaximal length of sequence: " << mx << "\nMinimal length of sequence: " << mn << "\n";
@@ -111,15 +170,14 @@ void basic_stats(const char* kind, const std::vector<Record>& recs) {   // refer
 }
 
 // distinct minimizers / singleton fraction of one sequence (reference :481-525, :610-624), via MinimizeBatch
-void minimizer_stats(int device, const std::string& seq, bool fwd, uint32_t k, uint32_t w, const char* label) {
-    const uint64_t cnt = b200_minimize_count((uint32_t)seq.size(), k, w);
+void minimizer_stats(int device, const char* seq, size_t seq_len, bool fwd, uint32_t k, uint32_t w, const char* label) {
+    const uint64_t cnt = b200_minimize_count((uint32_t)seq_len, k, w);
     std::vector<uint32_t> hash(cnt ? cnt : 1), pos(cnt ? cnt : 1);
     std::vector<uint8_t> flag(cnt ? cnt : 1);
     uint64_t off[2] = {0, 0};
-    const char* sp = seq.data();
-    const uint32_t len = (uint32_t)seq.size();
+    const uint32_t len = (uint32_t)seq_len;
     const uint8_t fl = fwd ? 1 : 0;
-    if (b200_minimize_batch(device, 1, &sp, &len, k, w, &fl, hash.data(), pos.data(), flag.data(), off, cnt) != B200_OK) return;
+    if (b200_minimize_batch(device, 1, &seq, &len, k, w, &fl, hash.data(), pos.data(), flag.data(), off, cnt) != B200_OK) return;
     std::unordered_map<uint32_t, int> freq;
     for (uint64_t i = 0; i < cnt; ++i) freq[hash[i]]++;
     size_t singles = 0;
@@ -137,82 +195,136 @@ struct Options {
     std::string file1, file2;
 };
 
-struct MappedRead { b200_mapping m; std::string cigar; };
+// ---- PAF text (reference :685-698) -----------------------------------------------------------------------------
+inline void put_u64(std::string& s, uint64_t v) {
+    char tmp[24];
+    const auto r = std::to_chars(tmp, tmp + sizeof tmp, v);
+    s.append(tmp, (size_t)(r.ptr - tmp));
+}
+inline void put_i64(std::string& s, int64_t v) {
+    char tmp[24];
+    const auto r = std::to_chars(tmp, tmp + sizeof tmp, v);
+    s.append(tmp, (size_t)(r.ptr - tmp));
+}
 
-// one device: replicated index, a contiguous slice of the reads, chunked to bound device memory
-int map_slice(int device, const Options& o, const std::string& ref, const std::vector<Record>& reads, size_t lo, size_t hi,
-              bool fastq, std::vector<MappedRead>& out, std::string& err) {
-    const bool trace = std::getenv("B200_TRACE") != nullptr;
+struct Batch {
+    size_t lo = 0, hi = 0;        // reads [lo, hi)
+    std::string paf;              // the batch's PAF lines, input order
+    bool done = false;
+};
+
+// Everything the workers share.
+struct Job {
+    const Options* o = nullptr;
+    const SeqSet* reads = nullptr;
+    std::string_view ref_name;
+    const char* ref = nullptr;
+    uint64_t ref_len = 0;
+    bool fastq = false;
+    std::vector<Batch> batches;
+    std::atomic<size_t> next{0};
+    std::atomic<int> failed{0};
+    std::mutex mu;                // guards `done` flags and `err`
+    std::condition_variable cv;
+    std::string err;
+    bool ready = false;           // batches are final (the fragments file has been parsed)
+    bool trace = false;
+    uint64_t max_bases = 0;       // largest batch, for the result buffers
+    size_t max_reads = 0;
+};
+
+void format_batch(const Job& J, const Batch& b, const b200_mapping* m, const char* cig, const uint64_t* coff, std::string& out) {
+    const Options& o = *J.o;
+    const uint64_t RL = J.ref_len;
+    out.clear();
+    for (size_t r = b.lo; r < b.hi; ++r) {
+        const b200_mapping& x = m[r - b.lo];
+        if (!x.mapped) continue;
+        const uint64_t ts = x.strand_fwd ? x.t_begin : RL - x.t_end - 1, te = x.strand_fwd ? (uint64_t)x.t_end + 1 : RL - x.t_begin;
+        out.append(J.reads->names[r]); out += '\t'; put_u64(out, J.reads->len(r)); out += '\t';
+        put_u64(out, x.q_begin); out += '\t'; put_u64(out, (uint64_t)x.q_end + 1); out += '\t';
+        out += x.strand_fwd ? '+' : '-'; out += '\t'; out.append(J.ref_name); out += '\t'; put_u64(out, RL); out += '\t';
+        put_u64(out, ts); out += '\t'; put_u64(out, te); out += '\t'; put_i64(out, x.score);
+        out += '\t'; put_u64(out, (uint64_t)x.q_end - x.q_begin + 1); out += "\t60";
+        if (o.cigar) { out += "\tcg:Z:"; out.append(cig + coff[r - b.lo], (size_t)(coff[r - b.lo + 1] - coff[r - b.lo])); }
+        out += '\n';
+    }
+}
+
+// One worker = one context (own streams and workspaces) on `device`, the device's index shared. Takes batches from
+// the job's queue until it is empty. b200_map_batch is a blocking call on one context; with two workers per device
+// one batch's seeding, chaining, planning and downloads overlap the other's alignment kernels.
+void worker(Job& J, int device, int wi, b200_ctx* ctx, const b200_index* ix) {
+    const Options& o = *J.o;
+    std::vector<b200_mapping> m(J.max_reads ? J.max_reads : 1);
+    const uint64_t cap = o.cigar ? 4 * J.max_bases + 64 * J.max_reads + 64 : 0;
+    std::vector<char> cig(cap ? cap : 1);
+    std::vector<uint64_t> coff(J.max_reads + 1, 0);
+    std::string text;
+    for (;;) {
+        const size_t bi = J.next.fetch_add(1);
+        if (bi >= J.batches.size() || J.failed.load()) return;
+        Batch& b = J.batches[bi];
+        const size_t n = b.hi - b.lo;
+        const double t0 = now_s();
+        const int e = b200_map_batch(ctx, ix, n, J.reads->buf.data(), J.reads->off.data() + b.lo, J.fastq ? 1 : 0, o.type, o.match,
+                                     o.mismatch, o.gap, o.cigar ? 1 : 0, m.data(), o.cigar ? cig.data() : nullptr,
+                                     o.cigar ? coff.data() : nullptr, cap);
+        if (e != B200_OK) {
+            // the reference logs and skips a read whose Align throws (:680-683); a batch failure is fatal here
+            std::lock_guard<std::mutex> g(J.mu);
+            if (J.err.empty()) J.err = std::string("ERROR: Exception during Align: ") + b200_last_error();
+            J.failed.store(1);
+            J.cv.notify_all();
+            return;
+        }
+        const double t1 = now_s();
+        format_batch(J, b, m.data(), cig.data(), coff.data(), text);
+        {
+            std::lock_guard<std::mutex> g(J.mu);
+            b.paf.swap(text);
+            b.done = true;
+        }
+        J.cv.notify_all();
+        if (J.trace)
+            std::fprintf(stderr, "[b200_mapper trace] gpu %d worker %d: batch of %zu reads mapped in %.3f s, formatted in %.3f s\n", device, wi, n,
+                         t1 - t0, now_s() - t1);
+    }
+}
+
+// One device: two contexts at most, one index; runs its workers to the end of the queue.
+void device_main(Job& J, int device, int n_workers) {
+    const Options& o = *J.o;
     const double t0 = now_s();
-    b200_ctx* ctx = nullptr;
-    if (b200_ctx_create(device, &ctx) != B200_OK) { err = b200_last_error(); return 1; }
+    std::vector<b200_ctx*> ctxs((size_t)n_workers, nullptr);
+    auto fail_with = [&](const std::string& what) {
+        std::lock_guard<std::mutex> g(J.mu);
+        if (J.err.empty()) J.err = what;
+        J.failed.store(1);
+        J.cv.notify_all();
+    };
+    if (b200_ctx_create(device, &ctxs[0]) != B200_OK) { fail_with(b200_last_error()); return; }
+    // the second context is created next to the index build (its start-up is host and allocator time)
+    std::thread second_ctx;
+    if (n_workers > 1) second_ctx = std::thread([&] { if (b200_ctx_create(device, &ctxs[1]) != B200_OK) ctxs[1] = nullptr; });
     const double t1 = now_s();
     b200_index* ix = nullptr;
-    if (b200_index_build(ctx, ref.data(), ref.size(), o.k, o.w, o.f, &ix) != B200_OK) { err = b200_last_error(); b200_ctx_destroy(ctx); return 1; }
-    if (trace) std::fprintf(stderr, "[b200_mapper trace] gpu %d: context %.3f s, index %.3f s\n", device, t1 - t0, now_s() - t1);
-    // Batches of bounded size, taken in turn by up to two workers. b200_map_batch is a blocking call on one context;
-    // with a second context (own streams and workspaces, the index shared) one batch's seeding, chaining, planning
-    // and downloads overlap the other's alignment kernels.
-    // (B200_MAPPER_BATCH_READS / B200_MAPPER_WORKERS: test knobs -- small batches, a single worker)
-    const char* env_batch = std::getenv("B200_MAPPER_BATCH_READS");
-    const char* env_workers = std::getenv("B200_MAPPER_WORKERS");
-    // A second context costs its own start-up (about half a second: tens of GB of workspace), so small inputs go
-    // through one context in large batches, as before; from 32 k reads on, batches of 8 k reads and two workers.
-    const bool small = hi - lo < 32768;
-    const size_t max_reads = env_batch && std::atol(env_batch) > 0 ? (size_t)std::atol(env_batch) : (small ? 65536 : 8192);
-    const uint64_t max_bases = small ? (256ull << 20) : (64ull << 20);
-    const int max_workers = env_workers && std::atoi(env_workers) > 0 ? std::atoi(env_workers) : (small ? 1 : 2);
-    std::vector<std::pair<size_t, size_t>> batches;
-    for (size_t i = lo; i < hi;) {
-        size_t j = i; uint64_t bases = 0;
-        while (j < hi && j - i < max_reads && bases < max_bases) bases += reads[j++].seq.size();
-        batches.emplace_back(i, j);
-        i = j;
+    const int rc = b200_index_build(ctxs[0], J.ref, J.ref_len, o.k, o.w, o.f, &ix);
+    if (second_ctx.joinable()) second_ctx.join();
+    if (rc != B200_OK) { fail_with(b200_last_error()); return; }
+    if (J.trace) std::fprintf(stderr, "[b200_mapper trace] gpu %d: context %.3f s, index %.3f s\n", device, t1 - t0, now_s() - t1);
+    {   // the fragments are parsed on the main thread meanwhile
+        std::unique_lock<std::mutex> lk(J.mu);
+        J.cv.wait(lk, [&] { return J.ready || J.failed.load(); });
     }
-    std::atomic<size_t> next{0};
-    std::atomic<int> rc{0};
-    std::mutex err_mutex;
-    auto worker = [&](b200_ctx* wctx, int wi) {
-        for (;;) {
-            const size_t bi = next.fetch_add(1);
-            if (bi >= batches.size() || rc.load()) return;
-            const size_t i = batches[bi].first, j = batches[bi].second;
-            uint64_t bases = 0;
-            for (size_t r = i; r < j; ++r) bases += reads[r].seq.size();
-            std::string buf; buf.reserve(bases);
-            std::vector<uint64_t> off(j - i + 1, 0);
-            for (size_t r = i; r < j; ++r) { buf += reads[r].seq; off[r - i + 1] = buf.size(); }
-            std::vector<b200_mapping> m(j - i);
-            const uint64_t cap = o.cigar ? 4 * bases + 64 * (j - i) + 64 : 0;
-            std::vector<char> cig(cap ? cap : 1);
-            std::vector<uint64_t> coff(j - i + 1, 0);
-            const double tb0 = now_s();
-            const int e = b200_map_batch(wctx, ix, j - i, buf.data(), off.data(), fastq ? 1 : 0, o.type, o.match, o.mismatch, o.gap,
-                                         o.cigar ? 1 : 0, m.data(), o.cigar ? cig.data() : nullptr, o.cigar ? coff.data() : nullptr, cap);
-            if (trace) std::fprintf(stderr, "[b200_mapper trace] gpu %d worker %d: batch of %zu reads mapped in %.3f s\n", device, wi, j - i, now_s() - tb0);
-            if (e != B200_OK) {
-                // the reference logs and skips a read whose Align throws (:680-683); a batch failure is fatal here
-                std::lock_guard<std::mutex> g(err_mutex);
-                err = std::string("ERROR: Exception during Align: ") + b200_last_error();
-                rc.store(1);
-                return;
-            }
-            for (size_t r = i; r < j; ++r) {
-                out[r].m = m[r - i];
-                if (o.cigar) out[r].cigar.assign(cig.data() + coff[r - i], cig.data() + coff[r - i + 1]);
-            }
-        }
-    };
-    b200_ctx* ctx2 = nullptr;
-    if (batches.size() >= 2 && max_workers >= 2 && b200_ctx_create(device, &ctx2) != B200_OK) ctx2 = nullptr;   // one worker is still correct
-    std::thread second;
-    if (ctx2) second = std::thread(worker, ctx2, 1);
-    worker(ctx, 0);
-    if (second.joinable()) second.join();
-    // The index and the context (tens of GB of device workspace) are deliberately not destroyed: the process is
+    if (J.failed.load()) return;
+    std::vector<std::thread> th;
+    for (int wi = 1; wi < n_workers; ++wi)
+        if (ctxs[(size_t)wi]) th.emplace_back(worker, std::ref(J), device, wi, ctxs[(size_t)wi], ix);   // one worker is still correct
+    worker(J, device, 0, ctxs[0], ix);
+    for (auto& t : th) t.join();
+    // The index and the contexts (tens of GB of device workspace) are deliberately not destroyed: the process is
     // about to exit, and returning that memory piece by piece costs about a second.
-    (void)ix;
-    return rc.load();
 }
 
 }  // namespace
@@ -250,56 +362,89 @@ int main(int argc, char** argv) {
     }
     if (o.file1.empty() || o.file2.empty()) { std::cerr << "Error: Two input files are required.\n"; usage(std::cout); return 1; }
 
-    std::vector<Record> refs;
-    if (!read_fasta(o.file1, refs)) { std::cerr << "Given reference file is not in FASTA format! \n"; return 1; }
-    const Record& ref = refs.front();   // only the first sequence is the reference (:415)
-    std::vector<Record> reads;
-    bool fastq = read_fastq(o.file2, reads);   // FASTQ first, FASTA on failure (:533-556)
-    if (!fastq) { reads.clear(); if (!read_fasta(o.file2, reads)) { std::cerr << "Given file is not in FASTA or FASTQ format! \n"; return 1; } }
-
-    const double t_parsed = now_s();
+    MappedFile f1, f2;
+    SeqSet refs, reads;
+    if (!f1.open(o.file1) || !parse_fasta(f1, refs)) { std::cerr << "Given reference file is not in FASTA format! \n"; return 1; }
+    // only the first sequence is the reference (:415)
+    const char* ref = refs.buf.data();
+    const uint64_t ref_len = refs.len(0);
     if (b200_device_count() <= 0) { std::cerr << "Error: no CUDA device visible (this mapper has no CPU fallback)\n"; return 1; }
     o.gpus = std::min(o.gpus, b200_device_count());
+
+    // The devices start up (contexts, index) while the fragments file is parsed. A second context per device (its
+    // start-up runs next to the index build) only when the input is large enough to keep two batches in flight.
+    // (B200_MAPPER_BATCH_READS / B200_MAPPER_WORKERS: test knobs.)
+    Job J;
+    J.o = &o; J.reads = &reads; J.ref_name = refs.names[0]; J.ref = ref; J.ref_len = ref_len; J.trace = trace;
+    if (!f2.open(o.file2)) { std::cerr << "Given file is not in FASTA or FASTQ format! \n"; return 1; }
+    const char* env_batch = std::getenv("B200_MAPPER_BATCH_READS");
+    const char* env_workers = std::getenv("B200_MAPPER_WORKERS");
+    const bool small = f2.n < ((size_t)192 << 20) * (size_t)o.gpus && o.gpus == 1;
+    const int workers_per_device = env_workers && std::atoi(env_workers) > 0 ? std::atoi(env_workers) : (small ? 1 : 2);
+    std::vector<std::thread> devs;
+    for (int g = 0; g < o.gpus; ++g) devs.emplace_back(device_main, std::ref(J), g, workers_per_device);
+    auto abort_devices = [&] {
+        { std::lock_guard<std::mutex> g(J.mu); J.failed.store(1); }
+        J.cv.notify_all();
+        for (auto& t : devs) t.join();
+    };
+
+    bool fastq = parse_fastq(f2, reads);   // FASTQ first, FASTA on failure (:533-556)
+    if (!fastq && !parse_fasta(f2, reads)) {
+        abort_devices();
+        std::cerr << "Given file is not in FASTA or FASTQ format! \n";
+        std::fflush(stderr);
+        std::_Exit(1);
+    }
+    J.fastq = fastq;
+    const double t_parsed = now_s();
 
     if (o.stats) {
         std::cerr << "Basic statistic for reference genome\n------------------------------------\n";
         basic_stats("FASTA", refs);
-        minimizer_stats(0, ref.seq, true, o.k, o.w, "forward strand");
+        minimizer_stats(0, ref, ref_len, true, o.k, o.w, "forward strand");
         std::cerr << "\nBasic statistic for fragments of genome\n------------------------------------\n";
         basic_stats(fastq ? "FASTQ" : "FASTA", reads);
     }
 
-    std::vector<MappedRead> mapped(reads.size());
-    std::vector<std::thread> th;
-    std::vector<int> rcs(o.gpus, 0);
-    std::vector<std::string> errs(o.gpus);
-    for (int g = 0; g < o.gpus; ++g) {
-        const size_t lo = reads.size() * g / o.gpus, hi = reads.size() * (g + 1) / o.gpus;
-        th.emplace_back([&, g, lo, hi] { rcs[g] = map_slice(g, o, ref.seq, reads, lo, hi, fastq, mapped, errs[g]); });
+    // Batches of bounded size: small inputs go through one context in large batches, larger ones in batches of 8 k
+    // reads taken from one queue by every worker of every device.
+    const size_t n_reads = reads.size();
+    const size_t max_reads = env_batch && std::atol(env_batch) > 0 ? (size_t)std::atol(env_batch) : (small ? 65536 : 8192);
+    const uint64_t max_bases = small ? (256ull << 20) : (64ull << 20);
+    for (size_t i = 0; i < n_reads;) {
+        size_t j = i;
+        uint64_t bases = 0;
+        while (j < n_reads && j - i < max_reads && bases < max_bases) bases += reads.len(j++);
+        Batch b; b.lo = i; b.hi = j;
+        J.batches.push_back(std::move(b));
+        J.max_bases = std::max(J.max_bases, bases);
+        J.max_reads = std::max(J.max_reads, j - i);
+        i = j;
     }
-    for (auto& t : th) t.join();
-    for (int g = 0; g < o.gpus; ++g) if (rcs[g]) { std::cerr << errs[g] << std::endl; return 1; }
-    const double t_mapped = now_s();
+    { std::lock_guard<std::mutex> g(J.mu); J.ready = true; }
+    J.cv.notify_all();
 
-    const uint64_t RL = ref.seq.size();
-    std::string outbuf;
-    for (size_t i = 0; i < reads.size(); ++i) {   // PAF, input order (:687-697)
-        const b200_mapping& m = mapped[i].m;
-        if (!m.mapped) continue;
-        const uint64_t ts = m.strand_fwd ? m.t_begin : RL - m.t_end - 1, te = m.strand_fwd ? (uint64_t)m.t_end + 1 : RL - m.t_begin;
-        outbuf += reads[i].name; outbuf += '\t'; outbuf += std::to_string(reads[i].seq.size()); outbuf += '\t';
-        outbuf += std::to_string(m.q_begin); outbuf += '\t'; outbuf += std::to_string((uint64_t)m.q_end + 1); outbuf += '\t';
-        outbuf += m.strand_fwd ? "+" : "-"; outbuf += '\t'; outbuf += ref.name; outbuf += '\t'; outbuf += std::to_string(RL); outbuf += '\t';
-        outbuf += std::to_string(ts); outbuf += '\t'; outbuf += std::to_string(te); outbuf += '\t'; outbuf += std::to_string(m.score);
-        outbuf += '\t'; outbuf += std::to_string(m.q_end - m.q_begin + 1); outbuf += "\t60";
-        if (o.cigar) { outbuf += "\tcg:Z:"; outbuf += mapped[i].cigar; }
-        outbuf += '\n';
-        if (outbuf.size() > (1u << 20)) { std::fwrite(outbuf.data(), 1, outbuf.size(), stdout); outbuf.clear(); }
+    // writer: finished batches in input order, while later ones are still being mapped
+    size_t written = 0;
+    bool failed = false;
+    while (written < J.batches.size()) {
+        std::string text;
+        {
+            std::unique_lock<std::mutex> lk(J.mu);
+            J.cv.wait(lk, [&] { return J.batches[written].done || J.failed.load(); });
+            if (!J.batches[written].done) { failed = true; break; }
+            text.swap(J.batches[written].paf);
+        }
+        std::fwrite(text.data(), 1, text.size(), stdout);
+        ++written;
     }
-    std::fwrite(outbuf.data(), 1, outbuf.size(), stdout);
+    for (auto& t : devs) t.join();
+    if (failed || J.failed.load()) { std::cerr << J.err << std::endl; std::fflush(stdout); std::_Exit(1); }
+    const double t_done = now_s();
     if (trace)
-        std::fprintf(stderr, "[b200_mapper trace] read files %.3f s, index + map %.3f s, write PAF %.3f s\n", t_parsed - t_start,
-                     t_mapped - t_parsed, now_s() - t_mapped);
+        std::fprintf(stderr, "[b200_mapper trace] read files %.3f s, index + map + write PAF %.3f s (%zu batches, %d devices x %d workers)\n",
+                     t_parsed - t_start, t_done - t_parsed, J.batches.size(), o.gpus, workers_per_device);
     std::fflush(stdout);
     std::fflush(stderr);
     std::_Exit(0);   // skip the CUDA runtime's teardown of the (large) device allocations

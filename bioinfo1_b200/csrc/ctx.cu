@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <new>
+#include <utility>
 
 #include "internal.hpp"
 
@@ -99,6 +100,10 @@ extern "C" int b200_ctx_create(int device, b200_ctx** out) {
         }
     }
     align_kernels_configure();
+    // tuning runs: defaults of a few options from the environment (B200_SUBST_LDS, B200_TAPER_TAIL, B200_CONCURRENT_WALK)
+    for (auto kv : {std::pair<const char*, int64_t*>{"B200_SUBST_LDS", &c->subst_lds}, {"B200_TAPER_TAIL", &c->taper_tail},
+                    {"B200_CONCURRENT_WALK", &c->concurrent_walk}})
+        if (const char* e = std::getenv(kv.first)) *kv.second = std::atoll(e);
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess)
         c->dir_budget_bytes = std::max<int64_t>(1ll << 30, (int64_t)(free_b / 3));
