@@ -217,8 +217,16 @@ __device__ __forceinline__ uint32_t max_tree16(const uint32_t (&Y)[N]) {
 // (8, 16, 24 or 32) register rows over every column. Blocks are 32 rows apart whatever RB is: only the LAST
 // block of a group is trimmed (150-row pairs: 4 x 32 + 24 rows instead of 5 x 32), its unused direction words
 // are stored as zeros and never read (the walker only visits rows <= Q).
-template <int TYPE, int SUB>   // SUB: 0 = substitution term by PRMT, 1 = by shared-memory lookup (SubstTable)
+// SUB bit 0: substitution term by PRMT (0) or by shared-memory lookup (1, SubstTable).
+// SUB bit 1: software-pipelined columns. The row loop of a column is one dependent chain (fused add-max, then the
+//   re-arm LOP3: 8 cycles per row) with little else to issue next to it once the 32 independent "diagonal or left"
+//   maxima of the column have been computed up front -- ncu shows the warps of a scheduler waiting on that chain
+//   (stall "wait") while the alu pipe idles. Pipelined, the loop computes next column's maximum for row r right after
+//   this column's value of row r exists: the independent work is spread along the chain instead of preceding it.
+template <int TYPE, int SUBV>
 struct ShortSweep {
+    static constexpr int SUB = SUBV & 1;
+    static constexpr bool PIPE = (SUBV & 2) != 0;
     uint32_t tab_at;       // SUB = 1: shared address of the lane's column of the substitution table
     // the thread's two pairs
     uint32_t QA, TA, QB, TB;
@@ -254,8 +262,10 @@ struct ShortSweep {
         // per-row PRMT selectors: byte0 = tabA[qA], byte1 = its sign, byte2 = tabB[qB], byte3 = sign
         uint32_t sel[RB], Y[RB];
         {
-            const uint32_t qa0 = qwA[(i0 >> 4)], qa1 = RB > 16 ? qwA[(i0 >> 4) + 1] : 0u;
-            const uint32_t qb0 = qwB[(i0 >> 4)], qb1 = RB > 16 ? qwB[(i0 >> 4) + 1] : 0u;
+            // (sequence words through L2: they are fetched a step ahead anyway, and in streaming mode they were written
+            // by a pack kernel that ran while this one was already resident -- L1 is not coherent with that)
+            const uint32_t qa0 = __ldcg(qwA + (i0 >> 4)), qa1 = RB > 16 ? __ldcg(qwA + (i0 >> 4) + 1) : 0u;
+            const uint32_t qb0 = __ldcg(qwB + (i0 >> 4)), qb1 = RB > 16 ? __ldcg(qwB + (i0 >> 4) + 1) : 0u;
 #pragma unroll
             for (int r = 0; r < RB; ++r) {
                 const uint32_t ca = ((r < 16 ? qa0 : qa1) >> (2 * (r & 15))) & 3u;
@@ -271,7 +281,7 @@ struct ShortSweep {
         // column would leave only a few instructions between issue and use)
         uint32_t top_next = (b == 0) ? dup16(frame * 1 + 1) : my_bnd[(size_t)1 * kWarp];
         uint32_t top_next2 = (b == 0) ? dup16(frame * 2 + 1) : my_bnd[(size_t)2 * kWarp];
-        uint32_t tA_next = twA[0], tB_next = twB[0], tA = 0, tB = 0;
+        uint32_t tA_next = __ldcg(twA), tB_next = __ldcg(twB), tA = 0, tB = 0;
         uint32_t* dcol = dirs_g ? dirs_g + (uint64_t)b * Tg * 128 : nullptr;
 
         // hoisted end-cell test: the column at which this block holds cell (Q,T) of either pair
@@ -284,18 +294,31 @@ struct ShortSweep {
         const uint32_t rqA = lastA ? QA - 1 - i0 : 0u, rqB = lastB ? QB - 1 - i0 : 0u;
         const bool full_rows = nvA == (uint32_t)RB && nvB == (uint32_t)RB;
         const uint32_t Tmin = min(TA, TB);
-#pragma unroll 2
-        for (uint32_t j = 1; j <= Tm; ++j) {
-            if (((j - 1) & 15u) == 0) {
+        // codes and substitution tables of column jj (columns are visited in order: a 16-column word at a time)
+        uint32_t tabA = 0, tabB = 0;
+        auto column_tables = [&](uint32_t jj) {
+            if (((jj - 1) & 15u) == 0) {
                 tA = tA_next; tB = tB_next;
-                tA_next = twA[((j - 1) >> 4) + 1]; tB_next = twB[((j - 1) >> 4) + 1];
+                tA_next = __ldcg(twA + ((jj - 1) >> 4) + 1); tB_next = __ldcg(twB + ((jj - 1) >> 4) + 1);
             }
             const uint32_t cA = tA & 3u, cB = tB & 3u;
             tA >>= 2; tB >>= 2;
             // per-column byte tables: entry c = S'(c, target) (match where c == target code); or the column part
             // of the shared-memory table index
-            const uint32_t tabA = SUB ? subst_col_part(cA, cB) : K.tab_mis ^ (K.tab_diff << (8 * cA));
-            const uint32_t tabB = SUB ? K.one32 : K.tab_mis ^ (K.tab_diff << (8 * cB));
+            tabA = SUB ? subst_col_part(cA, cB) : K.tab_mis ^ (K.tab_diff << (8 * cA));
+            tabB = SUB ? K.one32 : K.tab_mis ^ (K.tab_diff << (8 * cB));
+        };
+        auto subst = [&](int r) { return SUB ? subst_lookup(sel[r], tabA, tabB) : prmt(tabA, tabB, sel[r]); };
+        uint32_t M[PIPE ? RB : 1];   // PIPE: max(diagonal + S, left) of the column about to be swept
+        if (PIPE) {
+            column_tables(1);
+#pragma unroll
+            for (int r = 0; r < RB; ++r) M[r] = __viaddmax_s16x2(r ? Y[r - 1] : top_prev, subst(r), Y[r]);
+        }
+#pragma unroll 2
+        for (uint32_t j = 1; j <= Tm; ++j) {
+            // PIPE: the tables of the NEXT column (its maxima are made in this sweep; one word past the end is a spare)
+            column_tables(PIPE ? j + 1 : j);
             const uint32_t top = top_next;
             top_next = top_next2;
             if (j + 2 <= Tm) top_next2 = (b == 0) ? dup16(frame * (int)(j + 2) + 1) : my_bnd[(size_t)(j + 2) * kWarp];
@@ -306,13 +329,14 @@ struct ShortSweep {
             const uint32_t clampv = dup16(3 - 4 * K.gap * (int)j);   // local: H = 0 with the stop tag, this column's frame
 #pragma unroll
             for (int r = 0; r < RB; ++r) {
-                const uint32_t S = SUB ? subst_lookup(sel[r], tabA, tabB) : prmt(tabA, tabB, sel[r]);
-                const uint32_t m1 = __viaddmax_s16x2(dg, S, Y[r]);
-                uint32_t Z = __viaddmax_s16x2(up, K.cu, m1);
+                const uint32_t above = up;
+                const uint32_t m1 = PIPE ? M[r] : __viaddmax_s16x2(dg, subst(r), Y[r]);
+                uint32_t Z = __viaddmax_s16x2(above, K.cu, m1);
                 if (TYPE == 1) Z = __vmaxs2(Z, clampv);   // clamp at 0 (team_alignment.cpp:185), tag 3 = stop
                 dg = Y[r];
                 Y[r] = lop3_and_or(Z, MASK, ONE);
                 up = Y[r];
+                if (PIPE) M[r] = __viaddmax_s16x2(above, subst(r), Y[r]);   // next column: diagonal = the row above, left = this cell
                 // direction tags: two multiply-add chains on the fma pipe; (Z - Y) = tag - 1 per half
                 accZ = accZ * FOUR + Z;
                 accY = accY * FOUR + Y[r];
@@ -380,6 +404,27 @@ struct ShortSweep {
     }
 };
 
+// Streaming mode (host pipeline of a uniform batch): ONE launch of the fill serves the whole batch while its bytes
+// are still arriving. The upload goes in slices; after a slice has landed and been 2-bit packed, a one-thread kernel
+// raises `watermark` to the number of pairs that are ready. A warp that has taken group g waits until its 64 pairs are
+// below the watermark, sweeps them, and counts the group as done for its wave (= upload slice), on which that wave's
+// traceback kernel waits. Warps of a persistent launch drift apart and keep the alu pipe busy; a launch per wave
+// starts and ends every warp together and lost a third of the throughput. watermark == nullptr: the classic mode.
+struct ShortStream {
+    const uint32_t* watermark;   // pairs uploaded + packed so far (release / acquire)
+    uint32_t* wave_done;         // [n_waves] groups finished, one counter per wave
+    uint32_t* stall_flag;        // raised when a warp gives up waiting (never hang the device)
+    uint32_t n_waves;
+    uint32_t group_start[33];    // first group of each wave, then the group count
+    uint64_t dir_base[32];       // word offset of each wave's direction block
+};
+
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
 // The trimmed variants are real calls: inlined next to the 32-row loop they cost that loop its register
 // allocation (measured: -8 % on every block); a call per group is free.
 template <int TYPE, int SUB, int RB>
@@ -395,9 +440,10 @@ __global__ void __launch_bounds__(kShortThreads, 7)
 fill_short_kernel(const uint32_t* __restrict__ qpk, const uint32_t* __restrict__ tpk,
                   const PairDesc* __restrict__ pairs, const uint32_t* __restrict__ work, uint32_t n_work,
                   const ShortGroup* __restrict__ groups, uint32_t* __restrict__ group_counter,
-                  const uint8_t* __restrict__ flags, ShortConsts K,
+                  const uint8_t* flags, ShortConsts K,
                   uint32_t* __restrict__ dirs, uint32_t* bnd, uint32_t bnd_cols,
-                  int32_t* __restrict__ score, uint32_t* __restrict__ end_i, uint32_t* __restrict__ end_j) {
+                  int32_t* __restrict__ score, uint32_t* __restrict__ end_i, uint32_t* __restrict__ end_j,
+                  const ShortStream stream_ctl) {
     constexpr int R = kShortRows;
     const int lane = threadIdx.x & 31;
     const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -405,7 +451,7 @@ fill_short_kernel(const uint32_t* __restrict__ qpk, const uint32_t* __restrict__
     ShortSweep<TYPE, SUB> sw;
     sw.my_bnd = bnd + (size_t)warp_global * bnd_cols * kWarp + lane;   // [col][lane]
     sw.tab_at = 0;
-    if (SUB) {
+    if (SUB & 1) {
         __shared__ uint32_t subst_tab[kSubstWords];
         subst_table_fill(subst_tab, K, threadIdx.x, kShortThreads);
         __syncthreads();
@@ -417,6 +463,23 @@ fill_short_kernel(const uint32_t* __restrict__ qpk, const uint32_t* __restrict__
         if (lane == 0) g = atomicAdd(group_counter, 1u);
         g = __shfl_sync(kFull, g, 0);
         if (g >= n_groups) break;
+        uint32_t wave = 0;
+        uint64_t dir_base = 0;
+        if (stream_ctl.watermark) {   // streaming mode: wait until the group's pairs have landed and been packed
+            while (wave + 1 < stream_ctl.n_waves && g >= stream_ctl.group_start[wave + 1]) ++wave;
+            dir_base = stream_ctl.dir_base[wave];
+            const uint32_t need = min(n_work, (g + 1) * 64);
+            uint32_t ok = 1;
+            if (lane == 0) {
+                uint32_t spins = 0;
+                while (ld_acquire_gpu(stream_ctl.watermark) < need) {
+                    __nanosleep(200);
+                    if (++spins > (1u << 23)) { atomicExch(stream_ctl.stall_flag, 1u); ok = 0; break; }
+                }
+            }
+            ok = __shfl_sync(kFull, ok, 0);
+            if (!ok) break;
+        }
 
         // my two pairs
         const uint32_t wa = g * 64 + 2 * lane, wb = wa + 1;
@@ -424,17 +487,17 @@ fill_short_kernel(const uint32_t* __restrict__ qpk, const uint32_t* __restrict__
         sw.QA = 0; sw.TA = 0; sw.QB = 0; sw.TB = 0;
         sw.qwA = qpk; sw.twA = tpk; sw.qwB = qpk; sw.twB = tpk;
         sw.Tg = groups[g].cols;
-        sw.dirs_g = dirs ? dirs + groups[g].dir_off + (uint64_t)lane * 4 : nullptr;
+        sw.dirs_g = dirs ? dirs + dir_base + groups[g].dir_off + (uint64_t)lane * 4 : nullptr;
         if (wa < n_work) {
             pA = work[wa];
             const PairDesc d = pairs[pA];
-            if (flags[pA] == 0) { sw.QA = d.Q; sw.TA = d.T; sw.qwA = qpk + d.qpk_off; sw.twA = tpk + d.tpk_off; }
+            if (__ldcg(flags + pA) == 0) { sw.QA = d.Q; sw.TA = d.T; sw.qwA = qpk + d.qpk_off; sw.twA = tpk + d.tpk_off; }
             else pA = 0xffffffffu;   // not pure ACGT: the generic kernel owns it
         }
         if (wb < n_work) {
             pB = work[wb];
             const PairDesc d = pairs[pB];
-            if (flags[pB] == 0) { sw.QB = d.Q; sw.TB = d.T; sw.qwB = qpk + d.qpk_off; sw.twB = tpk + d.tpk_off; }
+            if (__ldcg(flags + pB) == 0) { sw.QB = d.Q; sw.TB = d.T; sw.qwB = qpk + d.qpk_off; sw.twB = tpk + d.tpk_off; }
             else pB = 0xffffffffu;
         }
         const uint32_t QA = sw.QA, TA = sw.TA, QB = sw.QB, TB = sw.TB;
@@ -481,6 +544,13 @@ fill_short_kernel(const uint32_t* __restrict__ qpk, const uint32_t* __restrict__
         if (TYPE == 1) {
             if (pA != 0xffffffffu) { score[pA] = liveA ? sw.bvA : 0; end_i[pA] = liveA ? sw.biA : 0u; end_j[pA] = liveA ? sw.bjA : 0u; }
             if (pB != 0xffffffffu) { score[pB] = liveB ? sw.bvB : 0; end_i[pB] = liveB ? sw.biB : 0u; end_j[pB] = liveB ? sw.bjB : 0u; }
+        }
+        if (stream_ctl.watermark) {
+            // every lane's direction words and results device-wide before the wave's count (the traceback kernel of the
+            // wave acquires the count): each lane fences its own stores, the warp barrier orders them before lane 0's
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) { __threadfence(); atomicAdd(stream_ctl.wave_done + wave, 1u); }
         }
     }
 }

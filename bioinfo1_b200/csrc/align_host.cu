@@ -4,6 +4,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <emmintrin.h>
+
 #include <algorithm>
 #include <atomic>
 #include <functional>
@@ -174,7 +176,7 @@ unsigned host_threads() {
     static const unsigned n = [] {
         const char* e = std::getenv("B200_HOST_THREADS");
         unsigned v = e ? (unsigned)std::atoi(e) : 0;
-        if (v == 0) v = std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+        if (v == 0) v = std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
         return std::max(1u, std::min(v, 64u));
     }();
     return n;
@@ -183,6 +185,18 @@ unsigned host_threads() {
 // Gathers n (pointer, length) sequences of two arrays into two packed buffers with their n+1 offsets. Pairs are cut
 // into blocks taken in order from a shared counter, so a prefix of the packed bytes is complete early and grows
 // steadily; wait_pairs(p) returns once every pair below p is in place.
+// memcpy for the gather: short sequences (a 150-base read) in 16-byte steps with an overlapping last step -- a
+// library call per read costs more than the copy itself -- and long runs through memcpy.
+inline void copy_bytes(char* d, const char* s, uint64_t n) {
+    if (n >= 16 && n <= 512) {
+        uint64_t k = 0;
+        for (; k + 16 <= n; k += 16) _mm_storeu_si128(reinterpret_cast<__m128i*>(d + k), _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + k)));
+        if (k < n) _mm_storeu_si128(reinterpret_cast<__m128i*>(d + n - 16), _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + n - 16)));
+    } else {
+        std::memcpy(d, s, n);
+    }
+}
+
 struct Gatherer {
     size_t n = 0;
     const char* const* src[2] = {nullptr, nullptr};
@@ -231,11 +245,18 @@ struct Gatherer {
                     if (b >= n_blocks) return;
                     const size_t a = b * kBlock, e = std::min(n, a + kBlock);
                     for (int w = 0; w < 2; ++w)
-                        for (size_t i = a; i < e; ++i) {
-                            const uint32_t l = len[w][i];
-                            if (!l) continue;
-                            if (!src[w][i]) { bad.store(1, std::memory_order_relaxed); continue; }
-                            std::memcpy(dst[w] + off[w][i], src[w][i], l);
+                        for (size_t i = a; i < e;) {
+                            const uint32_t l0 = len[w][i];
+                            if (l0 == 0) { ++i; continue; }
+                            const char* s0 = src[w][i];
+                            if (!s0) { bad.store(1, std::memory_order_relaxed); ++i; continue; }
+                            // sequences that already lie back to back in the caller's memory (one arena, a packed
+                            // buffer behind the pointers) are copied as one run
+                            uint64_t run = l0;
+                            size_t j = i + 1;
+                            while (j < e && (len[w][j] == 0 || src[w][j] == s0 + run)) { run += len[w][j]; ++j; }
+                            copy_bytes(dst[w] + off[w][i], s0, run);
+                            i = j;
                         }
                     done[b].store(1, std::memory_order_release);
                 }
@@ -288,12 +309,44 @@ extern "C" int b200_align_batch(int device, size_t n, const char* const* query, 
         const size_t pt = (size_t)(std::lower_bound(to, to + n + 1, t_end) - to);
         return g.wait_pairs(std::min(n, std::max(pq, pt)));
     };
-    int rc = align_batch_host(c, n, src, qo, to, type, match, mismatch, gap, score, target_begin, cigar_buf, cigar_off, cigar_cap);
+    // The caller's result arrays are ordinary (pageable) memory: a device-to-host copy into them goes through the
+    // driver's bounce buffers and blocks the calling thread each time, which serialises the wave pipeline. Large batches
+    // land in pinned staging instead (downloads overlap the later waves) and are copied out with a few threads at the end.
+    const bool stage_out = n >= 4 * Gatherer::kBlock;
+    int32_t* s_score = score; uint32_t* s_tb = target_begin; uint64_t* s_off = cigar_off; char* s_cig = cigar_buf;
+    uint64_t s_cap = cigar_cap;
+    if (stage_out) {
+        TRY(c->h_out_small.ensure(n * 8 + (n + 1) * 8 + 64));
+        s_score = c->h_out_small.as<int32_t>();
+        s_tb = target_begin ? reinterpret_cast<uint32_t*>(s_score + n) : nullptr;
+        if (cigar_off) {
+            s_off = reinterpret_cast<uint64_t*>(c->h_out_small.as<char>() + n * 8);
+            s_cap = std::min<uint64_t>(cigar_cap, 2 * (qo[n] + to[n]) + 2 * n + 16);   // no CIGAR is longer than 2 (Q + T) + 2
+            TRY(c->h_out_cigar.ensure(s_cap + 16));
+            s_cig = c->h_out_cigar.as<char>();
+        }
+    }
+    int rc = align_batch_host(c, n, src, qo, to, type, match, mismatch, gap, s_score, s_tb, s_cig, s_off, s_cap);
     g.join();
     if (rc != B200_OK) {
         const std::string msg = b200_last_error();
         ctx_sync_all_streams(c);   // no copy may still read the staging buffers the next call refills
         b200_fail(rc, msg);
+        return rc;
+    }
+    if (stage_out) {
+        struct Part { char* d; const char* s; uint64_t n; };
+        std::vector<Part> parts{{reinterpret_cast<char*>(score), reinterpret_cast<const char*>(s_score), n * 4}};
+        if (target_begin) parts.push_back({reinterpret_cast<char*>(target_begin), reinterpret_cast<const char*>(s_tb), n * 4});
+        if (cigar_off) {
+            parts.push_back({reinterpret_cast<char*>(cigar_off), reinterpret_cast<const char*>(s_off), (n + 1) * 8});
+            parts.push_back({cigar_buf, s_cig, s_off[n]});
+        }
+        std::vector<std::thread> th;
+        for (unsigned t = 1; t < T; ++t)
+            th.emplace_back([&, t] { for (const Part& p : parts) std::memcpy(p.d + p.n * t / T, p.s + p.n * t / T, p.n * (t + 1) / T - p.n * t / T); });
+        for (const Part& p : parts) std::memcpy(p.d, p.s, p.n / T);
+        for (auto& x : th) x.join();
     }
     return rc;
 }

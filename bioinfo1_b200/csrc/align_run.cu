@@ -1,10 +1,9 @@
 // align_run.cu -- runs a planned alignment batch: per wave 2-bit pack -> DP fill -> traceback walk, then
 // CIGAR offsets (scan) and text; the repair pass for pairs that turn out not to be pure ACGT.
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
-
-#include <cub/device/device_scan.cuh>
-#include <cub/iterator/transform_input_iterator.cuh>
 
 #include "align_fill_generic.cuh"
 #include "align_fill_long.cuh"
@@ -15,36 +14,28 @@
 
 using namespace b200;
 
-// Kernels only share an SM when they agree on its shared-memory carve-out: the long-pair fills use no shared
-// memory, the tile walkers 16 KB, and with the default preferences a walker CTA did not become resident until
-// the fill running on the SM was over (measured: the "concurrent" walkers finished 2.9 ms after the fill; launched
-// first, they kept the fill out instead). Same explicit preference on all of them.
-void align_kernels_configure() {
-    const int pct = 30;   // 68 KB: three fill CTAs with their 8 KB substitution tables + a 16 KB walker CTA
-    cudaFuncSetAttribute(fill_long16_kernel<0, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-    cudaFuncSetAttribute(fill_long16_kernel<1, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-    cudaFuncSetAttribute(fill_long16_kernel<2, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-    cudaFuncSetAttribute(fill_long16_kernel<0, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-    cudaFuncSetAttribute(fill_long16_kernel<1, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-    cudaFuncSetAttribute(fill_long16_kernel<2, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-    cudaFuncSetAttribute(fill_long_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-    cudaFuncSetAttribute(fill_long_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-    cudaFuncSetAttribute(fill_long_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-    cudaFuncSetAttribute(walk_tile_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-    cudaFuncSetAttribute(walk_tile_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-    cudaFuncSetAttribute(walk_tile_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-    cudaFuncSetAttribute(walk_tile_wait_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-    cudaFuncSetAttribute(walk_tile_wait_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-    cudaFuncSetAttribute(walk_tile_wait_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-    cudaGetLastError();
+// (subst_lds: bit 0 = the short-pair kernel, bit 1 = the long-pair kernel)
+static inline int fill_variant(const b200_ctx* c) { return ((c->subst_lds & 1) ? 1 : 0) | (c->fill_pipe ? 2 : 0); }
+
+// f.template operator()<TYPE, VARIANT>() for the run-time (type, variant)
+template <class F>
+static int dispatch_short(int type, int variant, F&& f) {
+#define ROW(TY) switch (variant) { case 0: return f.template operator()<TY, 0>(); case 1: return f.template operator()<TY, 1>(); \
+                                   case 2: return f.template operator()<TY, 2>(); default: return f.template operator()<TY, 3>(); }
+    if (type == 0) { ROW(0) } else if (type == 1) { ROW(1) } else { ROW(2) }
+#undef ROW
 }
 
-static int short_blocks_per_sm(int type, bool lds, int* per_sm) {
+struct ShortOccupancy {
+    int* per_sm;
+    template <int TY, int SB> int operator()() const {
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, fill_short_kernel<TY, SB>, kShortThreads, 0));
+        return B200_OK;
+    }
+};
+static int short_blocks_per_sm(int type, int variant, int* per_sm) {
     *per_sm = 0;
-#define OCC(TY, SB) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, fill_short_kernel<TY, SB>, kShortThreads, 0))
-    if (lds) { if (type == 0) OCC(0, 1); else if (type == 1) OCC(1, 1); else OCC(2, 1); }
-    else { if (type == 0) OCC(0, 0); else if (type == 1) OCC(1, 0); else OCC(2, 0); }
-#undef OCC
+    TRY(dispatch_short(type, variant, ShortOccupancy{per_sm}));
     *per_sm = std::max(*per_sm, 1);
     return B200_OK;
 }
@@ -52,14 +43,68 @@ static int short_blocks_per_sm(int type, bool lds, int* per_sm) {
 // One ROUND of the thread-per-pair fill: every resident warp takes one 64-pair group.
 int align_short_round_pairs(b200_ctx* c, int type, size_t* out) {
     int per_sm = 0;
-    TRY(short_blocks_per_sm(type, c->subst_lds != 0, &per_sm));
+    TRY(short_blocks_per_sm(type, fill_variant(c), &per_sm));
     *out = (size_t)c->sm_count * per_sm * (kShortThreads / 32) * 64;
     return B200_OK;
 }
 
-struct U32ToU64 {
-    __host__ __device__ uint64_t operator()(const uint32_t& v) const { return (uint64_t)v; }
-};
+// Inclusive scan of the per-pair CIGAR byte counts into 64-bit offsets (out[i] = base + len[0] + ... + len[i]), in three
+// small launches: tile sums, scan of the tile sums, tile rescan. Our own kernels rather than a library scan because they
+// run next to the persistent fill of the streaming mode: kernels only share an SM when they agree on its shared-memory
+// carve-out, and a library kernel with kilobytes of shared memory does not become resident next to the fill -- it then
+// waits at the head of the hardware queue and keeps the pack kernels the fill is waiting for from starting.
+constexpr int kScanThreads = 256, kScanPerThread = 16, kScanTile = kScanThreads * kScanPerThread;
+
+__device__ __forceinline__ uint64_t block_exclusive_scan_u64(uint64_t v, uint64_t* total_out) {
+    __shared__ uint64_t warp_sum[kScanThreads / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint64_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint64_t u = __shfl_up_sync(kFull, incl, o); if (lane >= o) incl += u; }
+    if (lane == 31) warp_sum[warp] = incl;
+    __syncthreads();
+    uint64_t before = 0, total = 0;
+#pragma unroll
+    for (int k = 0; k < kScanThreads / 32; ++k) { const uint64_t t = warp_sum[k]; if (k < warp) before += t; total += t; }
+    __syncthreads();
+    if (total_out) *total_out = total;
+    return before + incl - v;
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+scan_tile_sums_kernel(const uint32_t* __restrict__ len, uint32_t n, uint64_t* __restrict__ tile_sum) {
+    const uint32_t i0 = blockIdx.x * kScanTile + threadIdx.x * kScanPerThread;
+    uint64_t s = 0;
+#pragma unroll
+    for (int k = 0; k < kScanPerThread; ++k) if (i0 + k < n) s += len[i0 + k];
+    uint64_t total;
+    block_exclusive_scan_u64(s, &total);
+    if (threadIdx.x == 0) tile_sum[blockIdx.x] = total;
+}
+
+// one CTA: tile sums -> exclusive tile bases (+ *base when given); a thread owns a run of consecutive tiles
+__global__ void __launch_bounds__(kScanThreads)
+scan_tile_bases_kernel(uint64_t* __restrict__ tile_sum, uint32_t n_tiles, const uint64_t* __restrict__ base) {
+    const uint32_t per = (n_tiles + kScanThreads - 1) / kScanThreads, i0 = threadIdx.x * per;
+    uint64_t s = 0;
+    for (uint32_t k = 0; k < per; ++k) if (i0 + k < n_tiles) s += tile_sum[i0 + k];
+    uint64_t run = block_exclusive_scan_u64(s, nullptr) + (base ? *base : 0);
+    for (uint32_t k = 0; k < per; ++k)
+        if (i0 + k < n_tiles) { const uint64_t v = tile_sum[i0 + k]; tile_sum[i0 + k] = run; run += v; }
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+scan_write_kernel(const uint32_t* __restrict__ len, uint32_t n, const uint64_t* __restrict__ tile_base, uint64_t* __restrict__ out) {
+    const uint32_t i0 = blockIdx.x * kScanTile + threadIdx.x * kScanPerThread;
+    uint32_t v[kScanPerThread];
+    uint64_t s = 0;
+#pragma unroll
+    for (int k = 0; k < kScanPerThread; ++k) { v[k] = i0 + k < n ? len[i0 + k] : 0u; s += v[k]; }
+    uint64_t run = block_exclusive_scan_u64(s, nullptr) + tile_base[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < kScanPerThread; ++k) { run += v[k]; if (i0 + k < n) out[i0 + k] = run; }
+}
+
 
 struct RunBufs {   // per-wave device pointers shared by the launch helpers
     const uint8_t *dq, *dt;
@@ -86,28 +131,42 @@ static int launch_fill_generic(b200_align_plan* p, const uint32_t* d_work, uint3
     return B200_OK;
 }
 
-static int launch_fill_short(b200_align_plan* p, const Wave& wv, const RunBufs& rb) {
+struct ShortLaunch {
+    b200_align_plan* p; const Wave& wv; const RunBufs& rb; int n_blocks; uint32_t bnd_cols; const ShortConsts& K; const ShortStream& sc;
+    template <int TY, int SB> int operator()() const {
+        b200_ctx* c = p->ctx;
+        fill_short_kernel<TY, SB><<<n_blocks, kShortThreads, 0, rb.st>>>(
+            c->qpk.as<uint32_t>(), c->tpk.as<uint32_t>(), p->d_pairs.as<PairDesc>(), p->d_work.as<uint32_t>() + wv.first,
+            wv.count, p->d_groups.as<ShortGroup>() + wv.first_group, rb.ws->counter.as<uint32_t>(), c->flags.as<uint8_t>(), K,
+            rb.dirs, rb.ws->bnd_short.as<uint32_t>(), bnd_cols, rb.score, c->end_i.as<uint32_t>(), c->end_j.as<uint32_t>(), sc);
+        return B200_OK;
+    }
+};
+
+// One-thread kernel that publishes the streaming watermark (stream order puts it after the slice's pack kernel).
+__global__ void publish_watermark_kernel(uint32_t* watermark, uint32_t pairs_ready) {
+    __threadfence();
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(watermark), "r"(pairs_ready) : "memory");
+}
+
+// `sctl` (streaming mode, see ShortStream): the launch serves every wave of the run and leaves two CTA slots per SM
+// free (with one, measured, the pipeline stalls: a 256-thread scan CTA does not fit 8 K registers), so that the pack, traceback, scan and emit kernels it waits for and feeds can always become resident next to it
+// (a fill that owned every slot would spin on a watermark nobody can raise).
+static int launch_fill_short(b200_align_plan* p, const Wave& wv, const RunBufs& rb, const ShortStream* sctl = nullptr) {
     b200_ctx* c = p->ctx;
     const uint32_t n_groups = (wv.count + 63) / 64;
     int per_sm = 0;
-    TRY(short_blocks_per_sm(p->type, c->subst_lds != 0, &per_sm));
+    TRY(short_blocks_per_sm(p->type, fill_variant(c), &per_sm));
+    if (sctl) per_sm = std::max(1, per_sm - 2);   // two 64-thread slots = 16 K registers stay free for the small kernels
     const int n_blocks = (int)std::min<uint64_t>((uint64_t)c->sm_count * per_sm, div_up64(n_groups, kShortThreads / 32));
     const uint32_t bnd_cols = p->max_T_short + 4;
     TRY(rb.ws->bnd_short.ensure((size_t)n_blocks * (kShortThreads / 32) * bnd_cols * 32 * sizeof(uint32_t)));
     CU(cudaMemsetAsync(rb.ws->counter.p, 0, 64, rb.st));
     const ShortConsts K = make_short_consts(p->sc, p->type);
+    ShortStream sc{};
+    if (sctl) sc = *sctl;
     prof_begin(c, rb.st, 0);
-#define SHORTK(TY) SHORTK2(TY, 0)
-#define SHORTK1(TY) SHORTK2(TY, 1)
-#define SHORTK2(TY, SB) fill_short_kernel<TY, SB><<<n_blocks, kShortThreads, 0, rb.st>>>(                                         \
-        c->qpk.as<uint32_t>(), c->tpk.as<uint32_t>(), p->d_pairs.as<PairDesc>(), p->d_work.as<uint32_t>() + wv.first,     \
-        wv.count, p->d_groups.as<ShortGroup>() + wv.first_group, rb.ws->counter.as<uint32_t>(), c->flags.as<uint8_t>(), K, \
-        rb.dirs, rb.ws->bnd_short.as<uint32_t>(), bnd_cols, rb.score, c->end_i.as<uint32_t>(), c->end_j.as<uint32_t>())
-    if (c->subst_lds) { switch (p->type) { case 0: SHORTK1(0); break; case 1: SHORTK1(1); break; default: SHORTK1(2); break; } }
-    else { switch (p->type) { case 0: SHORTK(0); break; case 1: SHORTK(1); break; default: SHORTK(2); break; } }
-#undef SHORTK
-#undef SHORTK1
-#undef SHORTK2
+    TRY(dispatch_short(p->type, fill_variant(c), ShortLaunch{p, wv, rb, n_blocks, bnd_cols, K, sc}));
     prof_end(c, rb.st);
     c->kernel_launches++;
     return B200_OK;
@@ -116,8 +175,11 @@ static int launch_fill_short(b200_align_plan* p, const Wave& wv, const RunBufs& 
 static int launch_fill_long(b200_align_plan* p, const Wave& wv, const RunBufs& rb) {
     b200_ctx* c = p->ctx;
     int per_sm = 0;
-    if (p->long16 && c->subst_lds) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fill_long16_kernel<1, 1>, 128, 0));
-    else if (p->long16) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fill_long16_kernel<1, 0>, 128, 0));
+    const int v16 = (c->subst_lds & 2) ? 1 : 0;   // variant of the packed long-pair kernel: substitution term by PRMT / shared table
+    if (p->long16) {
+        if (v16 == 0) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fill_long16_kernel<1, 0>, 128, 0));
+        else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fill_long16_kernel<1, 1>, 128, 0));
+    }
     else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fill_long_kernel<0>, 128, 0));
     per_sm = std::max(per_sm, 1);
     const uint32_t* d_task_off = p->d_task_off.as<uint32_t>() + wv.first_group;
@@ -152,7 +214,7 @@ static int launch_fill_long(b200_align_plan* p, const Wave& wv, const RunBufs& r
             if (!ws.walk_event) CU(cudaEventCreateWithFlags(&ws.walk_event, cudaEventDisableTiming));
         }
         prof_begin(c, rb.st, 0);
-#define LONG16K(TY) if (c->subst_lds) { LONG16K2(TY, 1); } else { LONG16K2(TY, 0); }
+#define LONG16K(TY) if (v16 == 0) { LONG16K2(TY, 0); } else { LONG16K2(TY, 1); }
 #define LONG16K2(TY, SB)                                                                                               \
     if (cw) {   /* pairs without inner cells have nothing to wait for: result and ready flag now */                   \
         finalize_long_kernel<TY><<<(unsigned)div_up64(wv.count, 128), 128, 0, rb.st>>>(p->d_pairs.as<PairDesc>(), d_work, \
@@ -351,6 +413,52 @@ static int plan_run_body(b200_align_plan* p, const char* d_q_buf, const char* d_
         CU(cudaStreamWaitEvent(c->pack_stream, c->fork_event, 0));   // after the memsets queued on the caller's stream
     }
 
+    // Streaming fill (uniform short batches through the host pipeline, see ShortStream in align_fill_short.cuh): one
+    // persistent fill launch for all waves, fed by a watermark; the per-wave kernels left are pack + publish (pack
+    // stream) and the traceback, which waits on the device for its wave's groups. All waves' direction matrices are
+    // live at once, so it needs the whole batch to fit the budget.
+    uint64_t all_dir_words = 0;
+    for (const Wave& w : p->waves) all_dir_words += (w.dir_words + 3) & ~3ull;
+    const bool streaming = piped && pack_ahead && c->stream_fill && p->want_cigar && n_waves <= 32 &&
+                           all_dir_words <= wave_budget_words(c) && p->n_short == n;
+    ShortStream sctl{};
+    uint32_t* d_stream = nullptr;   // [0] watermark, [1 .. n_waves] groups done per wave
+    const bool check_stall = p->n_long != 0 || streaming;   // kernels that wait on the device raise a flag instead of hanging
+    if (streaming) {
+        if (!c->fill_stream) CU(cudaStreamCreateWithFlags(&c->fill_stream, cudaStreamNonBlocking));
+        if (!c->fill_event) CU(cudaEventCreateWithFlags(&c->fill_event, cudaEventDisableTiming));
+        WaveSlot& ws0 = c->slot[0];
+        TRY(ws0.dirs.ensure(std::max<uint64_t>(all_dir_words, 4) * 4 + 64));
+        TRY(c->stream_state.ensure(64 * 4));
+        TRY(c->scan_tmp.ensure((size_t)div_up64(n, kScanTile) * 8 + 64));   // no allocation once the fill is spinning
+        d_stream = c->stream_state.as<uint32_t>();
+        CU(cudaMemsetAsync(d_stream, 0, 64 * 4, st));
+        CU(cudaMemsetAsync(ws0.counter.as<uint32_t>() + 24, 0, 4, st));
+        CU(cudaMemsetAsync(c->slot[1].counter.as<uint32_t>() + 24, 0, 4, st));
+        sctl.watermark = d_stream; sctl.wave_done = d_stream + 1; sctl.stall_flag = ws0.counter.as<uint32_t>() + 24;
+        sctl.n_waves = (uint32_t)n_waves;
+        uint64_t base = 0;
+        for (size_t k = 0; k < n_waves; ++k) {
+            sctl.group_start[k] = p->waves[k].first / 64;
+            sctl.dir_base[k] = base;
+            base += (p->waves[k].dir_words + 3) & ~3ull;
+        }
+        sctl.group_start[n_waves] = (uint32_t)div_up64(n, 64);
+        // the fill goes first (it must own its share of every SM before the small kernels come), on a stream of its own;
+        // every other stream of the run starts after the counters have been zeroed
+        CU(cudaEventRecord(c->fork_event, st));
+        CU(cudaStreamWaitEvent(c->fill_stream, c->fork_event, 0));
+        CU(cudaStreamWaitEvent(c->pack_stream, c->fork_event, 0));
+        CU(cudaStreamWaitEvent(c->aux_stream, c->fork_event, 0));
+        Wave all{kClassShort, 0, (uint32_t)n, 0, all_dir_words};
+        RunBufs rbf{reinterpret_cast<const uint8_t*>(d_q_buf), reinterpret_cast<const uint8_t*>(d_t_buf), ws0.dirs.as<uint32_t>(),
+                    d_score, c->fill_stream, &ws0};
+        tl_mark(c, c->fill_stream, "fill-start");
+        TRY(launch_fill_short(p, all, rbf, &sctl));
+        tl_mark(c, c->fill_stream, "fill-end");
+        CU(cudaEventRecord(c->fill_event, c->fill_stream));
+    }
+
     if (!ho) tl_mark(c, st, "start");
     // A wave = classify (+ 2-bit pack) -> fill -> traceback walk, in order on its stream; when the host entry
     // point pipelines the upload, wave k first waits for the event that marks its bytes as resident.
@@ -367,8 +475,8 @@ static int plan_run_body(b200_align_plan* p, const char* d_q_buf, const char* d_
         if (wv.klass != kClassGeneric) {
             const uint32_t wpp = std::max(1u, div_up(wv.klass == kClassLong ? std::max(p->max_Q, p->max_T)
                                                                            : std::max(p->max_Q_short, p->max_T_short), 16));
-            dim3 grid((unsigned)div_up64((uint64_t)wv.count * wpp, 256), 2);
-            pack_kernel<<<grid, 256, 0, pst>>>(rb.dq, rb.dt, p->d_pairs.as<PairDesc>(), work, wv.count, wpp,
+            dim3 grid((unsigned)div_up64((uint64_t)wv.count * wpp, 128), 2);   // (128-thread CTAs: they fit one free fill slot)
+            pack_kernel<<<grid, 128, 0, pst>>>(rb.dq, rb.dt, p->d_pairs.as<PairDesc>(), work, wv.count, wpp,
                                                c->flags.as<uint8_t>(), c->qpk.as<uint32_t>(), c->tpk.as<uint32_t>(), d_nflag);
         } else {
             classify_kernel<<<(unsigned)div_up64((uint64_t)wv.count * 32, 256), 256, 0, pst>>>(
@@ -377,15 +485,21 @@ static int plan_run_body(b200_align_plan* p, const char* d_q_buf, const char* d_
         prof_end(c, pst);
         c->kernel_launches++;
         tl_mark(c, pst, "pack" + std::to_string(k));
+        if (streaming) {
+            publish_watermark_kernel<<<1, 1, 0, pst>>>(d_stream, wv.first + wv.count);
+            c->kernel_launches++;
+        }
         if (pack_ahead) {
             CU(cudaEventRecord(c->pack_done[k], pst));
             CU(cudaStreamWaitEvent(wst, c->pack_done[k], 0));
         }
         rb.dirs = p->want_cigar ? ws.dirs.as<uint32_t>() : nullptr;
+        if (streaming) rb.dirs = c->slot[0].dirs.as<uint32_t>() + sctl.dir_base[k];
         // in a wave of a 2-bit class a non-zero flag means "not this wave's pair"; in a generic wave the flags only
         // describe the content (classify_kernel) and every pair is the wave's own
         const uint8_t* skip = wv.klass != kClassGeneric ? c->flags.as<uint8_t>() : nullptr;
-        if (wv.klass == kClassShort) TRY(launch_fill_short(p, wv, rb));
+        if (streaming) {}   // the persistent launch above fills every wave
+        else if (wv.klass == kClassShort) TRY(launch_fill_short(p, wv, rb));
         else if (wv.klass != kClassGeneric) TRY(launch_fill_long(p, wv, rb));
         else TRY(launch_fill_generic(p, work, wv.count, rb));
         tl_mark(c, wst, "fill" + std::to_string(k));
@@ -395,6 +509,11 @@ static int plan_run_body(b200_align_plan* p, const char* d_q_buf, const char* d_
             ws.walk_inflight = false;
             CU(cudaStreamWaitEvent(wst, ws.walk_event, 0));
             tl_mark(c, wst, "cwalk" + std::to_string(k));
+        } else if (streaming) {
+            wave_gate_kernel<<<1, 1, 0, wst>>>(d_stream + 1 + k, (wv.count + 63) / 64, c->slot[0].counter.as<uint32_t>() + 24);
+            c->kernel_launches++;
+            tl_mark(c, wst, "gate" + std::to_string(k));
+            TRY(launch_walk(p, wv.klass, work, wv.count, rb, skip));
         } else if (p->want_cigar) TRY(launch_walk(p, wv.klass, work, wv.count, rb, skip));
         tl_mark(c, wst, "walk" + std::to_string(k));
         if (piped) {
@@ -410,6 +529,7 @@ static int plan_run_body(b200_align_plan* p, const char* d_q_buf, const char* d_
     }
     CU(cudaGetLastError());
     if (overlap) CU(cudaStreamWaitEvent(st, c->slot[1].done, 0));   // join: the rest runs on the caller's stream
+    if (streaming) CU(cudaStreamWaitEvent(st, c->fill_event, 0));
 
     if (d_target_begin && !piped) {
         target_begin_kernel<<<(unsigned)div_up64(n, 256), 256, 0, st>>>(0u, (uint32_t)n, p->type, c->end_j.as<uint32_t>(), d_target_begin);
@@ -428,27 +548,37 @@ static int plan_run_body(b200_align_plan* p, const char* d_q_buf, const char* d_
     // flagged pair, *flagged is set and nothing is emitted: the texts of those pairs do not exist yet.
     uint64_t* h_total = c->h_small.as<uint64_t>();
     auto scan_emit = [&](uint32_t a, uint32_t b, cudaStream_t es, uint64_t* total_out, size_t fk0, size_t fk1, bool* flagged) -> int {
-        cub::TransformInputIterator<uint64_t, U32ToU64, const uint32_t*> in(c->cigar_len.as<uint32_t>() + a, U32ToU64());
-        size_t tmp_bytes = 0;
-        CU(cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, in, d_cigar_off + a + 1, (int)(b - a), es));
-        TRY(c->scan_tmp.ensure(tmp_bytes));
+        const uint32_t cnt = b - a, n_tiles = (uint32_t)div_up64(cnt, kScanTile);
+        TRY(c->scan_tmp.ensure((size_t)n_tiles * 8 + 64));
         if (a == 0) CU(cudaMemsetAsync(d_cigar_off, 0, sizeof(uint64_t), es));
         prof_begin(c, es, 3);
-        CU(cub::DeviceScan::InclusiveSum(c->scan_tmp.p, tmp_bytes, in, d_cigar_off + a + 1, (int)(b - a), es));
-        if (a) add_offset_kernel<<<(unsigned)div_up64(b - a, 256), 256, 0, es>>>(d_cigar_off + a + 1, b - a, d_cigar_off + a);
+        scan_tile_sums_kernel<<<n_tiles, kScanThreads, 0, es>>>(c->cigar_len.as<uint32_t>() + a, cnt, c->scan_tmp.as<uint64_t>());
+        scan_tile_bases_kernel<<<1, kScanThreads, 0, es>>>(c->scan_tmp.as<uint64_t>(), n_tiles, a ? d_cigar_off + a : nullptr);
+        scan_write_kernel<<<n_tiles, kScanThreads, 0, es>>>(c->cigar_len.as<uint32_t>() + a, cnt, c->scan_tmp.as<uint64_t>(), d_cigar_off + a + 1);
         prof_end(c, es);
-        c->kernel_launches += 2 + (a ? 1 : 0);
+        c->kernel_launches += 3;
         CU(cudaMemcpyAsync(h_total, d_cigar_off + b, sizeof(uint64_t), cudaMemcpyDeviceToHost, es));
         TRY(queue_flag_counts(fk0, fk1, es));
         // a stripe or walker that gave up waiting leaves stale run counts behind: look at the stall flags with the same
         // read-back, before anything is emitted from them
         uint32_t* h_stall = c->h_small.as<uint32_t>() + 2;
-        if (p->n_long)
+        if (check_stall)
             for (int k = 0; k < n_slots; ++k)
                 CU(cudaMemcpyAsync(h_stall + k, c->slot[k].counter.as<uint32_t>() + 24, 4, cudaMemcpyDeviceToHost, es));
         CU(cudaStreamSynchronize(es));
-        if (p->n_long && (h_stall[0] | h_stall[1]))
-            return fail(B200_E_CUDA, "long-pair kernel: a stripe gave up waiting for its predecessor");
+        if (check_stall && (h_stall[0] | h_stall[1]) && streaming && std::getenv("B200_TRACE")) {
+            // diagnostic: where the streaming pipeline stood when a warp gave up
+            cudaDeviceSynchronize();
+            uint32_t hs[64] = {0}, cnt[32] = {0};
+            cudaMemcpy(hs, d_stream, sizeof hs, cudaMemcpyDeviceToHost);
+            cudaMemcpy(cnt, c->slot[0].counter.p, sizeof cnt, cudaMemcpyDeviceToHost);
+            std::fprintf(stderr, "[b200 stall] watermark=%u groups_taken=%u waves=%zu:", hs[0], cnt[0], n_waves);
+            for (size_t k = 0; k < n_waves; ++k) std::fprintf(stderr, " w%zu[first %u count %u done %u/%u]", k, p->waves[k].first, p->waves[k].count, hs[1 + k], (p->waves[k].count + 63) / 64);
+            std::fprintf(stderr, "\n");
+            tl_dump(c);
+        }
+        if (check_stall && (h_stall[0] | h_stall[1]))
+            return fail(B200_E_CUDA, "fill kernel: a warp gave up waiting (for the stripe above it, or for the upload watermark)");
         if (any_flagged(fk0, fk1)) { *flagged = true; return B200_OK; }
         const uint64_t total = *h_total;
         *total_out = total;
@@ -564,14 +694,54 @@ static int plan_run_body(b200_align_plan* p, const char* d_q_buf, const char* d_
         }
     }
     CU(cudaGetLastError());
-    if (p->n_long) {
+    if (check_stall) {
         uint32_t stalled[2] = {0, 0};
         for (int k = 0; k < n_slots; ++k)
             CU(cudaMemcpyAsync(&stalled[k], c->slot[k].counter.as<uint32_t>() + 24, 4, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
-        if (stalled[0] | stalled[1]) return fail(B200_E_CUDA, "long-pair kernel: a stripe gave up waiting for its predecessor");
+        if (stalled[0] | stalled[1])
+            return fail(B200_E_CUDA, "fill kernel: a warp gave up waiting (for the stripe above it, or for the upload watermark)");
     }
     prof_collect(c, st);
     if (!ho) tl_dump(c);
     return B200_OK;
 }
+
+// Kernels only share an SM when they agree on its shared-memory carve-out: the long-pair fills use no shared
+// memory, the tile walkers 16 KB, and with the default preferences a walker CTA did not become resident until
+// the fill running on the SM was over (measured: the "concurrent" walkers finished 2.9 ms after the fill; launched
+// first, they kept the fill out instead). Same explicit preference on all of them.
+void align_kernels_configure() {
+    const int pct = 30;   // 68 KB: three fill CTAs with their 8 KB substitution tables + a 16 KB walker CTA
+#define K3ATTR(SB) cudaFuncSetAttribute(fill_long16_kernel<0, SB>, cudaFuncAttributePreferredSharedMemoryCarveout, pct); \
+                   cudaFuncSetAttribute(fill_long16_kernel<1, SB>, cudaFuncAttributePreferredSharedMemoryCarveout, pct); \
+                   cudaFuncSetAttribute(fill_long16_kernel<2, SB>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    K3ATTR(0) K3ATTR(1)
+#undef K3ATTR
+    cudaFuncSetAttribute(fill_long_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(fill_long_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(fill_long_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(walk_tile_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(walk_tile_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(walk_tile_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(walk_tile_wait_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(walk_tile_wait_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(walk_tile_wait_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    // CUDA loads kernels lazily, and loading one may have to wait for the device to go idle. The streaming mode keeps a
+    // persistent fill kernel spinning on a watermark that only later launches (pack, publish, gate, traceback, scan, emit)
+    // can raise: a first-time launch among them would wait for the fill, and the fill for it. Everything the pipeline
+    // launches is therefore loaded here, once per context, before anything runs.
+    cudaFuncAttributes fa;
+#define PRELOAD(K) cudaFuncGetAttributes(&fa, K)
+#define PRELOAD_SHORT(SB) PRELOAD((fill_short_kernel<0, SB>)); PRELOAD((fill_short_kernel<1, SB>)); PRELOAD((fill_short_kernel<2, SB>));
+    PRELOAD_SHORT(0) PRELOAD_SHORT(1) PRELOAD_SHORT(2) PRELOAD_SHORT(3)
+#undef PRELOAD_SHORT
+    PRELOAD(pack_kernel); PRELOAD(classify_kernel); PRELOAD(publish_watermark_kernel); PRELOAD(wave_gate_kernel);
+    PRELOAD(walk_kernel<0>); PRELOAD(walk_kernel<1>); PRELOAD(walk_kernel<2>);
+    PRELOAD(target_begin_kernel); PRELOAD(scan_tile_sums_kernel); PRELOAD(scan_tile_bases_kernel); PRELOAD(scan_write_kernel);
+    PRELOAD(emit_kernel); PRELOAD(emit_warp_kernel);
+#undef PRELOAD
+    cudaGetLastError();
+}
+
+// Kernel variant of a context: bit 0 substitution term from the shared-memory table, bit 1 software-pipelined columns.

@@ -116,6 +116,19 @@ walk_kernel(const PairDesc* __restrict__ pairs, const uint32_t* __restrict__ wor
     cigar_len[p] = bytes;
 }
 
+// Streaming mode of the short-pair fill (ShortStream in align_fill_short.cuh): the gate in front of a wave's traceback.
+// One thread waits until every group of the wave has been counted as done by the (still running) persistent fill; the
+// traceback kernel follows it in stream order. A kernel of its own, one slot wide, on purpose: traceback CTAs that
+// waited themselves would fill every free slot of the machine and keep the next wave's pack kernel -- which the fill is
+// waiting for -- from becoming resident.
+__global__ void wave_gate_kernel(const uint32_t* counter, uint32_t target, uint32_t* stall_flag) {
+    uint32_t spins = 0;
+    while (ld_acquire_u32(counter) < target) {
+        __nanosleep(400);
+        if (++spins > (1u << 22)) { atomicExch(stall_flag, 1u); break; }   // never hang the device
+    }
+}
+
 // ---- warp-per-pair tile walker ------------------------------------------------------------
 struct RunWriter {   // the run list under construction (every lane tracks it, lane 0 stores)
     uint32_t* out;

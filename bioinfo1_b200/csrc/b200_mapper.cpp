@@ -81,9 +81,9 @@ struct MappedFile {
         if (fstat(fd, &st) != 0 || !S_ISREG(st.st_mode)) { ::close(fd); return false; }
         n = (size_t)st.st_size;
         if (n) {
-            void* m = mmap(nullptr, n, PROT_READ, MAP_PRIVATE, fd, 0);
+            void* m = mmap(nullptr, n, PROT_READ, MAP_PRIVATE | MAP_POPULATE, fd, 0);   // populated in one go: no fault per page
             if (m == MAP_FAILED) { ::close(fd); return false; }
-            madvise(m, n, MADV_SEQUENTIAL | MADV_WILLNEED);
+            madvise(m, n, MADV_SEQUENTIAL);
             p = static_cast<const char*>(m);
         }
         ::close(fd);

@@ -102,7 +102,7 @@ extern "C" int b200_ctx_create(int device, b200_ctx** out) {
     align_kernels_configure();
     // tuning runs: defaults of a few options from the environment (B200_SUBST_LDS, B200_TAPER_TAIL, B200_CONCURRENT_WALK)
     for (auto kv : {std::pair<const char*, int64_t*>{"B200_SUBST_LDS", &c->subst_lds}, {"B200_TAPER_TAIL", &c->taper_tail},
-                    {"B200_CONCURRENT_WALK", &c->concurrent_walk}})
+                    {"B200_CONCURRENT_WALK", &c->concurrent_walk}, {"B200_STREAM_FILL", &c->stream_fill}, {"B200_FILL_PIPE", &c->fill_pipe}})
         if (const char* e = std::getenv(kv.first)) *kv.second = std::atoll(e);
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess)
@@ -115,7 +115,7 @@ extern "C" int b200_ctx_create(int device, b200_ctx** out) {
 // host arrays) when the entry point returns, and the next call reuses these workspaces.
 void ctx_sync_all_streams(b200_ctx* c) {
     cudaSetDevice(c->device);
-    for (cudaStream_t s : {c->stream, c->aux_stream, c->emit_stream, c->pack_stream, c->copy_stream,
+    for (cudaStream_t s : {c->stream, c->aux_stream, c->emit_stream, c->pack_stream, c->copy_stream, c->fill_stream,
                            c->slot[0].walk_stream, c->slot[1].walk_stream})
         if (s) cudaStreamSynchronize(s);
     cudaGetLastError();
@@ -136,6 +136,9 @@ extern "C" void b200_ctx_destroy(b200_ctx* c) {
     if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
     if (c->emit_stream) cudaStreamDestroy(c->emit_stream);
     if (c->pack_stream) cudaStreamDestroy(c->pack_stream);
+    if (c->fill_stream) cudaStreamDestroy(c->fill_stream);
+    if (c->fill_event) cudaEventDestroy(c->fill_event);
+    c->stream_state.release();
     for (cudaEvent_t e : c->pack_done) cudaEventDestroy(e);
     for (auto e : c->wave_done) cudaEventDestroy(e);
     if (c->fork_event) cudaEventDestroy(c->fork_event);
@@ -150,7 +153,7 @@ extern "C" void b200_ctx_destroy(b200_ctx* c) {
                       &c->cigar_len, &c->scan_tmp, &c->flags, &c->total, &c->wave_flagged, &c->d_q, &c->d_t, &c->d_score, &c->d_tb,
                       &c->d_cigar, &c->d_cigar_off, &c->d_seq, &c->d_hash, &c->d_pos, &c->d_flag})
         b->release();
-    for (HostBuf* b : {&c->h_q, &c->h_t, &c->h_off, &c->h_small}) b->release();
+    for (HostBuf* b : {&c->h_q, &c->h_t, &c->h_off, &c->h_small, &c->h_out_small, &c->h_out_cigar}) b->release();
     delete c;
 }
 
@@ -161,10 +164,12 @@ extern "C" int b200_ctx_set_option(b200_ctx* c, const char* key, int64_t value) 
     else if (k == "force_generic") c->force_generic = value;
     else if (k == "long16") c->long16 = value;
     else if (k == "subst_lds") c->subst_lds = value;
+    else if (k == "fill_pipe") c->fill_pipe = value;
     else if (k == "overlap_waves") c->overlap_waves = value;
     else if (k == "concurrent_walk") c->concurrent_walk = value;
     else if (k == "chunk_pairs") c->chunk_pairs = value;
     else if (k == "taper_tail") c->taper_tail = value;
+    else if (k == "stream_fill") c->stream_fill = value;
     else if (k == "profile") c->profile = value;
     else if (k == "reset_counters") {
         c->kernel_launches = c->h2d_bytes = c->d2h_bytes = 0;
@@ -181,7 +186,7 @@ extern "C" int64_t b200_ctx_get_counter(b200_ctx* c, const char* key) {
     if (k == "h2d_bytes") return c->h2d_bytes;
     if (k == "d2h_bytes") return c->d2h_bytes;
     // alu-pipe issue slots the fill kernels spend per register (= two cells), times ten: PRMT counts double
-    if (k == "alu_slots_per_cell_pair_x10") return c->subst_lds ? 30 : 50;
+    if (k == "alu_slots_per_cell_pair_x10") return (c->subst_lds & 1) ? 30 : 50;
     static const char* kinds[4] = {"fill", "walk", "emit", "other"};
     for (int i = 0; i < 4; ++i) {
         if (k == std::string(kinds[i]) + "_ns") return (int64_t)(c->kind_us[i] * 1e3);

@@ -102,6 +102,14 @@ struct b200_ctx {
     cudaStream_t aux_stream = nullptr;      // second wave stream of a run
     cudaStream_t emit_stream = nullptr;     // host path: scan / emit / download of finished waves while later ones run
     cudaStream_t pack_stream = nullptr;     // host path: 2-bit packing of a wave as soon as its bytes have landed
+    cudaStream_t fill_stream = nullptr;     // host path, streaming mode: the one persistent fill launch of a run
+    cudaEvent_t fill_event = nullptr;
+    DevBuf stream_state;                    // streaming mode: watermark + per-wave completion counters
+    // Host pipeline of uniform short batches: 0 = one fill launch per wave (default), 1 = ONE persistent fill launch
+    // fed by an upload watermark (ShortStream). Measured on config 2: 7.13 against 7.20 ms per step -- the persistent
+    // launch gives up a quarter of the fill's occupancy so that the small kernels can run next to it, and what is left
+    // after the last byte of the upload is one group's latency either way; off by default, kept tested.
+    int64_t stream_fill = 0;
     std::vector<cudaEvent_t> pack_done;     // one event per wave of the current run
     std::vector<cudaEvent_t> wave_done;     // one event per wave of the current run
     // B200_TRACE=2: device timeline of a run (events with timing, printed relative to the first)
@@ -116,11 +124,13 @@ struct b200_ctx {
     // staging for the host-buffer entry points
     DevBuf d_q, d_t, d_score, d_tb, d_cigar, d_cigar_off, d_seq, d_hash, d_pos, d_flag;
     HostBuf h_q, h_t, h_off;
+    HostBuf h_out_small, h_out_cigar;       // pointer-array entry point: pinned landing zone of the results
     // options
     int64_t dir_budget_bytes = 48ll << 30;
     int64_t force_generic = 0;
     int64_t long16 = 1;                     // 0 = long pairs stay on the int32 kernel (align_fill_long.cuh)
-    int64_t subst_lds = 1;                  // 1 = substitution term from the shared-memory table, 0 = by PRMT (K1 and K3)
+    int64_t fill_pipe = 1;                  // 1 = software-pipelined columns in the 2-bit fill kernels (K1)
+    int64_t subst_lds = 2;                  // substitution term from the shared-memory table instead of PRMT: bit 0 = K1, bit 1 = K3
     int64_t chunk_pairs = 0;
     int64_t taper_tail = 1;                 // host pipeline of uniform batches: end with a few shrinking waves
     b200_align_plan* host_plan = nullptr;   // recycled by the host-buffer entry points
@@ -246,6 +256,7 @@ struct b200_min_plan {
     uint64_t tuples = 0;
     size_t n_tiles = 0;
     size_t smem_bytes = 0;
+    uint32_t warp_words = 0;   // staged 2-bit words per warp
     uint64_t buf_bytes = 0;   // bytes of the packed sequence buffer the plan was made for (= off[n])
     std::vector<uint64_t> out_off;
     DevBuf d_off, d_out_off, d_fwd, d_tiles;

@@ -25,6 +25,8 @@ namespace b200 {
 constexpr int kMinThreads = 256;
 constexpr int kMinTile = 8192;   // output tuples per CTA (four chunks of 8 per thread)
 constexpr int kMinMaxW = 8;      // largest window length with a register fast path
+constexpr int kMinWarpTuples = kMinTile / (kMinThreads / 32);   // slice positions per warp
+constexpr int kMinStageDepth = 3;  // 16-byte chunks a lane has in flight while staging
 
 // One CTA's work, precomputed by the host so that the kernel starts with ONE broadcast load instead of a
 // chain of dependent ones (tile -> sequence offsets -> bases). The tile covers tuples [o0, o1) of a sequence;
@@ -73,22 +75,32 @@ __device__ __forceinline__ void lmin(uint32_t& v, uint32_t& at, uint32_t bv, uin
 
 // W = compile-time window length for the register fast path (1..kMinMaxW), or 0: every tuple takes the
 // per-tuple path (any w; also used when the output pointers are not 16-byte aligned).
-template <int W>
-__global__ void __launch_bounds__(kMinThreads)
+// K16: k >= 16, the only case in which a hash can be 0xFFFFFFFF (the register path then checks for the zero tuple).
+template <int W, bool K16>
+__global__ void __launch_bounds__(kMinThreads, 6)
 minimize_kernel(const uint8_t* __restrict__ buf, const MinTile* __restrict__ tiles, uint32_t k, uint32_t w,
-                uint64_t buf_bytes, uint32_t* __restrict__ hash, uint32_t* __restrict__ pos, uint8_t* __restrict__ flag) {
-    extern __shared__ uint32_t codes[];
+                uint64_t buf_bytes, uint32_t warp_words, uint32_t* __restrict__ hash, uint32_t* __restrict__ pos,
+                uint8_t* __restrict__ flag) {
+    extern __shared__ uint32_t codes_all[];
     const MinTile tl = tiles[blockIdx.x];
     const uint32_t L = tl.L;
     const uint32_t n = L - k + 1;                            // k-mers inside the sequence (L >= k here)
     const uint32_t full = n >= w ? n - w + 1 : 0;
     const uint32_t tail = n < w - 1 ? n : w - 1;
     const uint32_t total = (w - 1) + full + tail;            // (sequences are shorter than 2^32 - 16: no wrap)
-    const uint32_t o0 = tl.o0;
-    const uint32_t g_in = (uint32_t)(tl.gout & (uint64_t)(kMinTile - 1));   // where the tile starts inside its aligned slice
-    const uint32_t o1 = min(total - o0, (uint32_t)kMinTile - g_in) + o0;
-    hash += tl.gout - g_in; pos += tl.gout - g_in; flag += tl.gout - g_in;  // slice-relative outputs: index g_in + (o - o0)
-
+    const uint32_t g_tile = (uint32_t)(tl.gout & (uint64_t)(kMinTile - 1));   // where the tile starts inside its aligned slice
+    const uint32_t o1_tile = min(total - tl.o0, (uint32_t)kMinTile - g_tile) + tl.o0;
+    hash += tl.gout - g_tile; pos += tl.gout - g_tile; flag += tl.gout - g_tile;  // slice-relative outputs: index g_in + (o - o0)
+    // Every WARP stages and processes its own eighth of the slice (kMinWarpTuples slice positions, with the few bases
+    // of overlap its windows need): no CTA-wide barrier between staging and use, so the warps of an SM drift apart and
+    // one warp's load latency is another's compute time (with CTA-wide staging ncu showed the warps parked at the barrier
+    // and on the loads: 6.7 + 8.4 stall cycles per issued instruction).
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t sp_lo = max(g_tile, (uint32_t)warp * kMinWarpTuples);
+    const uint32_t sp_hi = min(g_tile + (o1_tile - tl.o0), (uint32_t)(warp + 1) * kMinWarpTuples);
+    if (sp_lo >= sp_hi) return;
+    const uint32_t o0 = tl.o0 + (sp_lo - g_tile), o1 = tl.o0 + (sp_hi - g_tile), g_in = sp_lo;   // the warp's tuples / first slice position
+    uint32_t* codes = codes_all + (size_t)warp * warp_words;
     // k-mer index range this tile can touch: [x0, x1)
     const uint32_t x0 = o0 > 2 * w ? o0 - 2 * w : 0;
     const uint32_t nx = o1 + 1 - x0;                         // sections 1/2 use k-mers <= slot index; <= kMinTile + 2w + 1
@@ -103,26 +115,40 @@ minimize_kernel(const uint8_t* __restrict__ buf, const MinTile* __restrict__ til
     const int32_t cb0 = (int32_t)x0 - (int32_t)mis;              // sequence index of the first byte of word 0 (>= -15)
     const uint32_t nwords = (mis + nx + k - 1 + 15) / 16 + 2;    // two spare words: hashes read one and two words ahead
     const uint64_t room = buf_bytes - tl.src;                    // bytes from the sequence start to the end of the buffer
-    for (uint32_t wi = threadIdx.x; wi < nwords; wi += blockDim.x) {
-        const int64_t cb = (int64_t)cb0 + 16ll * wi;             // sequence index of this chunk's first byte
-        uint32_t word = 0;
-        if (cb < (int64_t)L) {
-            const uint8_t* src = origin + 16ull * wi;
-            if (cb + 16 <= (int64_t)L && (uint64_t)(cb + 16) <= room) {
-                const uint4 v = __ldg(reinterpret_cast<const uint4*>(src));
-                word = (code4(v.x) << 24) | (code4(v.y) << 16) | (code4(v.z) << 8) | code4(v.w);
-            } else {                                             // last chunk of the sequence: bytes past its end are code 0
+    // (all of a lane's loads are issued before the first conversion: up to kMinStageDepth 16-byte chunks in flight)
+    for (uint32_t w0i = 0; w0i < nwords; w0i += 32u * kMinStageDepth) {
+        uint4 v[kMinStageDepth];
+        bool whole[kMinStageDepth];
+#pragma unroll
+        for (int q = 0; q < kMinStageDepth; ++q) {
+            const uint32_t wi = w0i + 32u * q + lane;
+            const int64_t cb = (int64_t)cb0 + 16ll * wi;         // sequence index of this chunk's first byte
+            whole[q] = wi < nwords && cb >= 0 && cb + 16 <= (int64_t)L && (uint64_t)(cb + 16) <= room;
+            v[q] = whole[q] ? __ldg(reinterpret_cast<const uint4*>(origin + 16ull * wi)) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int q = 0; q < kMinStageDepth; ++q) {
+            const uint32_t wi = w0i + 32u * q + lane;
+            if (wi >= nwords) continue;
+            uint32_t word = 0;
+            if (whole[q]) {
+                word = (code4(v[q].x) << 24) | (code4(v[q].y) << 16) | (code4(v[q].z) << 8) | code4(v[q].w);
+            } else {                                             // first / last chunk of the sequence: bytes outside it are code 0
+                const int64_t cb = (int64_t)cb0 + 16ll * wi;
+                if (cb < (int64_t)L) {
+                    const uint8_t* src = origin + 16ull * wi;
 #pragma unroll 1
-                for (int bb = 0; bb < 16; ++bb) {
-                    const int64_t at = cb + bb;
-                    const uint32_t c = (at >= 0 && at < (int64_t)L) ? (uint32_t)src[bb] : 0u;
-                    word = (word << 2) | base_code(c);
+                    for (int bb = 0; bb < 16; ++bb) {
+                        const int64_t at = cb + bb;
+                        const uint32_t c = (at >= 0 && at < (int64_t)L) ? (uint32_t)src[bb] : 0u;
+                        word = (word << 2) | base_code(c);
+                    }
                 }
             }
+            codes[wi] = word;
         }
-        codes[wi] = word;
     }
-    __syncthreads();
+    __syncwarp();
 
     const uint32_t fl = tl.fwd;
     const uint32_t bshift = (k - kk) + mis - x0;             // base index in the staged words of k-mer x's first surviving base: x + bshift
@@ -152,7 +178,7 @@ minimize_kernel(const uint8_t* __restrict__ buf, const MinTile* __restrict__ til
 
     // chunk c of the slice = slice positions [8c, 8c+8) = tuples o0 - g_in + 8c ... of the sequence
     const uint32_t c_first = g_in >> 3, c_last = (g_in + (o1 - o0) + 7) >> 3;   // chunks that intersect the tile
-    for (uint32_t chunk = c_first + threadIdx.x; chunk < c_last; chunk += blockDim.x) {
+    for (uint32_t chunk = c_first + lane; chunk < c_last; chunk += kWarp) {
         const uint32_t sp = 8 * chunk;                        // slice position of the chunk
         const uint32_t lo = max(sp, g_in), hi = min(sp + 8, g_in + (o1 - o0));
         const uint32_t oc = sp - g_in + o0;                   // tuple index of the chunk's first slot (wraps if sp < g_in: then lo != sp)
@@ -172,35 +198,41 @@ minimize_kernel(const uint8_t* __restrict__ buf, const MinTile* __restrict__ til
             uint32_t h[NH];
 #pragma unroll
             for (int t = 0; t < NH; ++t) h[t] = __funnelshift_l(A1, A0, 2 * t) >> hshift;
-            uint32_t mv[8], ma[8];
-            if (W == 5) {   // shared partial minima: pairs, quads, then the fifth k-mer
-                uint32_t pv[11], pa[11];
-#pragma unroll
-                for (int t = 0; t < 11; ++t) { pv[t] = h[t]; pa[t] = t; lmin(pv[t], pa[t], h[t + 1], t + 1); }
-#pragma unroll
-                for (int t = 0; t < 8; ++t) {
-                    mv[t] = pv[t]; ma[t] = pa[t];
-                    lmin(mv[t], ma[t], pv[t + 2], pa[t + 2]);
-                    lmin(mv[t], ma[t], h[t + 4], t + 4);
-                }
-            } else {
-#pragma unroll
-                for (int t = 0; t < 8; ++t) {
-                    mv[t] = h[t]; ma[t] = t;
-#pragma unroll
-                    for (int u = 1; u < (W > 0 ? W : 1); ++u) lmin(mv[t], ma[t], h[t + u], t + u);
-                }
-            }
+            // Leftmost strict minimum of each of the 8 windows, without compare-and-select chains (they cost three
+            // alu-pipe instructions per candidate): the VALUE is a chain of three-input minima; the POSITION is the
+            // number of leading candidates that differ from it -- with n_u = min(h_u - m, 1) (0 where candidate u attains
+            // the minimum, one fused add-min each) the offset of the first zero is n_0 (1 + n_1 (1 + n_2 ( ... ))), a
+            // Horner chain of multiply-adds on the otherwise idle fma pipe.
             const uint32_t p0 = xa + 1;                       // reported positions are 1-based k-mer indices
             uint32_t ho[8], po[8];
-            uint32_t f0 = 0, f1 = 0;
 #pragma unroll
             for (int t = 0; t < 8; ++t) {
-                const bool none = mv[t] == 0xffffffffu;       // every hash of the window was 0xFFFFFFFF: the zero tuple
-                ho[t] = none ? 0u : mv[t];
-                po[t] = none ? 0u : p0 + ma[t];
-                const uint32_t fb = none ? 0u : fl;
-                if (t < 4) f0 |= fb << (8 * t); else f1 |= fb << (8 * (t - 4));
+                uint32_t m = h[t];
+                int u = 1;
+#pragma unroll
+                for (; u + 1 < W; u += 2) m = __vimin3_u32(m, h[t + u], h[t + u + 1]);
+                if (u < W) m = min(m, h[t + u]);
+                const uint32_t negm = 0u - m;
+                uint32_t P = 0;
+#pragma unroll
+                for (int v = W - 2; v >= 0; --v) {
+                    const uint32_t nv = __viaddmin_u32(h[t + v], negm, 1u);   // h >= m: the difference does not wrap
+                    P = nv * P + nv;
+                }
+                ho[t] = m;
+                po[t] = p0 + t + P;
+            }
+            uint32_t f0 = fl * 0x01010101u, f1 = f0;
+            if (K16) {   // only a 16-base hash can be 0xFFFFFFFF: a window of nothing else yields the zero tuple (:106-120)
+                f0 = 0; f1 = 0;
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    const bool none = ho[t] == 0xffffffffu;
+                    ho[t] = none ? 0u : ho[t];
+                    po[t] = none ? 0u : po[t];
+                    const uint32_t fb = none ? 0u : fl;
+                    if (t < 4) f0 |= fb << (8 * t); else f1 |= fb << (8 * (t - 4));
+                }
             }
             uint4* hp = reinterpret_cast<uint4*>(hash + sp);
             uint4* pp = reinterpret_cast<uint4*>(pos + sp);

@@ -47,9 +47,11 @@ int min_plan_build(b200_min_plan* p, b200_ctx* ctx, size_t n, const uint64_t* of
     p->tuples = p->out_off[n];
     p->n_tiles = tiles.size();
     // shared memory: the packed 2-bit codes of every base the tile can touch (+ spare words, see the kernel)
-    const uint64_t nx = (uint64_t)kMinTile + 2ull * w + 1;
+    // (per warp: its share of the slice plus the overlap its windows need, see the kernel)
+    const uint64_t nx = (uint64_t)kMinWarpTuples + 2ull * w + 1;
     const uint64_t nwords = (15 + nx + k - 1 + 15) / 16 + 3;
-    p->smem_bytes = (size_t)(nwords * 4);
+    p->warp_words = (uint32_t)nwords;
+    p->smem_bytes = (size_t)(nwords * 4) * (kMinThreads / 32);
     p->buf_bytes = n ? off[n] : 0;
     if (p->smem_bytes > 200 * 1024) return fail(B200_E_ARG, "window/k-mer length too large for the shared-memory tile");
     TRY(p->d_off.ensure((n + 1) * 8));
@@ -89,16 +91,19 @@ extern "C" int b200_min_plan_run(b200_min_plan* p, const char* d_buf, uint32_t* 
     const bool aligned = ((reinterpret_cast<uintptr_t>(d_hash) | reinterpret_cast<uintptr_t>(d_pos)) & 15u) == 0 &&
                          (reinterpret_cast<uintptr_t>(d_flag) & 7u) == 0;
     const uint32_t W = (aligned && p->w >= 1 && p->w <= (uint32_t)kMinMaxW) ? p->w : 0;
+#define MINK2(WW, KK)                                                                                                    \
+        if (p->smem_bytes > 48 * 1024)                                                                                   \
+            CU(cudaFuncSetAttribute(minimize_kernel<WW, KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes)); \
+        minimize_kernel<WW, KK><<<(unsigned)p->n_tiles, kMinThreads, p->smem_bytes, st>>>(                               \
+            reinterpret_cast<const uint8_t*>(d_buf), p->d_tiles.as<MinTile>(), p->k, p->w, p->buf_bytes, p->warp_words,  \
+            d_hash, d_pos, d_flag);
 #define MINK(WW)                                                                                                         \
     case WW:                                                                                                             \
-        if (p->smem_bytes > 48 * 1024)                                                                                   \
-            CU(cudaFuncSetAttribute(minimize_kernel<WW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes)); \
-        minimize_kernel<WW><<<(unsigned)p->n_tiles, kMinThreads, p->smem_bytes, st>>>(                                   \
-            reinterpret_cast<const uint8_t*>(d_buf), p->d_tiles.as<MinTile>(), p->k, p->w, p->buf_bytes, d_hash,         \
-            d_pos, d_flag);                                                                                              \
+        if (p->k >= 16) { MINK2(WW, true) } else { MINK2(WW, false) }                                                    \
         break;
     switch (W) { MINK(1) MINK(2) MINK(3) MINK(4) MINK(5) MINK(6) MINK(7) MINK(8) default: MINK(0) }
 #undef MINK
+#undef MINK2
     c->kernel_launches++;
     CU(cudaGetLastError());
     return B200_OK;

@@ -43,14 +43,38 @@ def _equal(got, exp, what):
 def test_host_pipeline_wave_schedules(ctx, n):
     qb, qo, tb, to = synth.short_pairs(77, n, 150)
     exp = CHK.align_batch_full(qb, qo, tb, to, 0, 1, -1, -1, threads=THREADS)
-    for taper in (1, 0):
+    for taper, stream in ((1, 1), (0, 1), (1, 0), (0, 0)):     # shrinking tail of waves; one persistent fill fed by a watermark
         ctx.set_option("taper_tail", taper)
-        got = ctx.align_packed(qb, qo, tb, to, 0, 1, -1, -1, True, cigar_cap=64 * n)
-        _equal(got, exp, f"n={n} taper={taper}")
+        ctx.set_option("stream_fill", stream)
+        for _ in range(2):   # twice: the second run reuses every workspace (stale flags / counters would show)
+            got = ctx.align_packed(qb, qo, tb, to, 0, 1, -1, -1, True, cigar_cap=64 * n)
+            _equal(got, exp, f"n={n} taper={taper} stream={stream}")
     ctx.set_option("taper_tail", 1)
+    ctx.set_option("stream_fill", 0)
     # score-only through the same pipeline
     s, t_, _, _ = ctx.align_packed(qb, qo, tb, to, 0, 1, -1, -1, False)
     assert np.array_equal(s, exp[0]) and np.array_equal(t_, exp[1])
+
+
+def test_streaming_fill_with_flagged_pairs_and_other_types(ctx):
+    """Pairs that are not pure ACGT inside a streamed batch: flagged by the pack kernels while the persistent fill is
+    already running, skipped by it, repaired afterwards -- all three alignment types."""
+    n = 420_000
+    qb, qo, tb, to = synth.short_pairs(81, n, 150)
+    qb = qb.copy(); tb = tb.copy()
+    rng = np.random.default_rng(5)
+    for i in rng.integers(0, n, size=300):
+        qb[int(i) * 150 + int(rng.integers(0, 150))] = ord("N")
+    for i in rng.integers(0, n, size=200):
+        tb[int(i) * 150 + int(rng.integers(0, 150))] = ord("-")
+    tb[(n - 1) * 150 + 149] = ord("n")          # the very last base of the batch
+    for typ in (0, 1, 2):
+        exp = CHK.align_batch_full(qb, qo, tb, to, typ, 1, -1, -1, threads=THREADS)
+        for stream in (1, 0):
+            ctx.set_option("stream_fill", stream)
+            got = ctx.align_packed(qb, qo, tb, to, typ, 1, -1, -1, True, cigar_cap=64 * n)
+            _equal(got, exp, f"type {typ} stream={stream}")
+    ctx.set_option("stream_fill", 0)
 
 
 def test_host_pipeline_other_lengths_and_types(ctx):
@@ -92,8 +116,9 @@ def test_pointer_array_entry_point_threaded_gather(n):
 
 
 @pytest.mark.parametrize("typ", [0, 1, 2])
-def test_substitution_by_prmt_and_by_shared_table_agree(ctx, typ):
-    """Both variants of K1 and K3 against the checker: unit scores and the largest scores the tables take."""
+def test_fill_kernel_variants_agree(ctx, typ):
+    """Every variant of K1 and K3 (substitution by PRMT / shared table, plain / software-pipelined columns) against the
+    checker: unit scores and larger ones."""
     n = 20_000
     qb, qo, tb, to = synth.short_pairs(79, n, 150)
     qs, ts = seqgen.ont_like_pairs(31 + typ, 6, mean_len=3000, min_len=2100, max_len=4500)
@@ -101,15 +126,20 @@ def test_substitution_by_prmt_and_by_shared_table_agree(ctx, typ):
     for (m, x, g) in ((1, -1, -1), (2, -3, -2), (5, -4, -6)):
         exp_s = CHK.align_batch_full(qb, qo[:4097], tb, to[:4097], typ, m, x, g, threads=THREADS)
         exp_l = CHK.align_batch_full(lq, lqo, lt, lto, typ, m, x, g, threads=min(6, THREADS))
-        res = {}
-        for lds in (1, 0):
+        first = None
+        for lds, pipe in ((3, 1), (3, 0), (0, 1), (0, 0)):   # subst_lds: bit 0 = K1, bit 1 = K3
             ctx.set_option("subst_lds", lds)
-            res[lds] = ctx.align_packed(qb, qo, tb, to, typ, m, x, g, True, cigar_cap=80 * n)
-            _equal(res[lds], exp_s, f"K1 lds={lds} scores {(m, x, g)}")   # (the checker saw the first 4 096 pairs)
+            ctx.set_option("fill_pipe", pipe)
+            got = ctx.align_packed(qb, qo, tb, to, typ, m, x, g, True, cigar_cap=80 * n)
+            _equal(got, exp_s, f"K1 lds={lds} pipe={pipe} scores {(m, x, g)}")   # (the checker saw the first 4 096 pairs)
+            if first is None:
+                first = got
+            else:
+                _equal(got, first, f"K1 lds={lds} pipe={pipe} against the first variant, every pair")
             got_l = ctx.align_packed(lq, lqo, lt, lto, typ, m, x, g, True)
-            _equal(got_l, exp_l, f"K3 lds={lds} scores {(m, x, g)}")
-        _equal(res[0], (res[1][0], res[1][1], res[1][2], res[1][3]), "K1 PRMT vs table, every pair")
-    ctx.set_option("subst_lds", 1)
+            _equal(got_l, exp_l, f"K3 lds={lds} pipe={pipe} scores {(m, x, g)}")
+    ctx.set_option("subst_lds", 2)
+    ctx.set_option("fill_pipe", 1)
 
 
 @pytest.mark.parametrize("typ", [0, 1, 2])
