@@ -118,7 +118,7 @@ def test_pointer_array_entry_point_threaded_gather(n):
 @pytest.mark.parametrize("typ", [0, 1, 2])
 def test_fill_kernel_variants_agree(ctx, typ):
     """Every variant of K1 and K3 (substitution by PRMT / shared table, plain / software-pipelined columns) against the
-    checker: unit scores and larger ones."""
+    checker: unit scores and larger ones. (The context is the test's own.)"""
     n = 20_000
     qb, qo, tb, to = synth.short_pairs(79, n, 150)
     qs, ts = seqgen.ont_like_pairs(31 + typ, 6, mean_len=3000, min_len=2100, max_len=4500)
@@ -127,19 +127,19 @@ def test_fill_kernel_variants_agree(ctx, typ):
         exp_s = CHK.align_batch_full(qb, qo[:4097], tb, to[:4097], typ, m, x, g, threads=THREADS)
         exp_l = CHK.align_batch_full(lq, lqo, lt, lto, typ, m, x, g, threads=min(6, THREADS))
         first = None
-        for lds, pipe in ((3, 1), (3, 0), (0, 1), (0, 0)):   # subst_lds: bit 0 = K1, bit 1 = K3
-            ctx.set_option("subst_lds", lds)
-            ctx.set_option("fill_pipe", pipe)
+        # subst_lds: bit 0 = K1, bit 1 = K3; fill_pipe: K1 pipelined columns
+        for lds, pipe in ((3, 1), (3, 0), (0, 1), (0, 0), (2, 1)):
+            for key, val in (("subst_lds", lds), ("fill_pipe", pipe)):
+                ctx.set_option(key, val)
+            what = f"lds={lds} pipe={pipe} scores {(m, x, g)}"
             got = ctx.align_packed(qb, qo, tb, to, typ, m, x, g, True, cigar_cap=80 * n)
-            _equal(got, exp_s, f"K1 lds={lds} pipe={pipe} scores {(m, x, g)}")   # (the checker saw the first 4 096 pairs)
+            _equal(got, exp_s, "K1 " + what)   # (the checker saw the first 4 096 pairs)
             if first is None:
                 first = got
             else:
-                _equal(got, first, f"K1 lds={lds} pipe={pipe} against the first variant, every pair")
+                _equal(got, first, "K1 against the first variant, every pair: " + what)
             got_l = ctx.align_packed(lq, lqo, lt, lto, typ, m, x, g, True)
-            _equal(got_l, exp_l, f"K3 lds={lds} pipe={pipe} scores {(m, x, g)}")
-    ctx.set_option("subst_lds", 2)
-    ctx.set_option("fill_pipe", 1)
+            _equal(got_l, exp_l, "K3 " + what)
 
 
 @pytest.mark.parametrize("typ", [0, 1, 2])
