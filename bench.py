@@ -218,7 +218,7 @@ def c4_strong(args, D, rank, world, local_rank, ctx, capi, torch):
     from bioinfo1_b200 import shard
     L = capi.lib()
     n_reads = args.c4_reads
-    S = {"t_index": 0.0, "t_index_first": 0.0, "t_local": 0.0, "n_workers": 1}
+    S = {"t_index": 0.0, "t_index_first": 0.0, "t_local": 0.0, "n_workers": 1, "batch_reads": 0}
     ph = Phases()
 
     def setup():
@@ -242,7 +242,12 @@ def c4_strong(args, D, rank, world, local_rank, ctx, capi, torch):
         torch.cuda.synchronize()
         S["t_index"] = time.perf_counter() - t0
         n_mine, off = S["n_mine"], S["off"]
-        batches = [(a, min(n_mine, a + args.c4_batch)) for a in range(0, n_mine, args.c4_batch)]
+        # The same rule at every N: two batches in flight per GPU, the rank's reads cut into an EVEN number of equal
+        # batches of at most --c4-batch reads (so that both workers get the same share whatever the shard size).
+        n_batches = 2 * max(1, -(-n_mine // (2 * args.c4_batch)))
+        per = -(-n_mine // n_batches)
+        batches = [(a, min(n_mine, a + per)) for a in range(0, n_mine, per)]
+        S["batch_reads"] = per
         n_workers = max(1, min(2, len(batches)))
         S["batches"], S["n_workers"] = batches, n_workers
         S["ctxs"] = [ctx] + [capi.Context(local_rank) for _ in range(n_workers - 1)]
@@ -314,7 +319,8 @@ def c4_strong(args, D, rank, world, local_rank, ctx, capi, torch):
         return {"error": ph.err or "another rank failed"}
     return {"reads": n_reads, "mapped": int(mapped), "bases": int(bases), "map_s": t, "reads_per_s": mapped / t,
             "index_build_s": t_index, "index_build_first_call_s": t_index_first,
-            "batch_reads": args.c4_batch, "batches_in_flight": S["n_workers"], "split": "by cost (span^2), shard.partition",
+            "batch_reads": S.get("batch_reads"), "batch_rule": f"even number of equal batches of <= {args.c4_batch} reads per rank",
+            "batches_in_flight": S["n_workers"], "split": "by cost (span^2), shard.partition",
             "rank_seconds_min_max": [t_min, t], "score_checksum": int(checksum), "cigar_bytes": int(cig_total),
             "note": "host buffers in, PAF fields + CIGAR out (b200_map_batch), semiGlobal 1/-1/-1, k=15 w=5 f=0.001, "
                     "FASTQ-flavoured lookup (both strands); time = wall clock of the slowest rank"}

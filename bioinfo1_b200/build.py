@@ -82,7 +82,7 @@ def build_all(verbose=False, force=False):
     if os.path.exists(cli_src):
         exe = os.path.join(HERE, "b200_mapper")
         if force or _newer(exe, [cli_src, out] + hdrs):
-            _run(["g++", "-O2", "-std=c++17", "-Wall", "-pthread", "-I", INCLUDE, "-o", exe, cli_src, "-L", HERE, "-lb200map",
+            _run(["g++", "-O2", "-std=c++17", "-Wall", "-pthread", "-I", INCLUDE, "-o", exe, cli_src, "-L", HERE, "-lb200map", "-lz",
                   "-Wl,-rpath,$ORIGIN"], verbose)
     test_src = os.path.join(ROOT, "tests", "cpp", "dropin_test.cpp")
     if cpp_src and os.path.exists(test_src):

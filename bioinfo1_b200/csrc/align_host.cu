@@ -192,6 +192,19 @@ inline void copy_bytes(char* d, const char* s, uint64_t n) {
         uint64_t k = 0;
         for (; k + 16 <= n; k += 16) _mm_storeu_si128(reinterpret_cast<__m128i*>(d + k), _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + k)));
         if (k < n) _mm_storeu_si128(reinterpret_cast<__m128i*>(d + n - 16), _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + n - 16)));
+    } else if (n >= 4096) {
+        // long runs: streaming stores (the staging buffer is written once and read by the DMA engine, never by this core:
+        // a cached store would first read every destination line -- a third more memory traffic)
+        while ((reinterpret_cast<uintptr_t>(d) & 15u) && n) { *d++ = *s++; --n; }
+        uint64_t k = 0;
+        for (; k + 64 <= n; k += 64) {
+            const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + k)), b = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + k + 16));
+            const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + k + 32)), e = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + k + 48));
+            _mm_stream_si128(reinterpret_cast<__m128i*>(d + k), a); _mm_stream_si128(reinterpret_cast<__m128i*>(d + k + 16), b);
+            _mm_stream_si128(reinterpret_cast<__m128i*>(d + k + 32), c); _mm_stream_si128(reinterpret_cast<__m128i*>(d + k + 48), e);
+        }
+        if (k < n) std::memcpy(d + k, s + k, n - k);
+        _mm_sfence();
     } else {
         std::memcpy(d, s, n);
     }
@@ -294,7 +307,9 @@ extern "C" int b200_align_batch(int device, size_t n, const char* const* query, 
     g.off[0] = c->h_off.as<uint64_t>(); g.off[1] = g.off[0] + (n + 1);
     // small batches: one thread, no pipeline to feed
     const unsigned T = n >= 4 * Gatherer::kBlock ? host_threads() : 1u;
+    PhaseTrace ptr_trace;
     g.offsets(T);
+    ptr_trace.mark("ptr:offsets");
     TRY(c->h_q.ensure(g.off[0][n] + 1));
     TRY(c->h_t.ensure(g.off[1][n] + 1));
     g.dst[0] = c->h_q.as<char>(); g.dst[1] = c->h_t.as<char>();
@@ -326,8 +341,10 @@ extern "C" int b200_align_batch(int device, size_t n, const char* const* query, 
             s_cig = c->h_out_cigar.as<char>();
         }
     }
+    ptr_trace.mark("ptr:start-gather");
     int rc = align_batch_host(c, n, src, qo, to, type, match, mismatch, gap, s_score, s_tb, s_cig, s_off, s_cap);
     g.join();
+    ptr_trace.mark("ptr:align");
     if (rc != B200_OK) {
         const std::string msg = b200_last_error();
         ctx_sync_all_streams(c);   // no copy may still read the staging buffers the next call refills
@@ -347,6 +364,7 @@ extern "C" int b200_align_batch(int device, size_t n, const char* const* query, 
             th.emplace_back([&, t] { for (const Part& p : parts) std::memcpy(p.d + p.n * t / T, p.s + p.n * t / T, p.n * (t + 1) / T - p.n * t / T); });
         for (const Part& p : parts) std::memcpy(p.d, p.s, p.n / T);
         for (auto& x : th) x.join();
+        ptr_trace.mark("ptr:copy-out");
     }
     return rc;
 }

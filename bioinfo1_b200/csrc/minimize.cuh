@@ -7,15 +7,18 @@
 // a window whose minimum is 0xFFFFFFFF yields the zero tuple (:106-120).
 //
 // HBM-bound by design: L bytes in, 9 bytes per window out -- so the kernel is written to spend as few
-// instructions per window as it can (the first version spent ~80 and ran at a quarter of the copy rate):
-//   * a CTA owns one 2048-aligned slice of the GLOBAL output index space (cut at sequence ends), so that
+// instructions per window as it can and to keep loads in flight while it computes:
+//   * a CTA owns one 8192-aligned slice of the GLOBAL output index space (cut at sequence ends), so that
 //     every thread's chunk of 8 consecutive tuples is 32-byte aligned in the hash/pos arrays and 8-byte
 //     aligned in the flag array: five vector stores per 8 tuples;
-//   * the bases the slice needs are staged once into shared memory as 2-bit codes (16 per word, first
-//     base most significant): one aligned 128-bit load per word, four bases at a time in SWAR form;
+//   * every WARP stages the bases of its own eighth of the slice into its own piece of shared memory as 2-bit
+//     codes (16 per word, first base most significant): three aligned 128-bit loads in flight per lane, sixteen
+//     bases validated and converted at a time in SWAR form; no CTA-wide barrier, so the warps of an SM drift
+//     apart and one warp's load latency is another's compute time;
 //   * a thread pulls three packed words, lines them up with two funnel shifts and gets each of the
 //     8+w-1 k-mer hashes its windows touch with one more funnel shift and a shift;
-//   * the leftmost minima of the 8 overlapping windows share partial minima (pairs, then quads, for w = 5).
+//   * the leftmost minimum of a window is a chain of three-input minima for the value and, for the position,
+//     the count of leading candidates that differ from it (fused add-min per candidate, a multiply-add chain).
 // Chunks that touch section 1 or 3, a sequence end or a slice edge take a per-tuple path.
 #pragma once
 #include "common.cuh"
@@ -46,38 +49,39 @@ __device__ __forceinline__ uint32_t base_code(uint32_t c) {
     return (c == 'A') ? 1u : (c == 'T') ? 2u : (c == 'G') ? 3u : 0u;
 }
 
-__device__ __forceinline__ uint32_t prmt_b32(uint32_t a, uint32_t b, uint32_t sel) {
-    uint32_t r;
-    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
-    return r;
+// Four ASCII bases (first base in the low byte) -> 8 bits, first base in the two most significant bits.
+// With h = v >> 1: the letters' codes are (h & 3) = A 0, C 1, T 2, G 3, and a byte is one of "ACGT" exactly when it
+// equals (0x41 | (v & 6)) ^ (0x11 if bit 2 is set and bit 1 is not, i.e. T) -- checked over all 256 byte values.
+__device__ __forceinline__ uint32_t acgt_mismatch4(uint32_t v, uint32_t h) {    // 0 iff all four bytes are in "ACGT"
+    const uint32_t t = (v >> 2) & ~h & 0x01010101u;
+    return ((0x41414141u | (v & 0x06060606u)) ^ (t * 0x11u)) ^ v;
 }
-
-// four ASCII bases (first base in the low byte) -> 8 bits, first base in the two most significant bits
+__device__ __forceinline__ uint32_t pack4_valid(uint32_t h) {                   // h = v >> 1 of four valid letters
+    const uint32_t c4 = h & 0x03030303u;
+    const uint32_t m4 = c4 ^ ((~c4 >> 1) & 0x01010101u);                        // -> C=0 A=1 T=2 G=3
+    return (m4 * 0x40100401u) >> 24;                                            // b0<<6 | b1<<4 | b2<<2 | b3
+}
 __device__ __forceinline__ uint32_t code4(uint32_t v) {
-    const uint32_t c4 = (v >> 1) & 0x03030303u;                               // A=0 C=1 T=2 G=3 per byte
-    const uint32_t sel = (c4 & 0x3u) | ((c4 >> 4) & 0x30u) | ((c4 >> 8) & 0x300u) | ((c4 >> 12) & 0x3000u);
-    if (prmt_b32(0x47544341u, 0u, sel) == v) {                                  // re-encoding "ACTG"[code] gives the bytes back
-        const uint32_t m4 = c4 ^ ((~c4 >> 1) & 0x01010101u);                    // -> C=0 A=1 T=2 G=3
-        return (m4 * 0x40100401u) >> 24;                                        // b0<<6 | b1<<4 | b2<<2 | b3
-    }
+    const uint32_t h = v >> 1;
+    if (acgt_mismatch4(v, h) == 0) return pack4_valid(h);
     uint32_t c8 = 0;
 #pragma unroll
     for (int bb = 0; bb < 4; ++bb) c8 = (c8 << 2) | base_code((v >> (8 * bb)) & 0xffu);
     return c8;
 }
-
-// leftmost strict minimum: b (the right-hand candidate) only wins when strictly smaller
-__device__ __forceinline__ void lmin(uint32_t& v, uint32_t& at, uint32_t bv, uint32_t bat) {
-    const bool take = bv < v;
-    v = take ? bv : v;
-    at = take ? bat : at;
+// sixteen bases at once: one validity test for the whole 16-byte chunk
+__device__ __forceinline__ uint32_t code16(const uint4& v) {
+    const uint32_t hx = v.x >> 1, hy = v.y >> 1, hz = v.z >> 1, hw = v.w >> 1;
+    if ((acgt_mismatch4(v.x, hx) | acgt_mismatch4(v.y, hy) | acgt_mismatch4(v.z, hz) | acgt_mismatch4(v.w, hw)) == 0)
+        return (pack4_valid(hx) << 24) | (pack4_valid(hy) << 16) | (pack4_valid(hz) << 8) | pack4_valid(hw);
+    return (code4(v.x) << 24) | (code4(v.y) << 16) | (code4(v.z) << 8) | code4(v.w);
 }
 
 // W = compile-time window length for the register fast path (1..kMinMaxW), or 0: every tuple takes the
 // per-tuple path (any w; also used when the output pointers are not 16-byte aligned).
 // K16: k >= 16, the only case in which a hash can be 0xFFFFFFFF (the register path then checks for the zero tuple).
 template <int W, bool K16>
-__global__ void __launch_bounds__(kMinThreads, 6)
+__global__ void __launch_bounds__(kMinThreads, 8)
 minimize_kernel(const uint8_t* __restrict__ buf, const MinTile* __restrict__ tiles, uint32_t k, uint32_t w,
                 uint64_t buf_bytes, uint32_t warp_words, uint32_t* __restrict__ hash, uint32_t* __restrict__ pos,
                 uint8_t* __restrict__ flag) {
@@ -132,7 +136,7 @@ minimize_kernel(const uint8_t* __restrict__ buf, const MinTile* __restrict__ til
             if (wi >= nwords) continue;
             uint32_t word = 0;
             if (whole[q]) {
-                word = (code4(v[q].x) << 24) | (code4(v[q].y) << 16) | (code4(v[q].z) << 8) | code4(v[q].w);
+                word = code16(v[q]);
             } else {                                             // first / last chunk of the sequence: bytes outside it are code 0
                 const int64_t cb = (int64_t)cb0 + 16ll * wi;
                 if (cb < (int64_t)L) {

@@ -40,7 +40,26 @@ def test_committed_bench_line_has_the_contract_keys():
 
 def test_roofline_traffic_comes_from_the_committed_capture():
     d = _latest_line()
-    with open(os.path.join(ROOT, "profiles", "ncu_traffic_r01b.json")) as f:
+    with open(os.path.join(ROOT, "profiles", "ncu_traffic_r02.json")) as f:
         tr = json.load(f)
     assert d["roofline"]["traffic"] == tr["fill_short_kernel"]["dram_bytes_per_launch"]
-    assert os.path.exists(os.path.join(ROOT, "profiles", "launches_r01b_bench.csv"))
+    assert abs(d["roofline"]["alu_pipe_frac"] - tr["fill_short_kernel"]["alu_pipe_pct"] / 100.0) < 1e-9
+    assert os.path.exists(os.path.join(ROOT, "profiles", "launches_r02_bench.csv"))
+
+
+def test_round2_fields_of_the_line():
+    """What the round-1 review asked the line to carry: the arithmetic that ran, e2e over the driver's step count with the
+    box's H2D ceiling beside it, the kernel's own ceiling, and configs 4 / 5 as strong-scaling sections."""
+    d = _latest_line()
+    assert "int16x2" in d["dtype"]
+    assert d["e2e"]["steps"] == d["steps"]
+    for k in ("h2d_ceiling_gbs", "h2d_bound_ms_per_step", "frac_of_h2d_bound", "pointer_api"):
+        assert k in d["e2e"], k
+    assert 0 < d["e2e"]["frac_of_h2d_bound"] <= 1.0
+    for k in ("alu_pipe_frac", "issue_slots_per_cell_pair", "ceiling_tcups", "frac_of_kernel_ceiling"):
+        assert k in d["roofline"], k
+    assert 0 < d["roofline"]["frac_of_kernel_ceiling"] < 1
+    c4, c5 = d["extra"]["c4_strong"], d["extra"]["c5_strong"]
+    assert c4["reads"] == 100_000 and c4["mapped"] > 99_000 and c4["reads_per_s"] > 0 and "shard.partition" in c4["split"]
+    assert c5["pairs"] == 10_000 and c5["gcups"] > 0 and c5["cells"] == 1e12
+    assert d["parity_spot_check"]["ok"] is True and "cigar bytes" in d["parity_spot_check"]["fields"]

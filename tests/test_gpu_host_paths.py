@@ -49,7 +49,7 @@ def test_host_pipeline_wave_schedules(ctx, n):
         for _ in range(2):   # twice: the second run reuses every workspace (stale flags / counters would show)
             got = ctx.align_packed(qb, qo, tb, to, 0, 1, -1, -1, True, cigar_cap=64 * n)
             _equal(got, exp, f"n={n} taper={taper} stream={stream}")
-    ctx.set_option("taper_tail", 1)
+    ctx.set_option("taper_tail", 0)
     ctx.set_option("stream_fill", 0)
     # score-only through the same pipeline
     s, t_, _, _ = ctx.align_packed(qb, qo, tb, to, 0, 1, -1, -1, False)

@@ -99,6 +99,22 @@ def test_cli_stdout_is_byte_identical_to_the_reference_mapper(case):
         assert r.stdout == f.read()
 
 
+def test_cli_reads_gzip_input(tmp_path):
+    """The reference links zlib (through bioparser) and takes .gz files; so does the CLI: same bytes as for the plain files."""
+    import gzip
+    import shutil
+    import subprocess
+    exe = os.path.join(ROOT, "bioinfo1_b200", "b200_mapper")
+    for name in ("ref.fa", "reads.fq"):
+        with open(os.path.join(GOLD, name), "rb") as src, gzip.open(tmp_path / (name + ".gz"), "wb") as dst:
+            shutil.copyfileobj(src, dst)
+    argv = ["-a", "semiGlobal", "-c", "-f", "0", str(tmp_path / "ref.fa.gz"), str(tmp_path / "reads.fq.gz")]
+    r = subprocess.run([exe] + argv, capture_output=True, timeout=300)
+    assert r.returncode == 0, r.stderr.decode(errors="replace")
+    with open(os.path.join(GOLD, "synth_fq_semi_c.paf"), "rb") as f:
+        assert r.stdout == f.read()
+
+
 def test_cli_statistics_go_to_stderr_and_two_gpus_option_is_accepted():
     import subprocess
     exe = os.path.join(ROOT, "bioinfo1_b200", "b200_mapper")

@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Hottest SASS region of an `ncu --page source --print-source sass --csv` export (gzip ok): the window of N
 consecutive instructions with the most stall samples, printed with samples, executions and the dominant stall reason.
-Usage: python tools/ncu_sass_hot.py file_sass.csv.gz [N]"""
+Usage: python tools/ncu_sass_hot.py file_sass.csv.gz [N] [kernel-name-substring]"""
 import csv
 import gzip
 import io
@@ -9,8 +9,14 @@ import sys
 
 path = sys.argv[1]
 N = int(sys.argv[2]) if len(sys.argv) > 2 else 120
+want = sys.argv[3] if len(sys.argv) > 3 else ""          # substring of the kernel name (an export can hold several launches)
 raw = gzip.open(path, "rt").read() if path.endswith(".gz") else open(path).read()
 rows = list(csv.reader(io.StringIO(raw)))
+starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
+pick = next((i for i in starts if want in rows[i][1]), starts[0])
+end = next((i for i in starts if i > pick), len(rows))
+rows = rows[pick:end]
+print("# kernel:", rows[0][1][:100])
 hdr_i = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
 hdr = rows[hdr_i]
 col = {h: i for i, h in enumerate(hdr)}
