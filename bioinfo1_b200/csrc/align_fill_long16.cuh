@@ -52,22 +52,6 @@ __device__ __forceinline__ uint32_t pick_uniform(const uint32_t (&Y)[32], uint32
 }
 #undef B200_PICK4
 
-// For both halves at once: 31 - (the smallest r whose half of Y[r] equals that half of `cm`, the packed maximum of
-// the 32 registers). Y[r] - cm is 0 where equal and at most -4 elsewhere (values carry the same tag, and a block's
-// values lie within the 16-bit window of each other, so the packed subtraction cannot wrap): max(Y[r] - cm, -1) is a
-// 0 / -1 mask, (mask & 0xffc0) | (31 - r) is 31 - r where equal and negative elsewhere, and a packed max tree picks
-// the smallest r. 32 VIADDMNMX + 32 LOP3 + 16 VIMNMX3 for the two blocks of a lane.
-__device__ __forceinline__ uint32_t first_rows_of_max(const uint32_t (&Y)[32], uint32_t cm) {
-    const uint32_t negm = __vneg2(cm);
-    const uint32_t keep = 0xffc0ffc0u;
-    auto key = [&](int r) { return lop3_and_or(__viaddmax_s16x2(Y[r], negm, 0xffffffffu), keep, dup16(31 - r)); };
-    uint32_t a = key(0), b = key(1);   // two running maxima (keys are folded as they are made: no 32-register array)
-#pragma unroll
-    for (int r = 2; r + 3 < 32; r += 4) { a = __vimax3_s16x2(a, key(r), key(r + 1)); b = __vimax3_s16x2(b, key(r + 2), key(r + 3)); }
-    a = __vimax3_s16x2(a, key(30), key(31));
-    return __vmaxs2(a, b);
-}
-
 // The same search restricted to the first vlo / vhi rows of the two blocks (the lanes that hold the end of the query):
 // {max of the low halves, max of the high halves, first row of each}. A real call on a copy of the registers: rare,
 // and inlined it costs the fill kernel 16 registers -- the room a traceback CTA needs next to it.

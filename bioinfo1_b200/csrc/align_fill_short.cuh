@@ -202,6 +202,22 @@ __device__ __forceinline__ uint32_t max_tree16(const uint32_t (&Y)[N]) {
     return __vmaxs2(v, m[N / 2 - 1]);
 }
 
+// For both halves at once: 31 - (the smallest r whose half of Y[r] equals that half of `cm`, the packed maximum of
+// the 32 registers). Y[r] - cm is 0 where equal and at most -4 elsewhere (values carry the same tag, and a block's
+// values lie within the 16-bit window of each other, so the packed subtraction cannot wrap): max(Y[r] - cm, -1) is a
+// 0 / -1 mask, (mask & 0xffc0) | (31 - r) is 31 - r where equal and negative elsewhere, and a packed max tree picks
+// the smallest r. 32 VIADDMNMX + 32 LOP3 + 16 VIMNMX3 for the two blocks of a lane.
+__device__ __forceinline__ uint32_t first_rows_of_max(const uint32_t (&Y)[32], uint32_t cm) {
+    const uint32_t negm = __vneg2(cm);
+    const uint32_t keep = 0xffc0ffc0u;
+    auto key = [&](int r) { return lop3_and_or(__viaddmax_s16x2(Y[r], negm, 0xffffffffu), keep, dup16(31 - r)); };
+    uint32_t a = key(0), b = key(1);   // two running maxima (keys are folded as they are made: no 32-register array)
+#pragma unroll
+    for (int r = 2; r + 3 < 32; r += 4) { a = __vimax3_s16x2(a, key(r), key(r + 1)); b = __vimax3_s16x2(b, key(r + 2), key(r + 3)); }
+    a = __vimax3_s16x2(a, key(30), key(31));
+    return __vmaxs2(a, b);
+}
+
 // Direction word layout written by this kernel (read back by walk_kernel, klass kClassShort):
 //   uint4 at dirs[dir_off + ((block * Tg + (j-1)) * 32 + lane) * 4 .. +3]; word k covers rows
 //   8k..8k+7 of the block, low half = pair A, high half = pair B, row 8k in the top 2 bits of the
@@ -373,8 +389,10 @@ struct ShortSweep {
             }
             if (TYPE == 1) {
                 int mA, mB;   // column maxima over the valid rows, as register halves
-                if (full_rows && j <= Tmin) {
-                    const uint32_t cm = max_tree16(Y);
+                uint32_t cm = 0;
+                const bool packed_cm = full_rows && j <= Tmin;
+                if (packed_cm) {
+                    cm = max_tree16(Y);
                     mA = half_lo(cm); mB = half_hi(cm);
                 } else {
                     mA = INT_MIN; mB = INT_MIN;
@@ -387,17 +405,29 @@ struct ShortSweep {
                 const int hA = (nvA && j <= TA) ? (mA + back) >> 2 : INT_MIN;
                 const int hB = (nvB && j <= TB) ? (mB + back) >> 2 : INT_MIN;
                 // a new maximum, or a tie that may sit on a smaller row of this block than the current holder
-                if (hA > bvA || (hA == bvA && biA > i0 + 1)) {
-                    uint32_t rr = RB;
+                const bool trigA = hA > bvA || (hA == bvA && biA > i0 + 1);
+                const bool trigB = hB > bvB || (hB == bvB && biB > i0 + 1);
+                if (trigA || trigB) {
+                    uint32_t rA = RB, rB = RB;   // smallest row of the block that holds each pair's column maximum
+                    bool found = false;
+                    if constexpr (RB == 32) {
+                        // full blocks: both pairs' rows at once with packed arithmetic (the scalar search below costs a
+                        // compare and a select per row and pair, and on related pairs it runs on every diagonal column)
+                        if (packed_cm && (cm & 0xffffu) != 0x8000u && (cm >> 16) != 0x8000u) {   // (-32768 has no packed negative)
+                            const uint32_t km = first_rows_of_max(Y, cm);
+                            rA = 31u - (uint32_t)half_lo(km); rB = 31u - (uint32_t)half_hi(km);
+                            found = true;
+                        }
+                    }
+                    if (!found) {
 #pragma unroll
-                    for (int r = RB - 1; r >= 0; --r) if ((uint32_t)r < nvA && half_lo(Y[r]) == mA) rr = r;
-                    if (hA > bvA || i0 + 1 + rr < biA) { bvA = hA; biA = i0 + 1 + rr; bjA = j; }
-                }
-                if (hB > bvB || (hB == bvB && biB > i0 + 1)) {
-                    uint32_t rr = RB;
-#pragma unroll
-                    for (int r = RB - 1; r >= 0; --r) if ((uint32_t)r < nvB && half_hi(Y[r]) == mB) rr = r;
-                    if (hB > bvB || i0 + 1 + rr < biB) { bvB = hB; biB = i0 + 1 + rr; bjB = j; }
+                        for (int r = RB - 1; r >= 0; --r) {
+                            if (trigA && (uint32_t)r < nvA && half_lo(Y[r]) == mA) rA = r;
+                            if (trigB && (uint32_t)r < nvB && half_hi(Y[r]) == mB) rB = r;
+                        }
+                    }
+                    if (trigA && (hA > bvA || i0 + 1 + rA < biA)) { bvA = hA; biA = i0 + 1 + rA; bjA = j; }
+                    if (trigB && (hB > bvB || i0 + 1 + rB < biB)) { bvB = hB; biB = i0 + 1 + rB; bjB = j; }
                 }
             }
         }

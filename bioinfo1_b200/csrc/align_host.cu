@@ -85,10 +85,16 @@ static int align_batch_host(b200_ctx* c, size_t n, const HostSource& src, const 
     if (chunk_pairs == 0) {
         size_t round_pairs = 0;
         TRY(align_short_round_pairs(c, type, &round_pairs));
-        if (c->taper_tail) {
+        if (c->taper_tail == 1) {
             std::vector<uint32_t> rev;
             for (double g = (double)c->sm_count * 4; g < (double)round_pairs / 64 && rev.size() < 8; g *= 1.38) rev.push_back((uint32_t)g);
             tail.assign(rev.rbegin(), rev.rend());
+        } else if (c->taper_tail == 2) {
+            // only the last wave cut in two: whatever does not fill whole rounds, halved
+            const uint64_t groups = div_up64(n, 64), round_groups = round_pairs / 64;
+            uint64_t last = groups % round_groups;
+            if (last == 0) last = round_groups;
+            if (groups > last && last >= 128) { tail.push_back((uint32_t)(last - last / 2)); tail.push_back((uint32_t)(last / 2)); }
         }
         const size_t rounds_per_chunk = std::max<size_t>(1, div_up64(div_up64(n, round_pairs), 16));   // at most 16 chunks
         chunk_pairs = round_pairs * rounds_per_chunk;

@@ -71,53 +71,84 @@ void usage(std::ostream& os) {
        << "\t  -h, --help, --version\n";
 }
 
-// ---- input files: mapped read-only, parsed in place ----------------------------------------------------------
+// ---- input files: read into memory once, parsed in place ----------------------------------------------------------
+// Large host buffers (file contents, packed sequences) come from 2 MB-aligned allocations advised to use huge pages:
+// a gigabyte filled through 4 KB page faults takes the process's memory-map lock a quarter of a million times, and the
+// CUDA contexts starting up on the other threads want that lock too (measured on 8 GPUs: the parse went from 1.1 s to
+// 5.6 s with a plain mmap of the file).
+struct HugeBuf {
+    char* p = nullptr;
+    size_t n = 0, cap = 0;
+    bool reserve(size_t want) {
+        if (want <= cap) return true;
+        const size_t two_mb = (size_t)2 << 20, sz = (want + two_mb - 1) / two_mb * two_mb;
+        void* q = nullptr;
+        if (posix_memalign(&q, two_mb, sz) != 0) return false;
+        madvise(q, sz, MADV_HUGEPAGE);
+        if (n) std::memcpy(q, p, n);
+        std::free(p);
+        p = static_cast<char*>(q); cap = sz;
+        return true;
+    }
+    bool append(const char* b, const char* e) {
+        const size_t k = (size_t)(e - b);
+        if (n + k > cap && !reserve(std::max(n + k, cap + cap / 2))) return false;
+        std::memcpy(p + n, b, k);
+        n += k;
+        return true;
+    }
+    const char* data() const { return p; }
+    size_t size() const { return n; }
+};
+
 struct MappedFile {
     const char* p = nullptr;
     size_t n = 0;
+    HugeBuf bytes;
     bool open(const std::string& path) {
         const int fd = ::open(path.c_str(), O_RDONLY);
         if (fd < 0) return false;
         struct stat st;
         if (fstat(fd, &st) != 0 || !S_ISREG(st.st_mode)) { ::close(fd); return false; }
-        n = (size_t)st.st_size;
-        if (n) {
-            void* m = mmap(nullptr, n, PROT_READ, MAP_PRIVATE, fd, 0);
-            if (m == MAP_FAILED) { ::close(fd); return false; }
-            madvise(m, n, MADV_SEQUENTIAL);   // (MAP_POPULATE was measured: slower, it competes with the CUDA start-up for the mm lock)
-            p = static_cast<const char*>(m);
+        const size_t sz = (size_t)st.st_size;
+        if (!bytes.reserve(sz + 64)) { ::close(fd); return false; }
+        while (bytes.n < sz) {
+            const ssize_t got = ::read(fd, bytes.p + bytes.n, std::min<size_t>(sz - bytes.n, (size_t)64 << 20));
+            if (got < 0) { ::close(fd); return false; }
+            if (got == 0) break;
+            bytes.n += (size_t)got;
         }
         ::close(fd);
+        p = bytes.p; n = bytes.n;
         // gzip input (the reference reads it through bioparser + zlib, CMakeLists.txt:28-30): inflated into memory once
         if (n >= 2 && (unsigned char)p[0] == 0x1f && (unsigned char)p[1] == 0x8b) return inflate_all(path);
         return true;
     }
-    std::vector<char> inflated;
     bool inflate_all(const std::string& path) {
         gzFile g = gzopen(path.c_str(), "rb");
         if (!g) return false;
         gzbuffer(g, 1 << 20);
-        inflated.clear();
-        inflated.reserve(4 * n + 64);
+        HugeBuf out;
+        if (!out.reserve(4 * n + 64)) { gzclose(g); return false; }
         std::vector<char> chunk(1 << 22);
         for (;;) {
             const int got = gzread(g, chunk.data(), (unsigned)chunk.size());
             if (got < 0) { gzclose(g); return false; }
             if (got == 0) break;
-            inflated.insert(inflated.end(), chunk.begin(), chunk.begin() + got);
+            if (!out.append(chunk.data(), chunk.data() + got)) { gzclose(g); return false; }
         }
         gzclose(g);
-        munmap(const_cast<char*>(p), n);
-        p = inflated.data();
-        n = inflated.size();
+        std::free(bytes.p);
+        bytes = out;
+        p = bytes.p; n = bytes.n;
         return true;
     }
 };
 
-// Sequences of a file, packed: sequence i is buf[off[i] .. off[i+1]); names point into the mapped file.
+// Sequences of a file, packed: sequence i is buf[off[i] .. off[i+1]); names point into the file's bytes.
 struct SeqSet {
     std::vector<std::string_view> names;
-    std::vector<char> buf;
+    HugeBuf buf;
     std::vector<uint64_t> off{0};
     size_t size() const { return names.size(); }
     uint64_t len(size_t i) const { return off[i + 1] - off[i]; }
@@ -142,7 +173,7 @@ inline std::string_view first_token(const char* b, const char* e) {   // header 
 
 bool parse_fasta(const MappedFile& f, SeqSet& out) {
     out = SeqSet();
-    out.buf.reserve(f.n);
+    if (!out.buf.reserve(f.n + 64)) return false;
     size_t at = 0;
     const char *b, *e;
     bool have = false;
@@ -153,7 +184,7 @@ bool parse_fasta(const MappedFile& f, SeqSet& out) {
             out.names.push_back(first_token(b, e));
             have = true;
         } else if (!have) return false;
-        else out.buf.insert(out.buf.end(), b, e);
+        else if (!out.buf.append(b, e)) return false;
     }
     if (have) out.off.push_back(out.buf.size());
     return !out.names.empty();
@@ -161,7 +192,7 @@ bool parse_fasta(const MappedFile& f, SeqSet& out) {
 
 bool parse_fastq(const MappedFile& f, SeqSet& out) {
     out = SeqSet();
-    out.buf.reserve(f.n / 2 + 64);
+    if (!out.buf.reserve(f.n / 2 + 64)) return false;
     size_t at = 0;
     const char *b, *e, *sb, *se, *pb, *pe, *qb, *qe;
     while (next_line(f.p, f.n, at, b, e)) {
@@ -170,7 +201,7 @@ bool parse_fastq(const MappedFile& f, SeqSet& out) {
         if (!next_line(f.p, f.n, at, sb, se) || !next_line(f.p, f.n, at, pb, pe) || !next_line(f.p, f.n, at, qb, qe)) return false;
         if (pb == pe || *pb != '+' || qe - qb != se - sb) return false;
         out.names.push_back(first_token(b, e));
-        out.buf.insert(out.buf.end(), sb, se);
+        if (!out.buf.append(sb, se)) return false;
         out.off.push_back(out.buf.size());
     }
     return !out.names.empty();
@@ -399,11 +430,15 @@ int main(int argc, char** argv) {
     // (B200_MAPPER_BATCH_READS / B200_MAPPER_WORKERS: test knobs.)
     Job J;
     J.o = &o; J.reads = &reads; J.ref_name = refs.names[0]; J.ref = ref; J.ref_len = ref_len; J.trace = trace;
-    if (!f2.open(o.file2)) { std::cerr << "Given file is not in FASTA or FASTQ format! \n"; return 1; }
+    struct stat st2;
+    if (stat(o.file2.c_str(), &st2) != 0 || !S_ISREG(st2.st_mode)) { std::cerr << "Given file is not in FASTA or FASTQ format! \n"; return 1; }
+    const size_t f2_bytes = (size_t)st2.st_size;   // (the file itself is read after the devices have been started)
     const char* env_batch = std::getenv("B200_MAPPER_BATCH_READS");
     const char* env_workers = std::getenv("B200_MAPPER_WORKERS");
-    const bool small = f2.n < ((size_t)192 << 20) * (size_t)o.gpus && o.gpus == 1;
-    const int workers_per_device = env_workers && std::atoi(env_workers) > 0 ? std::atoi(env_workers) : (small ? 1 : 2);
+    const bool small = f2_bytes < ((size_t)192 << 20) && o.gpus == 1;
+    // (a second context per device only pays when the device gets several batches: ~400 MB of input each)
+    const int workers_per_device = env_workers && std::atoi(env_workers) > 0 ? std::atoi(env_workers)
+                                   : (f2_bytes / (size_t)o.gpus >= ((size_t)384 << 20) ? 2 : 1);
     std::vector<std::thread> devs;
     for (int g = 0; g < o.gpus; ++g) devs.emplace_back(device_main, std::ref(J), g, workers_per_device);
     auto abort_devices = [&] {
@@ -412,8 +447,8 @@ int main(int argc, char** argv) {
         for (auto& t : devs) t.join();
     };
 
-    bool fastq = parse_fastq(f2, reads);   // FASTQ first, FASTA on failure (:533-556)
-    if (!fastq && !parse_fasta(f2, reads)) {
+    bool fastq = f2.open(o.file2) && parse_fastq(f2, reads);   // FASTQ first, FASTA on failure (:533-556)
+    if (!fastq && !(f2.p && parse_fasta(f2, reads))) {
         abort_devices();
         std::cerr << "Given file is not in FASTA or FASTQ format! \n";
         std::fflush(stderr);
