@@ -90,6 +90,11 @@ def build_all(verbose=False, force=False):
         if force or _newer(exe, [test_src, lib_path("libteam_b200.so")] + hdrs):
             _run(["g++", "-O1", "-std=c++17", "-Wall", "-I", INCLUDE, "-o", exe, test_src, "-L", HERE, "-lteam_b200",
                   "-lb200map", "-Wl,-rpath," + HERE], verbose)
+    hp_src = os.path.join(ROOT, "tests", "cpp", "host_pack_test.cpp")
+    if os.path.exists(hp_src):
+        exe = os.path.join(ROOT, "tests", "cpp", "host_pack_test")
+        if force or _newer(exe, [hp_src, os.path.join(CSRC, "host_pack.hpp")]):
+            _run(["g++", "-O2", "-std=c++17", "-Wall", "-o", exe, hp_src], verbose)
     return out
 
 

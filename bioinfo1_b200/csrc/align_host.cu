@@ -13,6 +13,7 @@
 #include <thread>
 #include <vector>
 
+#include "host_pack.hpp"
 #include "internal.hpp"
 
 using namespace b200;
@@ -24,62 +25,30 @@ struct HostSource {
     const char* q = nullptr;
     const char* t = nullptr;
     std::function<int(uint64_t q_end, uint64_t t_end)> wait;   // optional; returns B200_OK or the producer's error
+    // Host-packed mode (uniform short batches through the pointer-array entry point): the producer does not copy the
+    // bytes, it packs them to 2 bits (host_pack.hpp). What goes to the device per slice is then the 2-bit words of whole
+    // pairs (straight into the context's packed buffers), one flag byte per pair, and the raw bytes of the few pairs that
+    // are not pure ACGT (the byte-compare kernel of the repair pass reads those).
+    bool packed = false;
+    uint32_t Q = 0, T = 0;                      // the uniform lengths
+    const uint32_t* qpk = nullptr;              // n x (Q/16 + 2) words
+    const uint32_t* tpk = nullptr;              // n x (T/16 + 2) words
+    const uint8_t* flags = nullptr;             // n bytes
+    const char* const* q_ptr = nullptr;         // the caller's sequences (raw bytes of flagged pairs are uploaded from them)
+    const char* const* t_ptr = nullptr;
 };
 
-static int align_batch_host(b200_ctx* c, size_t n, const HostSource& src, const uint64_t* q_off, const uint64_t* t_off,
-                            int type, int match, int mismatch, int gap, int32_t* score, uint32_t* target_begin,
-                            char* cigar_buf, uint64_t* cigar_off, uint64_t cigar_cap) {
-    const bool want_cigar = cigar_off != nullptr;
-    TRY(set_device(c));
-    // rebase offsets so that only the referenced byte ranges are copied
-    const uint64_t q0 = q_off[0], q1 = q_off[n], t0 = t_off[0], t1 = t_off[n];
-    if (((q1 > q0) && !src.q) || ((t1 > t0) && !src.t)) return fail(B200_E_ARG, "null sequence buffer");
-    PhaseTrace tr;
-    // Start the sequence upload first, in byte slices on a separate copy stream with an event after each slice: the
-    // host-side planning below overlaps the DMA, and the plan's waves start as soon as the slice holding their last
-    // byte has landed. The first half goes in kHead equal slices before the plan exists; the second half is cut where
-    // the plan's waves end (uniform batches), so that no wave waits for bytes it does not need.
-    TRY(c->d_q.ensure(q1 - q0 + 64));
-    TRY(c->d_t.ensure(t1 - t0 + 64));
-    cudaStream_t st = c->stream;
-    constexpr int kHead = 8, kSlices = 16;
-    if (!c->copy_stream) CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-    const uint64_t qn = q1 - q0, tn = t1 - t0;
-    struct Cut { uint64_t q_end, t_end; };
-    std::vector<Cut> cuts;   // cuts[s] = bytes resident once copy_events[s] has fired
-    auto upload_to = [&](uint64_t q_end, uint64_t t_end) -> int {
-        const uint64_t qa = cuts.empty() ? 0 : cuts.back().q_end, ta = cuts.empty() ? 0 : cuts.back().t_end;
-        q_end = std::min(std::max(q_end, qa), qn); t_end = std::min(std::max(t_end, ta), tn);
-        if (src.wait) TRY(src.wait(q_end, t_end));
-        if (q_end > qa) CU(cudaMemcpyAsync(c->d_q.as<char>() + qa, src.q + q0 + qa, q_end - qa, cudaMemcpyHostToDevice, c->copy_stream));
-        if (t_end > ta) CU(cudaMemcpyAsync(c->d_t.as<char>() + ta, src.t + t0 + ta, t_end - ta, cudaMemcpyHostToDevice, c->copy_stream));
-        if (c->copy_events.size() <= cuts.size()) {
-            cudaEvent_t e; CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-            c->copy_events.push_back(e);
-        }
-        CU(cudaEventRecord(c->copy_events[cuts.size()], c->copy_stream));
-        cuts.push_back(Cut{q_end, t_end});
-        return B200_OK;
-    };
-    tl_mark(c, c->copy_stream, "start");
-    for (int s = 0; s < kHead; ++s) {
-        TRY(upload_to(qn * (s + 1) / kSlices, tn * (s + 1) / kSlices));
-        if (s == 0 || s == kHead - 1) tl_mark(c, c->copy_stream, "h2d" + std::to_string(s));
-    }
-    c->h2d_bytes += qn + tn;
-    tr.mark("enqueue-h2d");
+// The plan of a host-buffer call (recycled in the context). Uniform short batches are cut into chunks of whole ROUNDS
+// of the thread-per-pair kernel (every resident warp takes one 64-pair group per round): any other size leaves a partly
+// empty last round in every chunk. (`taper_tail`: two measured alternatives for the end of the batch)
+static int host_plan_build(b200_ctx* c, size_t n, const uint64_t* q_off, const uint64_t* t_off, int type, int match,
+                           int mismatch, int gap, bool want_cigar) {
     if (!c->host_plan) {
         c->host_plan = new (std::nothrow) b200_align_plan();
         if (!c->host_plan) return fail(B200_E_NOMEM, "out of host memory");
         c->host_plan->ctx = c;
     }
     b200_align_plan* plan = c->host_plan;   // recycled: its device and host buffers keep their capacity
-    // Uniform short batches are cut into chunks of whole ROUNDS of the thread-per-pair kernel (every resident warp
-    // takes one 64-pair group per round): any other size leaves a partly empty last round in every chunk.
-    // The batch ends with a few shrinking waves: a wave of one warp per SM sub-partition fills in a quarter of the
-    // time a full round takes (its warps do not queue for the alu pipe), and each wave before it is sized so that its
-    // fill is over when the next, smaller wave's bytes have landed (fill time / upload time of a wave is ~0.7) -- what
-    // is left to do after the last byte of the upload is the smallest wave's work.
     size_t chunk_pairs = (size_t)c->chunk_pairs;
     std::vector<uint32_t> tail;
     if (chunk_pairs == 0) {
@@ -99,8 +68,93 @@ static int align_batch_host(b200_ctx* c, size_t n, const HostSource& src, const 
         const size_t rounds_per_chunk = std::max<size_t>(1, div_up64(div_up64(n, round_pairs), 16));   // at most 16 chunks
         chunk_pairs = round_pairs * rounds_per_chunk;
     }
-    TRY(plan_build(plan, c, n, q_off, t_off, true, false, type, match, mismatch, gap, want_cigar ? 1 : 0, chunk_pairs, &tail));
+    return plan_build(plan, c, n, q_off, t_off, true, false, type, match, mismatch, gap, want_cigar ? 1 : 0, chunk_pairs, &tail);
+}
+
+// `plan_ready`: the context's host plan has already been built for exactly this batch (the pointer-array entry point
+// plans before it decides how to gather).
+static int align_batch_host(b200_ctx* c, size_t n, const HostSource& src, const uint64_t* q_off, const uint64_t* t_off,
+                            int type, int match, int mismatch, int gap, int32_t* score, uint32_t* target_begin,
+                            char* cigar_buf, uint64_t* cigar_off, uint64_t cigar_cap, bool plan_ready = false) {
+    const bool want_cigar = cigar_off != nullptr;
+    TRY(set_device(c));
+    // rebase offsets so that only the referenced byte ranges are copied
+    const uint64_t q0 = q_off[0], q1 = q_off[n], t0 = t_off[0], t1 = t_off[n];
+    if (!src.packed && (((q1 > q0) && !src.q) || ((t1 > t0) && !src.t))) return fail(B200_E_ARG, "null sequence buffer");
+    PhaseTrace tr;
+    // Start the sequence upload first, in byte slices on a separate copy stream with an event after each slice: the
+    // host-side planning below overlaps the DMA, and the plan's waves start as soon as the slice holding their last
+    // byte has landed. The first half goes in kHead equal slices before the plan exists; the second half is cut where
+    // the plan's waves end (uniform batches), so that no wave waits for bytes it does not need.
+    TRY(c->d_q.ensure(q1 - q0 + 64));
+    TRY(c->d_t.ensure(t1 - t0 + 64));
+    cudaStream_t st = c->stream;
+    constexpr int kHead = 8, kSlices = 16;
+    if (!c->copy_stream) CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    const uint64_t qn = q1 - q0, tn = t1 - t0;
+    struct Cut { uint64_t q_end, t_end; };
+    std::vector<Cut> cuts;   // cuts[s] = bytes resident once copy_events[s] has fired
+    const uint32_t wq = src.Q / 16 + 2, wt = src.T / 16 + 2;   // packed words per sequence (host-packed mode)
+    if (src.packed) {   // the run must find these buffers at their final size: it would otherwise reallocate them after the upload
+        TRY(c->qpk.ensure(((uint64_t)n * wq + src.Q / 16 + 72) * 4));
+        TRY(c->tpk.ensure(((uint64_t)n * wt + src.T / 16 + 72) * 4));
+        TRY(c->flags.ensure(n + 8));
+        TRY(c->wave_flagged.ensure(64 * 4 + 16));
+        TRY(c->h_wave_cnt.ensure(64 * 4));
+    }
+    uint64_t pairs_up = 0;   // host-packed mode: pairs uploaded so far
+    auto upload_to = [&](uint64_t q_end, uint64_t t_end) -> int {
+        const uint64_t qa = cuts.empty() ? 0 : cuts.back().q_end, ta = cuts.empty() ? 0 : cuts.back().t_end;
+        q_end = std::min(std::max(q_end, qa), qn); t_end = std::min(std::max(t_end, ta), tn);
+        if (src.packed) {
+            // whole pairs only: the slice ends at the last pair that lies below both byte marks
+            uint64_t pe = std::min<uint64_t>(n, std::min(src.Q ? q_end / src.Q : n, src.T ? t_end / src.T : n));
+            pe = std::max(pe, pairs_up);
+            q_end = pe * src.Q; t_end = pe * src.T;
+            if (src.wait) TRY(src.wait(q_end, t_end));
+            if (pe > pairs_up) {
+                const uint64_t a = pairs_up, cnt = pe - a;
+                CU(cudaMemcpyAsync(c->qpk.as<uint32_t>() + a * wq, src.qpk + a * wq, cnt * wq * 4, cudaMemcpyHostToDevice, c->copy_stream));
+                CU(cudaMemcpyAsync(c->tpk.as<uint32_t>() + a * wt, src.tpk + a * wt, cnt * wt * 4, cudaMemcpyHostToDevice, c->copy_stream));
+                CU(cudaMemcpyAsync(c->flags.as<uint8_t>() + a, src.flags + a, cnt, cudaMemcpyHostToDevice, c->copy_stream));
+                c->h2d_bytes += cnt * (wq + wt) * 4 + cnt;
+                for (uint64_t i = a; i < pe; ++i) {   // rare: the raw bytes of a pair the 2-bit kernels cannot take
+                    if (!src.flags[i]) continue;
+                    if (src.Q) CU(cudaMemcpyAsync(c->d_q.as<char>() + i * src.Q, src.q_ptr[i], src.Q, cudaMemcpyHostToDevice, c->copy_stream));
+                    if (src.T) CU(cudaMemcpyAsync(c->d_t.as<char>() + i * src.T, src.t_ptr[i], src.T, cudaMemcpyHostToDevice, c->copy_stream));
+                    c->h2d_bytes += src.Q + src.T;
+                }
+                pairs_up = pe;
+            }
+        } else {
+            if (src.wait) TRY(src.wait(q_end, t_end));
+            if (q_end > qa) CU(cudaMemcpyAsync(c->d_q.as<char>() + qa, src.q + q0 + qa, q_end - qa, cudaMemcpyHostToDevice, c->copy_stream));
+            if (t_end > ta) CU(cudaMemcpyAsync(c->d_t.as<char>() + ta, src.t + t0 + ta, t_end - ta, cudaMemcpyHostToDevice, c->copy_stream));
+        }
+        if (c->copy_events.size() <= cuts.size()) {
+            cudaEvent_t e; CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            c->copy_events.push_back(e);
+        }
+        CU(cudaEventRecord(c->copy_events[cuts.size()], c->copy_stream));
+        cuts.push_back(Cut{q_end, t_end});
+        return B200_OK;
+    };
+    tl_mark(c, c->copy_stream, "start");
+    for (int s = 0; s < kHead; ++s) {
+        TRY(upload_to(qn * (s + 1) / kSlices, tn * (s + 1) / kSlices));
+        if (s == 0 || s == kHead - 1) tl_mark(c, c->copy_stream, "h2d" + std::to_string(s));
+    }
+    if (!src.packed) c->h2d_bytes += qn + tn;
+    tr.mark("enqueue-h2d");
+    if (!plan_ready) TRY(host_plan_build(c, n, q_off, t_off, type, match, mismatch, gap, want_cigar));
+    b200_align_plan* plan = c->host_plan;
     tr.mark("plan");
+    if (src.packed) {
+        // the producer packed for the uniform thread-per-pair plan; anything else cannot use what it made
+        if (!plan->uniform || plan->uQ != src.Q || plan->uT != src.T || plan->waves.size() > 64)
+            return fail(B200_E_ARG, "internal: host-packed upload without a uniform plan");
+        plan->host_packed = true;
+    }
     // second half of the upload, and which slice each wave has to wait for
     plan->wave_events.assign(plan->waves.size(), nullptr);
     if (plan->uniform) {
@@ -110,6 +164,23 @@ static int align_batch_host(b200_ctx* c, size_t n, const HostSource& src, const 
             if (qe > cuts.back().q_end || te > cuts.back().t_end) {
                 TRY(upload_to(qe, te));
                 tl_mark(c, c->copy_stream, "h2dw" + std::to_string(k));
+            }
+            if (src.packed) {
+                // how many of the wave's pairs the host flagged: the run reads this count back instead of one made by
+                // pack_kernel; it travels behind the wave's slice, and the wave waits for an event of its own after it
+                if (src.wait) TRY(src.wait(qe, te));
+                uint32_t cnt = 0;
+                for (uint64_t i = plan->waves[k].first; i < last_pair; ++i) cnt += src.flags[i] != 0;
+                c->h_wave_cnt.as<uint32_t>()[k] = cnt;
+                CU(cudaMemcpyAsync(c->wave_flagged.as<uint32_t>() + k, c->h_wave_cnt.as<uint32_t>() + k, 4, cudaMemcpyHostToDevice, c->copy_stream));
+                if (c->copy_events.size() <= cuts.size()) {
+                    cudaEvent_t e; CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                    c->copy_events.push_back(e);
+                }
+                CU(cudaEventRecord(c->copy_events[cuts.size()], c->copy_stream));
+                plan->wave_events[k] = c->copy_events[cuts.size()];
+                cuts.push_back(cuts.back());
+                continue;
             }
             size_t need = 0;
             while (need + 1 < cuts.size() && (cuts[need].q_end < qe || cuts[need].t_end < te)) ++need;
@@ -229,6 +300,12 @@ struct Gatherer {
     std::atomic<size_t> next{0};
     std::atomic<int> bad{0};
     size_t prefix = 0;   // blocks [0, prefix) are known to be done (consumer side only)
+    // packed mode (uniform lengths Q / T): instead of copying, every sequence is packed to 2 bits (host_pack.hpp) into
+    // its wq / wt words, and a pair's flag byte says whether both sequences were pure ACGT
+    bool packed = false;
+    uint32_t len_q = 0, len_t = 0, wq = 0, wt = 0;
+    uint32_t* pk[2] = {nullptr, nullptr};
+    uint8_t* flags = nullptr;
 
     void offsets(unsigned T) {   // parallel prefix sum of the lengths
         std::vector<uint64_t> part(2 * (size_t)T, 0);
@@ -263,6 +340,14 @@ struct Gatherer {
                     const size_t b = next.fetch_add(1, std::memory_order_relaxed);
                     if (b >= n_blocks) return;
                     const size_t a = b * kBlock, e = std::min(n, a + kBlock);
+                    if (packed) {
+                        for (size_t i = a; i < e; ++i) {
+                            if ((len_q && !src[0][i]) || (len_t && !src[1][i])) { bad.store(1, std::memory_order_relaxed); flags[i] = 0; continue; }
+                            const uint8_t fq = host_pack_sequence(src[0][i], len_q, pk[0] + i * wq);
+                            const uint8_t ft = host_pack_sequence(src[1][i], len_t, pk[1] + i * wt);
+                            flags[i] = fq | ft;
+                        }
+                    } else
                     for (int w = 0; w < 2; ++w)
                         for (size_t i = a; i < e;) {
                             const uint32_t l0 = len[w][i];
@@ -316,14 +401,35 @@ extern "C" int b200_align_batch(int device, size_t n, const char* const* query, 
     PhaseTrace ptr_trace;
     g.offsets(T);
     ptr_trace.mark("ptr:offsets");
-    TRY(c->h_q.ensure(g.off[0][n] + 1));
-    TRY(c->h_t.ensure(g.off[1][n] + 1));
-    g.dst[0] = c->h_q.as<char>(); g.dst[1] = c->h_t.as<char>();
-    g.start(T);
-    HostSource src;
-    src.q = g.dst[0]; src.t = g.dst[1];
     const uint64_t* qo = g.off[0];
     const uint64_t* to = g.off[1];
+    // Option `host_pack`: the plan comes first -- it says whether the batch is a uniform one for the thread-per-pair
+    // kernel -- and then the gather pass packs to 2 bits instead of copying (the upload shrinks from Q + T bytes per pair
+    // to 4 (Q/16 + T/16 + 4)). Off by default: on the 16-thread host of the B200 boxes both passes run at the same
+    // ~35 GB/s of sequence bytes (12.8 ms against 12.3 ms per config-2 step), i.e. the gather is bound by the host's
+    // cores, not by what it writes or by the upload that follows; a host with more cores per GPU is where it would pay.
+    bool plan_ready = false;
+    if (c->host_pack && n >= 4 * Gatherer::kBlock) {
+        TRY(host_plan_build(c, n, qo, to, type, match, mismatch, gap, cigar_off != nullptr));
+        plan_ready = true;
+    }
+    const b200_align_plan* plan = c->host_plan;
+    HostSource src;
+    if (plan_ready && plan->uniform && plan->waves.size() <= 64) {
+        g.packed = true; g.len_q = plan->uQ; g.len_t = plan->uT; g.wq = g.len_q / 16 + 2; g.wt = g.len_t / 16 + 2;
+        TRY(c->h_qpk.ensure((uint64_t)n * g.wq * 4 + 64));
+        TRY(c->h_tpk.ensure((uint64_t)n * g.wt * 4 + 64));
+        TRY(c->h_flags.ensure(n + 64));
+        g.pk[0] = c->h_qpk.as<uint32_t>(); g.pk[1] = c->h_tpk.as<uint32_t>(); g.flags = c->h_flags.as<uint8_t>();
+        src.packed = true; src.Q = g.len_q; src.T = g.len_t; src.qpk = g.pk[0]; src.tpk = g.pk[1]; src.flags = g.flags;
+        src.q_ptr = query; src.t_ptr = target;
+    } else {
+        TRY(c->h_q.ensure(g.off[0][n] + 1));
+        TRY(c->h_t.ensure(g.off[1][n] + 1));
+        g.dst[0] = c->h_q.as<char>(); g.dst[1] = c->h_t.as<char>();
+        src.q = g.dst[0]; src.t = g.dst[1];
+    }
+    g.start(T);
     src.wait = [&g, qo, to, n](uint64_t q_end, uint64_t t_end) -> int {
         // the first pair whose bytes start at or beyond both ends: everything below it is needed
         const size_t pq = (size_t)(std::lower_bound(qo, qo + n + 1, q_end) - qo);
@@ -348,7 +454,7 @@ extern "C" int b200_align_batch(int device, size_t n, const char* const* query, 
         }
     }
     ptr_trace.mark("ptr:start-gather");
-    int rc = align_batch_host(c, n, src, qo, to, type, match, mismatch, gap, s_score, s_tb, s_cig, s_off, s_cap);
+    int rc = align_batch_host(c, n, src, qo, to, type, match, mismatch, gap, s_score, s_tb, s_cig, s_off, s_cap, plan_ready);
     g.join();
     ptr_trace.mark("ptr:align");
     if (rc != B200_OK) {

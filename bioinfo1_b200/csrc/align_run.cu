@@ -368,7 +368,7 @@ static int plan_run_body(b200_align_plan* p, const char* d_q_buf, const char* d_
     if (n_packed) {
         TRY(c->qpk.ensure((p->qpk_words + p->max_Q / 16 + 72) * 4));
         TRY(c->tpk.ensure((p->tpk_words + p->max_T / 16 + 72) * 4));
-        CU(cudaMemsetAsync(c->flags.p, 0, n + 4, st));
+        if (!p->host_packed) CU(cudaMemsetAsync(c->flags.p, 0, n + 4, st));   // (host-packed runs upload the flags)
     }
     if (p->patched) {   // a previous run (other content) left fallback descriptors behind
         materialize_uniform_host(p);
@@ -385,7 +385,7 @@ static int plan_run_body(b200_align_plan* p, const char* d_q_buf, const char* d_
     TRY(c->h_small.ensure((n_waves + 8) * 8));
     uint32_t* h_flagged = c->h_small.as<uint32_t>() + 4;   // [n_waves], after the 8-byte slot of the CIGAR total
     std::memset(c->h_small.p, 0, (n_waves + 8) * 8);
-    CU(cudaMemsetAsync(c->wave_flagged.p, 0, n_waves * 4 + 16, st));
+    if (!p->host_packed) CU(cudaMemsetAsync(c->wave_flagged.p, 0, n_waves * 4 + 16, st));   // (... and the per-wave counts)
     if (overlap) {   // the second stream starts after everything already queued on the caller's stream
         CU(cudaEventRecord(c->fork_event, st));
         CU(cudaStreamWaitEvent(c->aux_stream, c->fork_event, 0));
@@ -472,7 +472,9 @@ static int plan_run_body(b200_align_plan* p, const char* d_q_buf, const char* d_
         cudaStream_t pst = pack_ahead ? c->pack_stream : wst;
         if (k < p->wave_events.size() && p->wave_events[k]) CU(cudaStreamWaitEvent(pst, p->wave_events[k], 0));
         prof_begin(c, pst, 3);
-        if (wv.klass != kClassGeneric) {
+        if (p->host_packed) {
+            // the wave's 2-bit words and flags were packed by the host's gather pass and came with its upload slice
+        } else if (wv.klass != kClassGeneric) {
             const uint32_t wpp = std::max(1u, div_up(wv.klass == kClassLong ? std::max(p->max_Q, p->max_T)
                                                                            : std::max(p->max_Q_short, p->max_T_short), 16));
             dim3 grid((unsigned)div_up64((uint64_t)wv.count * wpp, 128), 2);   // (128-thread CTAs: they fit one free fill slot)
@@ -483,7 +485,7 @@ static int plan_run_body(b200_align_plan* p, const char* d_q_buf, const char* d_
                 rb.dq, rb.dt, p->d_pairs.as<PairDesc>(), work, wv.count, c->flags.as<uint8_t>());
         }
         prof_end(c, pst);
-        c->kernel_launches++;
+        if (!p->host_packed) c->kernel_launches++;
         tl_mark(c, pst, "pack" + std::to_string(k));
         if (streaming) {
             publish_watermark_kernel<<<1, 1, 0, pst>>>(d_stream, wv.first + wv.count);

@@ -102,7 +102,7 @@ extern "C" int b200_ctx_create(int device, b200_ctx** out) {
     align_kernels_configure();
     // tuning runs: defaults of a few options from the environment (B200_SUBST_LDS, B200_TAPER_TAIL, B200_CONCURRENT_WALK)
     for (auto kv : {std::pair<const char*, int64_t*>{"B200_SUBST_LDS", &c->subst_lds}, {"B200_TAPER_TAIL", &c->taper_tail},
-                    {"B200_CONCURRENT_WALK", &c->concurrent_walk}, {"B200_STREAM_FILL", &c->stream_fill}, {"B200_FILL_PIPE", &c->fill_pipe}})
+                    {"B200_CONCURRENT_WALK", &c->concurrent_walk}, {"B200_STREAM_FILL", &c->stream_fill}, {"B200_HOST_PACK", &c->host_pack}, {"B200_FILL_PIPE", &c->fill_pipe}})
         if (const char* e = std::getenv(kv.first)) *kv.second = std::atoll(e);
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess)
@@ -153,7 +153,9 @@ extern "C" void b200_ctx_destroy(b200_ctx* c) {
                       &c->cigar_len, &c->scan_tmp, &c->flags, &c->total, &c->wave_flagged, &c->d_q, &c->d_t, &c->d_score, &c->d_tb,
                       &c->d_cigar, &c->d_cigar_off, &c->d_seq, &c->d_hash, &c->d_pos, &c->d_flag})
         b->release();
-    for (HostBuf* b : {&c->h_q, &c->h_t, &c->h_off, &c->h_small, &c->h_out_small, &c->h_out_cigar}) b->release();
+    for (HostBuf* b : {&c->h_q, &c->h_t, &c->h_off, &c->h_small, &c->h_out_small, &c->h_out_cigar, &c->h_qpk, &c->h_tpk,
+                       &c->h_flags, &c->h_wave_cnt})
+        b->release();
     delete c;
 }
 
@@ -169,6 +171,7 @@ extern "C" int b200_ctx_set_option(b200_ctx* c, const char* key, int64_t value) 
     else if (k == "concurrent_walk") c->concurrent_walk = value;
     else if (k == "chunk_pairs") c->chunk_pairs = value;
     else if (k == "taper_tail") c->taper_tail = value;
+    else if (k == "host_pack") c->host_pack = value;
     else if (k == "stream_fill") c->stream_fill = value;
     else if (k == "profile") c->profile = value;
     else if (k == "reset_counters") {

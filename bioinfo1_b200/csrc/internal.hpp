@@ -125,6 +125,8 @@ struct b200_ctx {
     DevBuf d_q, d_t, d_score, d_tb, d_cigar, d_cigar_off, d_seq, d_hash, d_pos, d_flag;
     HostBuf h_q, h_t, h_off;
     HostBuf h_out_small, h_out_cigar;       // pointer-array entry point: pinned landing zone of the results
+    HostBuf h_qpk, h_tpk, h_flags, h_wave_cnt;   // ... and of the 2-bit words / flags its gather pass packs on the host
+    int64_t host_pack = 0;                  // 1 = the pointer-array gather of a uniform short batch packs to 2 bits on the host
     // options
     int64_t dir_budget_bytes = 48ll << 30;
     int64_t force_generic = 0;
@@ -210,6 +212,7 @@ struct b200_align_plan {
     std::vector<PairDesc> h_pairs;     // kept for the non-ACGT fallback (content is only known at run time)
     std::vector<uint32_t> h_order;
     bool patched = false;              // d_pairs currently holds run-specific fallback descriptors
+    bool host_packed = false;          // the 2-bit copies, flags and per-wave flag counts of this run come from the host
     std::vector<cudaEvent_t> wave_events;   // optional, per wave: "this wave's sequence bytes are resident" (host pipeline)
     bool uniform = false;              // every pair has the same (Q,T): descriptors were built on the device
     uint32_t uQ = 0, uT = 0;
@@ -225,6 +228,7 @@ struct b200_align_plan {
         n = 0; cells = cigar_bound = run_slots = q_bytes = t_bytes = qpk_words = tpk_words = 0;
         max_T = max_Q = max_T_short = max_Q_short = 0; n_short = n_long = 0;
         waves.clear(); h_pairs.clear(); h_order.clear(); patched = false; uniform = false; wave_events.clear();
+        host_packed = false;
     }
 };
 

@@ -90,3 +90,12 @@ def test_cli_help_version_and_usage_errors_without_a_device():
     assert r.returncode == 1 and "two input files" in r.stderr.lower()
     r = subprocess.run([exe, "-a", "bogus", "a", "b"], capture_output=True, text=True)
     assert r.returncode == 1 and "Expected Alignment type" in r.stderr
+
+
+def test_host_side_2bit_packer_matches_the_device_layout():
+    """bioinfo1_b200/csrc/host_pack.hpp (what the pointer-array gather uses) against a byte-at-a-time restatement of
+    pack_kernel's layout and flag rules: 200 000 random sequences, with and without foreign bytes (CPU only)."""
+    import subprocess
+    exe = os.path.join(ROOT, "tests", "cpp", "host_pack_test")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "host_pack ok" in r.stdout, r.stdout + r.stderr

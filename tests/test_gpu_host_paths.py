@@ -86,8 +86,41 @@ def test_host_pipeline_other_lengths_and_types(ctx):
         _equal(got, exp, f"length {length} type {typ}")
 
 
+def _in_fresh_thread(env, fn):
+    """The pointer-array entry point uses a per-thread default context whose option defaults come from the environment
+    when it is created: a new thread is a new context."""
+    import threading
+    out = {}
+    old = {k: os.environ.get(k) for k in env}
+
+    def work():
+        try:
+            fn()
+        except BaseException as e:   # surfaced in the caller
+            out["err"] = e
+    os.environ.update(env)
+    try:
+        t = threading.Thread(target=work)
+        t.start()
+        t.join()
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    if "err" in out:
+        raise out["err"]
+
+
+@pytest.mark.parametrize("host_pack", ["0", "1"])
 @pytest.mark.parametrize("n", [1, 300, 9000, 150_000])
-def test_pointer_array_entry_point_threaded_gather(n):
+def test_pointer_array_entry_point_threaded_gather(n, host_pack):
+    """host_pack = 1: the gather pass packs uniform batches to 2 bits on the host (host_pack.hpp) instead of copying."""
+    _in_fresh_thread({"B200_HOST_PACK": host_pack}, lambda: _pointer_array_checks(n))
+
+
+def _pointer_array_checks(n):
     from bioinfo1_b200 import capi
     L = capi.lib()
     qb, qo, tb, to = synth.short_pairs(78, n, 150)
@@ -103,6 +136,27 @@ def test_pointer_array_entry_point_threaded_gather(n):
         capi.check(L.b200_align_batch(0, n, qptr.ctypes.data, qlen.ctypes.data, tptr.ctypes.data, tlen.ctypes.data, 0, 1, -1, -1,
                                       score.ctypes.data, tbeg.ctypes.data, cig.ctypes.data, coff.ctypes.data, cap))
         _equal((score, tbeg, cig, coff), exp, f"pointer arrays n={n}")
+    if n >= 9000:
+        # foreign bytes inside a uniform batch: the gather pass (which packs such batches to 2 bits on the host) flags the
+        # pairs, uploads their raw bytes and the repair pass aligns them with the byte-compare kernel
+        qb2, tb2 = qb.copy(), tb.copy()
+        rng = np.random.default_rng(9)
+        for i in rng.integers(0, n, size=60):
+            qb2[int(i) * 150 + int(rng.integers(0, 150))] = ord("N")
+        for i in rng.integers(0, n, size=40):
+            tb2[int(i) * 150 + int(rng.integers(0, 150))] = ord("-")
+        tb2[(n - 1) * 150 + 149] = ord("a")
+        qptr2 = (qb2.ctypes.data + qo[:n]).astype(np.uint64)
+        tptr2 = (tb2.ctypes.data + to[:n]).astype(np.uint64)
+        for typ in (0, 2):
+            exp2 = CHK.align_batch_full(qb2, qo, tb2, to, typ, 1, -1, -1, threads=THREADS)
+            capi.check(L.b200_align_batch(0, n, qptr2.ctypes.data, qlen.ctypes.data, tptr2.ctypes.data, tlen.ctypes.data, typ, 1, -1, -1,
+                                          score.ctypes.data, tbeg.ctypes.data, cig.ctypes.data, coff.ctypes.data, cap))
+            _equal((score, tbeg, cig, coff), exp2, f"pointer arrays with foreign bytes n={n} type={typ}")
+        # score only
+        capi.check(L.b200_align_batch(0, n, qptr2.ctypes.data, qlen.ctypes.data, tptr2.ctypes.data, tlen.ctypes.data, 2, 1, -1, -1,
+                                      score.ctypes.data, tbeg.ctypes.data, None, None, 0))
+        assert np.array_equal(score, exp2[0]) and np.array_equal(tbeg, exp2[1])
     # ragged lengths (not a uniform batch), some empty sequences, pointers in scattered order
     rng = np.random.default_rng(3)
     m = min(n, 20_000)
