@@ -422,26 +422,43 @@ int main(int argc, char** argv) {
     // only the first sequence is the reference (:415)
     const char* ref = refs.buf.data();
     const uint64_t ref_len = refs.len(0);
-    if (b200_device_count() <= 0) { std::cerr << "Error: no CUDA device visible (this mapper has no CPU fallback)\n"; return 1; }
-    o.gpus = std::min(o.gpus, b200_device_count());
-
-    // The devices start up (contexts, index) while the fragments file is parsed. A second context per device (its
-    // start-up runs next to the index build) only when the input is large enough to keep two batches in flight.
+    // Everything that touches CUDA happens on other threads from here on: initialising the driver on a box with eight
+    // GPUs takes seconds by itself (measured: 4-5 s of the first 8-GPU run's 10 s), and the input files can be read and
+    // parsed meanwhile. The starter thread counts the devices, clamps --gpus and starts one thread per device; the devices
+    // create their contexts and indexes, then wait for the batches. A second context per device (its start-up runs
+    // next to the index build) only when the device's share of the input is several batches.
     // (B200_MAPPER_BATCH_READS / B200_MAPPER_WORKERS: test knobs.)
     Job J;
     J.o = &o; J.reads = &reads; J.ref_name = refs.names[0]; J.ref = ref; J.ref_len = ref_len; J.trace = trace;
     struct stat st2;
     if (stat(o.file2.c_str(), &st2) != 0 || !S_ISREG(st2.st_mode)) { std::cerr << "Given file is not in FASTA or FASTQ format! \n"; return 1; }
-    const size_t f2_bytes = (size_t)st2.st_size;   // (the file itself is read after the devices have been started)
+    const size_t f2_bytes = (size_t)st2.st_size;
     const char* env_batch = std::getenv("B200_MAPPER_BATCH_READS");
     const char* env_workers = std::getenv("B200_MAPPER_WORKERS");
-    const bool small = f2_bytes < ((size_t)192 << 20) && o.gpus == 1;
-    // (a second context per device only pays when the device gets several batches: ~400 MB of input each)
-    const int workers_per_device = env_workers && std::atoi(env_workers) > 0 ? std::atoi(env_workers)
-                                   : (f2_bytes / (size_t)o.gpus >= ((size_t)384 << 20) ? 2 : 1);
+    const int gpus_asked = o.gpus;
+    int workers_per_device = 1;
+    bool no_device = false;
+    double t_cuda_ready = 0;
     std::vector<std::thread> devs;
-    for (int g = 0; g < o.gpus; ++g) devs.emplace_back(device_main, std::ref(J), g, workers_per_device);
+    // The driver initialises every VISIBLE device, used or not (about 0.6 s per B200 on the 8-GPU boxes): unless the user
+    // has set it, the process only sees the first --gpus devices.
+    if (!std::getenv("CUDA_VISIBLE_DEVICES")) {
+        std::string vis;
+        for (int g = 0; g < gpus_asked; ++g) vis += (g ? "," : "") + std::to_string(g);
+        setenv("CUDA_VISIBLE_DEVICES", vis.c_str(), 0);
+    }
+    std::thread starter([&] {
+        const int count = b200_device_count();
+        t_cuda_ready = now_s();
+        if (count <= 0) { no_device = true; return; }
+        o.gpus = std::min(gpus_asked, count);
+        // (a second context per device only pays when the device gets several batches: ~400 MB of input each)
+        workers_per_device = env_workers && std::atoi(env_workers) > 0 ? std::atoi(env_workers)
+                             : (f2_bytes / (size_t)o.gpus >= ((size_t)384 << 20) ? 2 : 1);
+        for (int g = 0; g < o.gpus; ++g) devs.emplace_back(device_main, std::ref(J), g, workers_per_device);
+    });
     auto abort_devices = [&] {
+        if (starter.joinable()) starter.join();
         { std::lock_guard<std::mutex> g(J.mu); J.failed.store(1); }
         J.cv.notify_all();
         for (auto& t : devs) t.join();
@@ -456,6 +473,8 @@ int main(int argc, char** argv) {
     }
     J.fastq = fastq;
     const double t_parsed = now_s();
+    starter.join();   // (o.gpus is final from here on)
+    if (no_device) { std::cerr << "Error: no CUDA device visible (this mapper has no CPU fallback)\n"; std::fflush(stderr); std::_Exit(1); }
 
     if (o.stats) {
         std::cerr << "Basic statistic for reference genome\n------------------------------------\n";
@@ -468,6 +487,7 @@ int main(int argc, char** argv) {
     // Batches of bounded size: small inputs go through one context in large batches, larger ones in batches of 8 k
     // reads taken from one queue by every worker of every device.
     const size_t n_reads = reads.size();
+    const bool small = f2_bytes < ((size_t)192 << 20) && o.gpus == 1;
     const size_t max_reads = env_batch && std::atol(env_batch) > 0 ? (size_t)std::atol(env_batch) : (small ? 65536 : 8192);
     const uint64_t max_bases = small ? (256ull << 20) : (64ull << 20);
     for (size_t i = 0; i < n_reads;) {
@@ -511,8 +531,8 @@ int main(int argc, char** argv) {
     if (failed || J.failed.load()) { std::cerr << J.err << std::endl; std::fflush(stdout); std::_Exit(1); }
     const double t_done = now_s();
     if (trace)
-        std::fprintf(stderr, "[b200_mapper trace] read files %.3f s, index + map + write PAF %.3f s (%zu batches, %d devices x %d workers)\n",
-                     t_parsed - t_start, t_done - t_parsed, J.batches.size(), o.gpus, workers_per_device);
+        std::fprintf(stderr, "[b200_mapper trace] read + parse files %.3f s (CUDA driver up after %.3f s), index + map + write PAF %.3f s (%zu batches, %d devices x %d workers)\n",
+                     t_parsed - t_start, t_cuda_ready - t_start, t_done - t_parsed, J.batches.size(), o.gpus, workers_per_device);
     std::fflush(stdout);
     std::fflush(stderr);
     std::_Exit(0);   // skip the CUDA runtime's teardown of the (large) device allocations

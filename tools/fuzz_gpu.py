@@ -25,9 +25,23 @@ while time.time() < t_end:
     typ = pr.randrange(3)
     m = pr.randint(-3, 12); x = pr.randint(-12, 3); g = pr.randint(-12, 2)
     route = pr.choice(["default", "default", "long32", "generic"])
-    shape = pr.choice(["tiny", "mid", "long", "k1"])
+    shape = pr.choice(["tiny", "mid", "long", "k1", "k1u"])
+    # kernel variants and host-pipeline schedules (round 2): every combination must give the reference's bytes
+    opts = {"subst_lds": pr.choice([0, 1, 2, 3]), "fill_pipe": pr.choice([0, 1]), "stream_fill": pr.choice([0, 1]),
+            "taper_tail": pr.choice([0, 1, 2]), "chunk_pairs": pr.choice([0, 0, 1024, 2048])}
+    for k_, v_ in opts.items():
+        ctx.set_option(k_, v_)
     qs, ts = [], []
-    if shape == "k1":      # >= 8192 short pairs: the thread-per-pair kernel (if the scores allow)
+    if shape == "k1u":     # a UNIFORM batch: the device-built plan, several waves, pipelined downloads, streaming fill
+        n = 8192 + pr.randrange(9000)
+        Lq, Lt = pr.randint(1, 160), pr.randint(1, 160)
+        for k in range(n):
+            t = seqgen.random_dna(rng, Lt)
+            q = seqgen.fixed_len(rng, seqgen.mutate(rng, t, sub=0.06, ins=0.03, dele=0.03), Lq) if k % 3 else seqgen.random_dna(rng, Lq)
+            if pr.random() < 0.001:
+                q = q.copy(); q[pr.randrange(len(q))] = ord(pr.choice("N-a"))
+            qs.append(q.tobytes()); ts.append(t.tobytes())
+    elif shape == "k1":      # >= 8192 short pairs: the thread-per-pair kernel (if the scores allow)
         n = 8192 + pr.randrange(700)
         for k in range(n):
             T = int(rng.integers(0, 120)); t = seqgen.random_dna(rng, T)
@@ -53,12 +67,12 @@ while time.time() < t_end:
         got = ctx.align(qs, ts, typ, m, x, g, True)
     finally:
         ctx.set_option("long16", 1); ctx.set_option("force_generic", 0)
-    step = 1 if shape != "k1" else 37
+    step = 1 if shape not in ("k1", "k1u") else 37
     for k in range(0, len(qs), step):
         exp = O.align(qs[k], ts[k], typ, m, x, g, True)
         cases += 1
         if got[k] != exp:
-            print("MISMATCH", dict(seed=seed, round=rounds, typ=typ, scores=(m, x, g), route=route, shape=shape, k=k,
+            print("MISMATCH", dict(seed=seed, round=rounds, typ=typ, scores=(m, x, g), route=route, shape=shape, opts=opts, k=k,
                                    Q=len(qs[k]), T=len(ts[k]), got=got[k][:2], exp=exp[:2]))
             sys.exit(1)
 print(f"fuzz ok: {rounds} rounds, {cases} pairs checked against the oracle, seed {seed}")
