@@ -126,6 +126,26 @@ def test_cli_statistics_go_to_stderr_and_two_gpus_option_is_accepted():
     assert b"N50 length" in r.stderr and b"Number of distinct minimizers" in r.stderr
 
 
+def test_cli_output_does_not_depend_on_the_number_of_devices():
+    """--gpus 2 (two devices taking batches of 3 reads from one queue) prints the bytes --gpus 1 prints. Needs two GPUs."""
+    import subprocess
+    from bioinfo1_b200 import capi
+    if capi.lib().b200_device_count() < 2:
+        pytest.skip("one device visible")
+    exe = os.path.join(ROOT, "bioinfo1_b200", "b200_mapper")
+    outs = []
+    for g in ("1", "2"):
+        env = dict(os.environ, B200_MAPPER_BATCH_READS="3", B200_TRACE="1")
+        r = subprocess.run([exe, "-a", "semiGlobal", "-c", "-f", "0", "--gpus", g, "ref.fa", "reads.fq"], cwd=GOLD, capture_output=True, timeout=300, env=env)
+        assert r.returncode == 0, r.stderr.decode(errors="replace")
+        outs.append(r.stdout)
+        if g == "2":
+            assert b"gpu 1 worker 0: batch of" in r.stderr      # the second device really took batches
+    assert outs[0] == outs[1]
+    with open(os.path.join(GOLD, "synth_fq_semi_c.paf"), "rb") as f:
+        assert outs[0] == f.read()
+
+
 def test_cli_two_workers_over_small_batches_keep_the_output(monkeypatch):
     """Batches of 3 reads taken in turn by two contexts / host threads: same bytes, same (input) order."""
     import subprocess

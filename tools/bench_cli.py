@@ -1,6 +1,7 @@
 #!/usr/bin/env python3
 """Wall-clock of the b200_mapper executable on BASELINE config 4's data set (tests/synth.c: 4.6 Mbp reference, distinct
 ONT-like reads; files in, PAF on stdout): python tools/bench_cli.py [reads] [gpus]"""
+import hashlib
 import json
 import os
 import subprocess
@@ -38,4 +39,5 @@ with tempfile.TemporaryDirectory(dir=base) as td:
         paf = open(os.path.join(td, "out.paf"), "rb").read()
         print(json.dumps({"argv": argv, "gpus": gpus, "reads": n_reads, "bases": nb, "rc": r.returncode, "wall_s": t,
                           "reads_per_s": n_reads / t, "paf_lines": paf.count(b"\n"), "paf_bytes": len(paf),
+                          "paf_md5": hashlib.md5(paf).hexdigest(),
                           "trace": [l for l in r.stderr.decode(errors="replace").splitlines() if "b200_mapper trace" in l][-6:]}), flush=True)

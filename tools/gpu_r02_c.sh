@@ -1,4 +1,5 @@
 #!/bin/bash
+# (historical: B200_LONG_PIPE selected the software-pipelined K3 variant, removed after this measurement -- profiles/variants_r02.json)
 # Round-2 GPU pass C (one GPU): streaming fill (gate kernels), pipelined K3, per-warp minimizer staging.
 set -u
 out=gpurun_out

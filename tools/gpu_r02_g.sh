@@ -1,4 +1,5 @@
 #!/bin/bash
+# (historical: B200_SHORT_SEL_SMEM / B200_LONG_SEL_SMEM selected the selectors-in-shared-memory variants, removed after this measurement -- profiles/variants_r02.json)
 # Round-2 GPU pass G (one GPU): per-row selectors in shared memory (more warps per scheduler) for K1 and K3.
 set -u
 out=gpurun_out
