@@ -100,7 +100,7 @@ extern "C" int b200_ctx_create(int device, b200_ctx** out) {
         }
     }
     align_kernels_configure();
-    // tuning runs: defaults of a few options from the environment (B200_SUBST_LDS, B200_TAPER_TAIL, B200_CONCURRENT_WALK)
+    // tuning runs: defaults of six options from the environment (listed in include/b200map.h)
     for (auto kv : {std::pair<const char*, int64_t*>{"B200_SUBST_LDS", &c->subst_lds}, {"B200_TAPER_TAIL", &c->taper_tail},
                     {"B200_CONCURRENT_WALK", &c->concurrent_walk}, {"B200_STREAM_FILL", &c->stream_fill}, {"B200_HOST_PACK", &c->host_pack}, {"B200_FILL_PIPE", &c->fill_pipe}})
         if (const char* e = std::getenv(kv.first)) *kv.second = std::atoll(e);

@@ -60,11 +60,20 @@ void b200_ctx_destroy(b200_ctx* ctx);
 /* Tunables (all optional): "dir_budget_bytes" (HBM given to 2-bit direction storage; a batch that needs more
  * is cut into waves of half of it, two in flight), "force_generic" (1 = route every pair through the int32
  * byte-compare kernel), "long16" (0 = long pairs stay on the int32 stripe kernel), "overlap_waves" (0 = waves
- * run one after the other on the caller's stream), "chunk_pairs" (host-API pipeline chunk), "profile" (1 =
- * bracket kernels with events: the "*_ns" counters), "reset_counters". Returns B200_E_ARG for an unknown key. */
+ * run one after the other on the caller's stream), "concurrent_walk" (0 = long pairs are walked after their wave's
+ * fill instead of next to it), "chunk_pairs" (host-API pipeline chunk), "taper_tail" (host pipeline of uniform short
+ * batches: 1 = shrinking tail of waves, 2 = last wave cut in two), "stream_fill" (1 = one persistent fill launch fed
+ * by an upload watermark), "host_pack" (pointer-array entry point: 1 = the gather pass packs to 2 bits on the host),
+ * "subst_lds" (substitution term from a shared-memory table instead of PRMT: bit 0 short-pair kernel, bit 1 long-pair
+ * kernel), "fill_pipe" (0 = the short-pair kernel without software-pipelined columns), "profile" (1 = bracket kernels
+ * with events: the "*_ns" counters), "reset_counters". Defaults are what measured best; the
+ * environment variables B200_SUBST_LDS, B200_FILL_PIPE, B200_TAPER_TAIL, B200_STREAM_FILL, B200_HOST_PACK and
+ * B200_CONCURRENT_WALK preset those six for every context a process creates (tuning runs). Returns B200_E_ARG for an
+ * unknown key. */
 int b200_ctx_set_option(b200_ctx* ctx, const char* key, int64_t value);
 /* Counters since the context was created (or the last "reset_counters"): "kernel_launches", "h2d_bytes",
- * "d2h_bytes"; with "profile" on also "fill_ns", "walk_ns", "emit_ns", "other_ns" and "*_launches". */
+ * "d2h_bytes", "alu_slots_per_cell_pair_x10" (of the short-pair kernel variant in use); with "profile" on also
+ * "fill_ns", "walk_ns", "emit_ns", "other_ns" and "*_launches". */
 int64_t b200_ctx_get_counter(b200_ctx* ctx, const char* key);
 
 /* ------------------------------------------------------------------ alignment ---- */
